@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def relinf(a, b):
+    """max|a-b| / max|b|  (SURVEY section 7 hard part 4: the tolerance is infinity-norm relative)."""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    denom = max(float(np.max(np.abs(b))), 1e-30)
+    return float(np.max(np.abs(a - b))) / denom
+
+
+def outlier_fraction(a, b, tol=1e-5):
+    """Fraction of elements with |a-b| > tol * max|b|.
+
+    Used for post-Adam tables: the first Adam steps move an element by ~lr*sign(g), so an element whose
+    gradient cancels to rounding noise can legitimately land lr*2 away (hard part 4).
+    Parity is then stated as: all but a vanishing fraction of elements within tol, none further than the
+    Adam step bound."""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    denom = max(float(np.max(np.abs(b))), 1e-30)
+    return float(np.mean(np.abs(a - b) > tol * denom))
