@@ -1,0 +1,151 @@
+/*
+ * kge_b200.h -- C ABI of libkge_b200.so: the B200 (sm_100a) implementation of the RotatE toolkit's
+ * scoring / loss / backward / Adam / filtered-ranking hot path.
+ *
+ * The reference (kahrabian/KnowledgeGraphEmbedding) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the Python class codes/model.py:22 `KGEModel`.  Each entry point below is
+ * what a ctypes binding inside that class would call; the comment on each names the reference lines
+ * it replaces.  knowledgegraphembedding_b200/model.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with `host_`; the caller owns all memory;
+ *   - all tables are row-major fp32, indices are int64 exactly as the reference's LongTensors;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); nothing is allocated;
+ *   - return value 0 = success, negative = error; kge_last_error() gives the message (thread-local);
+ *   - no C++ exceptions cross the boundary, no torch types appear in any signature.
+ */
+#ifndef KGE_B200_H_
+#define KGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+
+/* model.py:151-157 `model_func` keys */
+enum { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_ROTATE = 3, KGE_PROTATE = 4 };
+/* model.py:83,104,126 `mode` strings */
+enum { KGE_SINGLE = 0, KGE_HEAD_BATCH = 1, KGE_TAIL_BATCH = 2 };
+/* model.py:270-279 loss kinds evaluated per positive row */
+enum { KGE_LOSS_NEG_ADVERSARIAL = 0, KGE_LOSS_NEG_UNIFORM = 1, KGE_LOSS_POSITIVE = 2 };
+
+enum {
+  KGE_OK = 0,
+  KGE_ERR_INVALID = -1,      /* bad argument / unsupported shape (maps to ValueError)            */
+  KGE_ERR_CUDA = -2,         /* CUDA runtime error                                               */
+  KGE_ERR_DEVICE = -3        /* not an sm_100 device                                             */
+};
+
+/* State of a KGEModel (model.py:23-70).  Plain struct, lives in host memory. */
+typedef struct kge_model {
+  int32_t model;             /* KGE_TRANSE ...                                                   */
+  int32_t device;            /* CUDA ordinal the pointers live on                                */
+  int64_t nentity;           /* model.py:27                                                      */
+  int64_t nrelation;         /* model.py:28                                                      */
+  int64_t hidden_dim;        /* model.py:29                                                      */
+  int64_t entity_dim;        /* model.py:42                                                      */
+  int64_t relation_dim;      /* model.py:43                                                      */
+  float gamma;               /* model.py:32  gamma.item()                                        */
+  float embedding_range;     /* model.py:37  embedding_range.item()                              */
+  const float *entity;       /* [nentity, entity_dim]     model.py:45                            */
+  const float *relation;     /* [nrelation, relation_dim] model.py:52                            */
+  const float *modulus;      /* [1,1] pRotatE only, else NULL (model.py:60)                      */
+} kge_model_t;
+
+int kge_abi_version(void);
+const char *kge_last_error(void);
+/* Refuses anything that is not compute capability 10.x; reports SM count and L2 size. */
+int kge_device_check(int device, int *sm_count, int64_t *l2_bytes);
+
+/* ---- scoring: KGEModel.forward (model.py:72-164) + the five score functions (model.py:166-249) ----
+ * mode SINGLE:      positive [B,3]; negative ignored; N must be 1; score [B,1]
+ * mode HEAD_BATCH:  negative [B,N] are candidate heads; mode TAIL_BATCH: candidate tails.
+ * err_flag (device int32, may be NULL) is set to 1 if an index is out of range (the row is then
+ * read as id 0 instead of faulting; torch raises an index error at the same place).             */
+int kge_score_forward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
+                      int64_t B, int64_t N, float *score, int32_t *err_flag, void *stream);
+
+/* autograd of the above (what loss.backward() at model.py:301 does through index_select):
+ * accumulates d(sum dscore*score)/dE etc. into dense fp32 tables with vector atomics.          */
+int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
+                       int64_t B, int64_t N, const float *dscore,
+                       float *grad_entity, float *grad_relation, float *grad_modulus,
+                       int32_t *err_flag, void *stream);
+
+/* ---- fused train pass: model.py:268-288 (scores, self-adversarial / uniform loss) + model.py:301 ----
+ * One launch per call: gather+score the N candidates of each positive row, softmax-weighted
+ * logsigmoid loss in the same CTA, closed-form backward with vector atomic scatter.
+ *   loss_kind NEG_*: candidates = negative[B,N] in `mode`;  POSITIVE: the positive triple itself
+ *   weight: subsampling_weight [B_total] or NULL (= --uni_weight);  weight_sum: device scalar sum(weight)
+ *   row_begin/row_count: this rank's slice of the batch (row_count == B_total on one GPU)
+ *   row_loss [B_total]: per-row  sum_j w_ij logsig(-s_ij)  (NEG) or logsig(s_i) (POSITIVE)
+ *   score_out: optional [row_count, N] copy of the scores (tests), may be NULL                   */
+int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                   const int64_t *positive, const int64_t *negative, const float *weight,
+                   const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
+                   int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
+                   float *grad_modulus, float *score_out, int32_t *err_flag, void *stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes): clears the gradient workspace at the top of a train step (the
+ * reference's optimizer.zero_grad() at model.py:259 drops the grads, autograd re-creates zero tables). */
+int kge_zero(void *ptr, int64_t bytes, void *stream);
+
+/* deterministic sum of weight[0..B) into out[0] (model.py:285 `subsampling_weight.sum()`)         */
+int kge_weight_sum(const float *weight, int64_t B, float *out, void *stream);
+
+/* model.py:281-288 + 296: out[0]=positive_sample_loss out[1]=negative_sample_loss out[2]=loss
+ * out[3]=regularization, from the per-row values; reg_partials (may be NULL) are the block sums of
+ * |x|^3 written by kge_adam_step.                                                                */
+int kge_loss_finalize(const float *pos_row, const float *neg_row, const float *weight,
+                      const float *weight_sum, int64_t B, float regularization,
+                      const double *reg_partials, int64_t n_reg_partials, float *out, void *stream);
+
+/* ---- optimizer: torch.optim.Adam.step() as called at model.py:303 (defaults of run.py:266-269) ----
+ * Dense fused update of up to 4 tensors in one launch.  l3 != 0 adds the gradient of the L3
+ * regulariser (model.py:290-296), 3*l3*x*|x|, to `grad` (written back) and accumulates sum|x|^3
+ * of the pre-update values into reg_partials[gridDim] (doubles).                                 */
+typedef struct kge_adam_tensor {
+  float *param; float *grad; float *exp_avg; float *exp_avg_sq;
+  int64_t numel;
+  int32_t step;              /* 1-based, after increment (state['step'])                         */
+  int32_t l3;                /* 1: this tensor takes part in the L3 regulariser                  */
+} kge_adam_tensor_t;
+
+int kge_adam_step(const kge_adam_tensor_t *host_tensors, int n_tensors, double lr, double beta1,
+                  double beta2, double eps, double l3_coefficient, double *reg_partials,
+                  int64_t n_reg_partials, void *stream);
+
+/* ---- filtered ranking: KGEModel.test_step (model.py:346-427) with dataloader.py:134-154's filter ----
+ * Step 1: per query the fixed side is folded into a query vector (model.py:214-223 etc.)
+ *   queries [Q,3] int64 triples, mode HEAD_BATCH/TAIL_BATCH; qvec [Q, entity_dim]
+ * pRotatE additionally needs the phase table  entity / (rho/pi)  [nentity, entity_dim] (model.py:236-238). */
+int kge_eval_query_vectors(const kge_model_t *m, int mode, const int64_t *queries, int64_t Q,
+                           float *qvec, int32_t *err_flag, void *stream);
+int kge_eval_phase_table(const kge_model_t *m, float *phase_table, void *stream);
+
+/* Step 2: score of the positive column, bit-identical to what step 3 computes for that column.   */
+int kge_eval_positive_scores(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries,
+                             int64_t Q, const float *phase_table, float *pos_score, void *stream);
+
+/* Step 3: fused all-entity scoring + filter + count.  For each query q and each entity j in
+ * [ent_begin, ent_end):   counts[q] += !filtered(q,j) && j != pos(q) &&
+ *                                       (s(q,j) > s_pos(q) || (s(q,j) == s_pos(q) && j < pos(q)))
+ * so that rank = 1 + sum over entity shards of counts (model.py:396-411 with a stable descending sort).
+ *   filter_bits [Q, ceil(nentity/32)] uint32 bitmap of the filtered columns (dataloader.py:138-144)
+ *   scores_out: optional [Q, nentity] dump of s(q,j) + filter_bias (tests), may be NULL           */
+int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries,
+                         int64_t Q, const float *phase_table, const float *pos_score,
+                         const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
+                         int32_t *counts, float *scores_out, void *stream);
+
+/* filter bitmap from a CSR of true entities per query (dataloader.py:138-144)                     */
+int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q,
+                         int64_t nentity, uint32_t *filter_bits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H_ */

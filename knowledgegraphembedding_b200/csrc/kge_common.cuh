@@ -1,0 +1,107 @@
+// kge_common.cuh -- shared device helpers and host-side error plumbing for libkge_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/kge_b200.h"
+#include "kge_math.h"
+
+namespace kge {
+
+// ---- error plumbing (no exceptions across the C ABI) --------------------------------------------
+void set_error(const char *fmt, ...);
+int check_model(const kge_model_t *m);
+int set_device(const kge_model_t *m);
+
+#define KGE_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      kge::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return KGE_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define KGE_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) {                          \
+      kge::set_error(__VA_ARGS__);          \
+      return KGE_ERR_INVALID;               \
+    }                                       \
+  } while (0)
+
+// ---- per-candidate inner operations --------------------------------------------------------------
+// Every (model, mode) folds the fixed side of the triple into a query vector q (model.py:166-249);
+// what is left per candidate row x is one of these element operations followed by a sum over k.
+enum Op {
+  OP_SUBABS = 0,   // TransE tail-batch/single: |(h+r) - t|      q = h + r
+  OP_ADDABS = 1,   // TransE head-batch:        |h + (r-t)|      q = r - t
+  OP_MUL = 2,      // DistMult:                 q * x            q = h*r or r*t
+  OP_CMUL = 3,     // ComplEx:                  q_re x_re + q_im x_im
+  OP_CDIST = 4,    // RotatE:                   |q - x| (complex modulus)
+  OP_SUBSIN = 5,   // pRotatE tail/single:      |sin((ph+pr) - pt)|
+  OP_ADDSIN = 6    // pRotatE head-batch:       |sin(ph + (pr-pt))|
+};
+
+__host__ __device__ constexpr bool op_is_complex(int op) { return op == OP_CMUL || op == OP_CDIST; }
+
+__host__ __device__ constexpr int op_of(int model, bool head_batch) {
+  return model == KGE_TRANSE ? (head_batch ? OP_ADDABS : OP_SUBABS)
+         : model == KGE_DISTMULT ? OP_MUL
+         : model == KGE_COMPLEX ? OP_CMUL
+         : model == KGE_ROTATE ? OP_CDIST
+                               : (head_batch ? OP_ADDSIN : OP_SUBSIN);
+}
+
+// rho/pi as the fp32 scalar torch divides by (`relation/(self.embedding_range.item()/pi)`)
+inline float phase_scale(const kge_model_t *m) {
+  const double pi = m->model == KGE_PROTATE ? 3.14159262358979323846 : 3.14159265358979323846;
+  return (float)((double)m->embedding_range / pi);
+}
+
+#if defined(__CUDACC__)
+// ---- warp / block reductions --------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- 128-bit global access ----------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {   // read-only, do not pollute L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_add4(float *p, float a, float b, float c, float d) {
+  // sm_90+ vector reduction: one 16-byte fire-and-forget atomic add per lane
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void red_add1(float *p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float log_sigmoid(float x) {     // F.logsigmoid: min(x,0) - log1p(exp(-|x|))
+  return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid(float x) {
+  float e = expf(-fabsf(x));
+  return x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+}
+#endif
+
+}  // namespace kge

@@ -1,0 +1,415 @@
+// kge_eval.cu -- filtered all-entity ranking without a sort (KGEModel.test_step, model.py:346-427).
+//
+// The reference scores every entity as a candidate, adds filter_bias, argsorts each row and looks up the
+// position of the positive.  The position only depends on how many unfiltered candidates beat the
+// positive, so this file computes exactly that count:
+//   query_vectors    fold the fixed side of every query into q[Q, D_e]           (model.py:214-223 ...)
+//   positive_scores  s_pos[q], bit-identical to the tile kernel's value for that column
+//   count_ranks      register-tiled [64 queries x 64 entities] CTA tiles streamed over k through a
+//                    double-buffered cp.async pipeline; epilogue compares with s_pos, applies the filter
+//                    bitmap and accumulates integer counts (bit-exact, order independent)
+// All score arithmetic here is written with un-contractable IEEE primitives and accumulated over k in
+// index order, so the CPU oracle (oracle/kge_oracle.c) reproduces every score bit-for-bit.
+#include "kge_rows.cuh"
+
+namespace kge {
+
+// ---- exact element ops -----------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float op_exact(float q0, float q1, float x0, float x1) {
+  if constexpr (OP == OP_SUBABS) return fabsf(fsub(q0, x0));                       // model.py:170,172
+  else if constexpr (OP == OP_ADDABS) return fabsf(fadd(x0, q0));                  // model.py:168,172
+  else if constexpr (OP == OP_MUL) return fmul(q0, x0);                            // model.py:177-179
+  else if constexpr (OP == OP_CMUL) return fadd(fmul(q0, x0), fmul(q1, x1));       // model.py:192,196
+  else if constexpr (OP == OP_CDIST) {                                             // model.py:217-226
+    const float a = fsub(q0, x0), b = fsub(q1, x1);
+    return fsqrt(ffma(b, b, fmul(a, a)));
+  } else if constexpr (OP == OP_SUBSIN) return fabsf(sin_rep(fsub(q0, x0)));       // model.py:243-246 (x = phase table)
+  else return fabsf(sin_rep(fadd(x0, q0)));                                        // model.py:241
+}
+
+template <int OP>
+__device__ __forceinline__ float finish_exact(float acc, float gamma, float modulus) {
+  if constexpr (OP == OP_MUL || OP == OP_CMUL) return acc;
+  else if constexpr (OP == OP_SUBSIN || OP == OP_ADDSIN) return fsub(gamma, fmul(acc, modulus));
+  else return fsub(gamma, acc);
+}
+
+// ---- query vectors ---------------------------------------------------------------------------------------
+template <int MODEL, bool HEAD>
+__global__ void query_vectors_kernel(const float *__restrict__ E, const float *__restrict__ R,
+                                     const int64_t *__restrict__ queries, int64_t Q, int64_t nentity,
+                                     int64_t nrelation, int d, int De, int Dr, float scale,
+                                     float *__restrict__ qvec, int32_t *err) {
+  for (int64_t qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    int64_t fid = queries[qi * 3 + (HEAD ? 2 : 0)], rid = queries[qi * 3 + 1];
+    const int64_t pid = queries[qi * 3 + (HEAD ? 0 : 2)];
+    if ((uint64_t)pid >= (uint64_t)nentity && threadIdx.x == 0 && err) *err = 1;
+    if ((uint64_t)fid >= (uint64_t)nentity || (uint64_t)rid >= (uint64_t)nrelation) {
+      if (threadIdx.x == 0 && err) *err = 1;
+      fid = 0; rid = 0;
+    }
+    const float *F = E + fid * De, *Rr = R + rid * Dr;
+    float *q = qvec + qi * De;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) build_q<MODEL, HEAD>(F, Rr, k, d, scale, q);
+  }
+}
+
+__global__ void phase_table_kernel(const float *__restrict__ E, int64_t n, float scale, float *__restrict__ P) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    P[i] = fdiv(E[i], scale);
+}
+
+// Accumulation order of every evaluation score (the "canonical order"): the k axis is cut
+// into blocks of KC consecutive indices; each block is summed in index order from 0.0f, and the block sums are
+// added in index order.  (Error grows with sqrt(KC) + sqrt(d/KC) instead of sqrt(d).)
+constexpr int TQ = 64, TJ = 64, KC = 32, ST = KC + 4, EVAL_THREADS = 256;
+
+// ---- positive scores ----------------------------------------------------------------------------------------
+template <int OP>
+__global__ void positive_scores_kernel(const float *__restrict__ qvec, const float *__restrict__ X,
+                                       const int64_t *__restrict__ queries, int pos_col, int64_t Q, int64_t nentity,
+                                       int d, int De, float gamma, const float *__restrict__ modulus,
+                                       float *__restrict__ pos_score) {
+  constexpr bool CPLX = op_is_complex(OP);
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= Q) return;
+  int64_t pid = queries[qi * 3 + pos_col];
+  if ((uint64_t)pid >= (uint64_t)nentity) pid = 0;
+  const float *q = qvec + qi * De, *x = X + pid * De;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < d; k0 += KC) {                     // same blocked order as count_ranks_kernel
+    float part = 0.f;
+    const int k1 = k0 + KC < d ? k0 + KC : d;
+    for (int k = k0; k < k1; ++k)
+      part = fadd(part, op_exact<OP>(q[k], CPLX ? q[d + k] : 0.f, x[k], CPLX ? x[d + k] : 0.f));
+    acc = fadd(acc, part);
+  }
+  pos_score[qi] = finish_exact<OP>(acc, gamma, modulus ? modulus[0] : 1.f);
+}
+
+// ---- tiled score + count ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;                       // src-size 0 => 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct EvalArgs {
+  const float *qvec;            // [Q, De]
+  const float *X;               // candidate table [nentity, De] (entity table, or phase table for pRotatE)
+  const int64_t *queries;       // [Q, 3]
+  const float *pos_score;       // [Q]
+  const uint32_t *filter_bits;  // [Q, words]
+  int32_t *counts;              // [Q]
+  float *scores_out;            // [Q, nentity] or null
+  const float *modulus;
+  int64_t Q, nentity, ent_begin, ent_end;
+  int d, De, pos_col, words;
+  float gamma;
+};
+
+// Stage one k-chunk of the query tile and the entity tile:  smem[row][half][ST]
+template <bool CPLX, bool ALIGNED>
+__device__ __forceinline__ void stage_tiles(const EvalArgs &a, float *sq, float *sx, int64_t q0, int64_t j0, int k0) {
+  constexpr int H = CPLX ? 2 : 1;
+  constexpr int VPR = KC / 4;                              // float4 per row-half per chunk
+  constexpr int TOTAL = (TQ + TJ) * H * VPR;
+  for (int idx = threadIdx.x; idx < TOTAL; idx += EVAL_THREADS) {
+    const int v = idx % VPR;
+    const int h = (idx / VPR) % H;
+    const int row = idx / (VPR * H);
+    const int k = k0 + v * 4;
+    const bool is_q = row < TQ;
+    int64_t g = is_q ? q0 + row : j0 + (row - TQ);
+    const int64_t lim = is_q ? a.Q : a.ent_end;
+    if (g >= lim) g = lim - 1;                             // clamp: the duplicate row's results are masked out
+    const float *src = (is_q ? a.qvec : a.X) + g * a.De + h * a.d + k;
+    float *dst = (is_q ? sq + row * (H * ST) : sx + (row - TQ) * (H * ST)) + h * ST + v * 4;
+    if constexpr (ALIGNED) {
+      cp_async16(dst, k < a.d ? src : (is_q ? a.qvec : a.X), k < a.d);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dst[e] = (k + e < a.d) ? src[e] : 0.f;
+    }
+  }
+}
+
+template <int OP, bool ALIGNED>
+__global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const EvalArgs a) {
+  constexpr bool CPLX = op_is_complex(OP);
+  constexpr int H = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TILE_Q = TQ * H * ST, TILE_X = TJ * H * ST;
+  constexpr int STAGE = TILE_Q + TILE_X;
+  __shared__ int cnt_sh[TQ];
+
+  const int tid = threadIdx.x;
+  const int tq = tid % 16, tj = tid / 16;
+  const int64_t j0 = a.ent_begin + (int64_t)blockIdx.x * TJ;
+  const int64_t q0 = (int64_t)blockIdx.y * TQ;
+  if (tid < TQ) cnt_sh[tid] = 0;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nchunks = (a.d + KC - 1) / KC;
+  stage_tiles<CPLX, ALIGNED>(a, smem, smem + TILE_Q, q0, j0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks)
+      stage_tiles<CPLX, ALIGNED>(a, smem + (cur ^ 1) * STAGE, smem + (cur ^ 1) * STAGE + TILE_Q, q0, j0, (c + 1) * KC);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float *Q_ = smem + cur * STAGE, *X_ = Q_ + TILE_Q;
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+#pragma unroll 2
+    for (int kk = 0; kk < KC; kk += 4) {
+      float4 qa[4], qb[4], xa[4], xb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qa[i] = *reinterpret_cast<const float4 *>(Q_ + (tq + 16 * i) * (H * ST) + kk);
+        xa[i] = *reinterpret_cast<const float4 *>(X_ + (tj + 16 * i) * (H * ST) + kk);
+        if constexpr (CPLX) {
+          qb[i] = *reinterpret_cast<const float4 *>(Q_ + (tq + 16 * i) * (H * ST) + ST + kk);
+          xb[i] = *reinterpret_cast<const float4 *>(X_ + (tj + 16 * i) * (H * ST) + ST + kk);
+        } else {
+          qb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xb[i] = qb[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // k ascending inside the group => index-order accumulation
+          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].x, qb[i].x, xa[j].x, xb[j].x));
+          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].y, qb[i].y, xa[j].y, xb[j].y));
+          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z));
+          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].w, qb[i].w, xa[j].w, xb[j].w));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fadd(acc[i][j], part[i][j]);
+    __syncthreads();
+  }
+
+  // ---- epilogue: compare with the positive, apply the filter, count -------------------------------------------
+  const float modulus = a.modulus ? a.modulus[0] : 1.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t qi = q0 + tq + 16 * i;
+    if (qi >= a.Q) continue;
+    const float sp = a.pos_score[qi];
+    int64_t pid = a.queries[qi * 3 + a.pos_col];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t ej = j0 + tj + 16 * j;
+      if (ej >= a.ent_end) continue;
+      float s = finish_exact<OP>(acc[i][j], a.gamma, modulus);
+      const bool filtered = ej != pid && ((a.filter_bits[qi * a.words + (ej >> 5)] >> (ej & 31)) & 1u);
+      if (filtered) s = fadd(sp, -1.0f);                   // candidate replaced by the positive, bias -1
+      else if (ej != pid) c += (s > sp) || (s == sp && ej < pid);
+      if (a.scores_out) a.scores_out[qi * a.nentity + ej] = s;
+    }
+    if (c) atomicAdd(&cnt_sh[tq + 16 * i], c);
+  }
+  __syncthreads();
+  if (tid < TQ && cnt_sh[tid] && q0 + tid < a.Q) atomicAdd(&a.counts[q0 + tid], cnt_sh[tid]);
+}
+
+__global__ void filter_bits_kernel(const int64_t *__restrict__ offsets, const int32_t *__restrict__ ents, int64_t Q,
+                                   int64_t nentity, int words, uint32_t *__restrict__ bits) {
+  for (int64_t qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    const int64_t b = offsets[qi], e = offsets[qi + 1];
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int32_t j = ents[i];
+      if (j >= 0 && j < nentity) atomicOr(&bits[qi * words + (j >> 5)], 1u << (j & 31));
+    }
+  }
+}
+
+template <int OP>
+static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
+  constexpr int H = op_is_complex(OP) ? 2 : 1;
+  const size_t smem = sizeof(float) * 2 * (TQ + TJ) * H * ST;
+  dim3 grid((unsigned)((a.ent_end - a.ent_begin + TJ - 1) / TJ), (unsigned)((a.Q + TQ - 1) / TQ));
+  if (aligned) {
+    auto k = count_ranks_kernel<OP, true>;
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, EVAL_THREADS, smem, st>>>(a);
+  } else {
+    auto k = count_ranks_kernel<OP, false>;
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, EVAL_THREADS, smem, st>>>(a);
+  }
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+static int eval_mode(int mode, bool &head) {
+  if (mode == KGE_HEAD_BATCH) head = true;
+  else if (mode == KGE_TAIL_BATCH) head = false;
+  else {
+    set_error("negative batch mode %d not supported", mode);     // dataloader.py:147
+    return KGE_ERR_INVALID;
+  }
+  return KGE_OK;
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_eval_query_vectors(const kge_model_t *m, int mode, const int64_t *queries, int64_t Q, float *qvec,
+                                      int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  bool head;
+  if ((rc = eval_mode(mode, head))) return rc;
+  KGE_REQUIRE(queries && qvec, "null pointer");
+  if (Q <= 0) return KGE_OK;
+  if ((rc = set_device(m))) return rc;
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  const int d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
+  const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
+  const float scale = phase_scale(m);
+  cudaStream_t st = (cudaStream_t)stream;
+#define KGE_QV(MODEL)                                                                                              \
+  case MODEL:                                                                                                      \
+    if (head)                                                                                                      \
+      query_vectors_kernel<MODEL, true><<<grid, 256, 0, st>>>(m->entity, m->relation, queries, Q, m->nentity,       \
+                                                              m->nrelation, d, (int)m->entity_dim,                 \
+                                                              (int)m->relation_dim, scale, qvec, err_flag);        \
+    else                                                                                                           \
+      query_vectors_kernel<MODEL, false><<<grid, 256, 0, st>>>(m->entity, m->relation, queries, Q, m->nentity,      \
+                                                               m->nrelation, d, (int)m->entity_dim,                \
+                                                               (int)m->relation_dim, scale, qvec, err_flag);       \
+    break;
+  switch (m->model) {
+    KGE_QV(KGE_TRANSE)
+    KGE_QV(KGE_DISTMULT)
+    KGE_QV(KGE_COMPLEX)
+    KGE_QV(KGE_ROTATE)
+    KGE_QV(KGE_PROTATE)
+  }
+#undef KGE_QV
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_phase_table(const kge_model_t *m, float *phase_table, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(phase_table, "null pointer");
+  if ((rc = set_device(m))) return rc;
+  phase_table_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(m->entity, m->nentity * m->entity_dim, phase_scale(m),
+                                                              phase_table);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+static int fill_eval_args(const kge_model_t *m, bool head, const float *qvec, const int64_t *queries, int64_t Q,
+                          const float *phase_table, EvalArgs &a) {
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  KGE_REQUIRE(m->model != KGE_PROTATE || phase_table, "pRotatE evaluation needs kge_eval_phase_table");
+  a.qvec = qvec;
+  a.X = m->model == KGE_PROTATE ? phase_table : m->entity;
+  a.queries = queries;
+  a.modulus = m->modulus;
+  a.Q = Q;
+  a.nentity = m->nentity;
+  a.d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
+  a.De = (int)m->entity_dim;
+  a.pos_col = head ? 0 : 2;
+  a.words = (int)((m->nentity + 31) / 32);
+  a.gamma = m->gamma;
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_positive_scores(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries,
+                                        int64_t Q, const float *phase_table, float *pos_score, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  bool head;
+  if ((rc = eval_mode(mode, head))) return rc;
+  KGE_REQUIRE(qvec && queries && pos_score, "null pointer");
+  if (Q <= 0) return KGE_OK;
+  if ((rc = set_device(m))) return rc;
+  EvalArgs a{};
+  if ((rc = fill_eval_args(m, head, qvec, queries, Q, phase_table, a))) return rc;
+  const int grid = (int)((Q + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define KGE_PS(OP)                                                                                              \
+  case OP:                                                                                                      \
+    positive_scores_kernel<OP><<<grid, 128, 0, st>>>(a.qvec, a.X, a.queries, a.pos_col, a.Q, a.nentity, a.d, a.De, \
+                                                     a.gamma, a.modulus, pos_score);                            \
+    break;
+  switch (op_of(m->model, head)) {
+    KGE_PS(OP_SUBABS) KGE_PS(OP_ADDABS) KGE_PS(OP_MUL) KGE_PS(OP_CMUL) KGE_PS(OP_CDIST) KGE_PS(OP_SUBSIN)
+    KGE_PS(OP_ADDSIN)
+  }
+#undef KGE_PS
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries, int64_t Q,
+                                    const float *phase_table, const float *pos_score, const uint32_t *filter_bits,
+                                    int64_t ent_begin, int64_t ent_end, int32_t *counts, float *scores_out,
+                                    void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  bool head;
+  if ((rc = eval_mode(mode, head))) return rc;
+  KGE_REQUIRE(qvec && queries && pos_score && filter_bits && counts, "null pointer");
+  KGE_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= m->nentity, "entity slice [%lld,%lld) outside [0,%lld)",
+              (long long)ent_begin, (long long)ent_end, (long long)m->nentity);
+  if (Q <= 0 || ent_begin == ent_end) return KGE_OK;
+  KGE_REQUIRE((Q + TQ - 1) / TQ <= 65535, "at most %d queries per call", 65535 * TQ);
+  if ((rc = set_device(m))) return rc;
+  EvalArgs a{};
+  if ((rc = fill_eval_args(m, head, qvec, queries, Q, phase_table, a))) return rc;
+  a.pos_score = pos_score; a.filter_bits = filter_bits; a.counts = counts; a.scores_out = scores_out;
+  a.ent_begin = ent_begin; a.ent_end = ent_end;
+  const bool aligned = (a.d % 4 == 0) && (a.De % 4 == 0) && ((((uintptr_t)a.qvec | (uintptr_t)a.X) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+#define KGE_CR(OP) \
+  case OP:         \
+    return launch_count<OP>(a, aligned, st);
+  switch (op_of(m->model, head)) {
+    KGE_CR(OP_SUBABS) KGE_CR(OP_ADDABS) KGE_CR(OP_MUL) KGE_CR(OP_CMUL) KGE_CR(OP_CDIST) KGE_CR(OP_SUBSIN)
+    KGE_CR(OP_ADDSIN)
+  }
+#undef KGE_CR
+  set_error("unreachable");
+  return KGE_ERR_INVALID;
+}
+
+extern "C" int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q, int64_t nentity,
+                                    uint32_t *filter_bits, void *stream) {
+  KGE_REQUIRE(csr_offsets && filter_bits && Q >= 0 && nentity > 0, "bad arguments");
+  if (Q == 0) return KGE_OK;
+  const int words = (int)((nentity + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(filter_bits, 0, sizeof(uint32_t) * (size_t)Q * words, st));
+  const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
+  filter_bits_kernel<<<grid, 128, 0, st>>>(csr_offsets, csr_entities, Q, nentity, words, filter_bits);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}

@@ -1,0 +1,397 @@
+// kge_train.cu -- the fused gather + score + loss + backward kernel ("row kernel") and its C ABI.
+//
+// One CTA owns one positive row b of the batch (model.py:261) and walks its N candidate rows twice:
+//   phase 0  fold the fixed side (h,r) or (r,t) into the query vector q in shared memory
+//   phase 1  one warp per candidate: 128-bit coalesced gather of the row, element op against q,
+//            warp-shuffle reduction over the hidden dimension -> score s[n] in shared memory
+//   phase 2  (train) self-adversarial softmax / logsigmoid loss of the row in the same CTA -> g[n]
+//   phase 3  one warp per candidate again (rows now come from L2): recompute the element terms, emit
+//            dL/dx with 16-byte vector atomics (red.global.add.v4.f32) into the dense gradient table,
+//            keep dL/dq in registers, summed over the warp's candidates
+//   phase 4  warps fold their dL/dq into shared memory in a fixed order (deterministic)
+//   phase 5  chain rule q -> fixed entity row and relation row, atomics into the gradient tables
+// The same kernel serves KGEModel.forward (phases 0-1), its autograd backward (0,3,4,5 with a given
+// dL/ds) and train_step (all phases); 'single' mode is tail-batch with the positive tail as the only
+// candidate (model.py:83-102 uses the non-head-batch association of every score function).
+#include "kge_rows.cuh"
+
+namespace kge {
+
+struct RowArgs {
+  const float *E, *R, *modulus;
+  const int64_t *positive;     // [B_total, 3]
+  const int64_t *cand;         // candidate (b, n) = cand[b * cand_stride + n]
+  int64_t cand_stride;
+  int64_t row_begin;
+  int row_count, N;
+  int64_t nentity, nrelation;
+  int d;                       // k-extent: hidden_dim for complex ops, entity_dim for real ops
+  int De, Dr;
+  float gamma, scale;
+  int do_loss, loss_kind;
+  float alpha;
+  const float *weight, *wsum;
+  float uniform_u;
+  float *row_loss;
+  float *score_out;
+  const float *dscore;
+  float *gE, *gR, *gM;
+  int32_t *err;
+};
+
+constexpr int kChunks = 8;     // units per lane per k-tile: 8 x float4 x (re,im) = 64 accumulator registers
+
+template <int V>
+__device__ __forceinline__ void load_global(float (&o)[V], const float *p) {
+  if constexpr (V == 4) {
+    float4 t = ldg_stream4(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+    o[0] = __ldg(p);
+  }
+}
+template <int V>
+__device__ __forceinline__ void load_shared(float (&o)[V], const float *p) {
+  if constexpr (V == 4) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+    o[0] = *p;
+  }
+}
+template <int V>
+__device__ __forceinline__ void red_global(float *p, const float (&v)[V]) {
+  if constexpr (V == 4) red_add4(p, v[0], v[1], v[2], v[3]);
+  else red_add1(p, v[0]);
+}
+
+__device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();                       // protect scratch from the previous use
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int w = 0; w < nw; ++w) r = is_max ? fmaxf(r, scratch[w]) : r + scratch[w];   // fixed order
+  return r;
+}
+
+template <int MODEL, bool HEAD, int V>
+__global__ void __launch_bounds__(512, 1) row_kernel(const RowArgs a) {
+  constexpr int OP = op_of(MODEL, HEAD);
+  constexpr bool CPLX = op_is_complex(OP);
+  constexpr int H = CPLX ? 2 : 1;              // halves per unit
+  extern __shared__ __align__(16) float smem[];
+  const int Dq = CPLX ? 2 * a.d : a.d;
+  float *q = smem;                             // [Dq]
+  float *dq = q + ((Dq + 3) & ~3);             // [Dq]
+  float *sc = dq + ((Dq + 3) & ~3);            // [N] scores (only when do_loss)
+  float *gg = sc + (a.do_loss ? a.N : 0);      // [N] dL/ds   (only when do_loss)
+  float *scratch = gg + (a.do_loss ? a.N : 0); // [32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int nunits = a.d / V;                  // host guarantees divisibility
+  const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
+  const bool do_bwd = a.gE != nullptr;
+
+  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
+    const int64_t b = a.row_begin + rl;
+    int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
+    int64_t fid = HEAD ? tidx : hid;
+    if ((uint64_t)fid >= (uint64_t)a.nentity || (uint64_t)rid >= (uint64_t)a.nrelation) {
+      if (tid == 0 && a.err) *a.err = 1;
+      fid = 0; rid = 0;
+    }
+    const float *F = a.E + fid * a.De;
+    const float *Rr = a.R + rid * a.Dr;
+    const int64_t *cand = a.cand + b * a.cand_stride;
+
+    // ---- phase 0: query vector -------------------------------------------------------------------
+    __syncthreads();
+    for (int k = tid; k < a.d; k += blockDim.x) {
+      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q);
+      dq[k] = 0.f;
+      if (CPLX) dq[a.d + k] = 0.f;
+    }
+    __syncthreads();
+
+    // ---- phase 1: scores -------------------------------------------------------------------------
+    if (a.do_loss || a.score_out) {
+      for (int n = warp; n < a.N; n += nwarps) {
+        int64_t id = cand[n];
+        if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
+        const float *x = a.E + id * a.De;
+        float part = 0.f;
+        for (int kt = 0; kt < nunits; kt += 32 * kChunks) {
+#pragma unroll
+          for (int i = 0; i < kChunks; ++i) {
+            const int u = kt + lane + 32 * i;
+            if (u < nunits) {
+              float x0[V], x1[V], q0[V], q1[V];
+              load_global<V>(x0, x + u * V);
+              load_shared<V>(q0, q + u * V);
+              if constexpr (CPLX) {
+                load_global<V>(x1, x + a.d + u * V);
+                load_shared<V>(q1, q + a.d + u * V);
+              }
+#pragma unroll
+              for (int j = 0; j < V; ++j)
+                part += op_forward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale);
+            }
+          }
+        }
+        part = warp_sum(part);
+        const float s = finish_score<MODEL>(part, a.gamma, modulus);
+        if (lane == 0) {
+          if (a.do_loss) sc[n] = s;
+          if (a.score_out) a.score_out[(int64_t)rl * a.N + n] = s;
+        }
+      }
+    }
+    if (!a.do_loss && !do_bwd) continue;
+
+    // ---- phase 2: loss of this row (model.py:270-288) and dL/ds ---------------------------------------
+    if (a.do_loss) {
+      __syncthreads();
+      const float u = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
+      float row_val;
+      if (a.loss_kind == KGE_LOSS_POSITIVE) {              // model.py:277-279
+        const float s = sc[0];
+        row_val = log_sigmoid(s);
+        if (tid == 0) gg[0] = -0.5f * u * sigmoid(-s);
+      } else {
+        float zmax = -INFINITY;
+        if (a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL) {     // softmax(alpha * s).detach(), model.py:272
+          for (int n = tid; n < a.N; n += blockDim.x) zmax = fmaxf(zmax, sc[n] * a.alpha);
+          zmax = block_reduce(zmax, scratch, true);
+        }
+        float zsum = 0.f;
+        for (int n = tid; n < a.N; n += blockDim.x) {
+          const float e = a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL ? expf(sc[n] * a.alpha - zmax) : 1.f;
+          gg[n] = e;
+          zsum += e;
+        }
+        zsum = block_reduce(zsum, scratch, false);
+        float acc = 0.f;
+        for (int n = tid; n < a.N; n += blockDim.x) {
+          const float w = gg[n] / zsum;                    // = 1/N for the uniform case (model.py:275)
+          const float s = sc[n];
+          acc += w * log_sigmoid(-s);
+          gg[n] = 0.5f * u * w * sigmoid(s);
+        }
+        row_val = block_reduce(acc, scratch, false);
+      }
+      if (tid == 0) a.row_loss[b] = row_val;
+      __syncthreads();
+    }
+    if (!do_bwd) continue;
+    const float *gsrc = a.do_loss ? gg : a.dscore + (int64_t)rl * a.N;
+
+    // ---- phase 3/4: backward over the candidates, k-tiled so dL/dq stays in registers -----------------
+    float gmod = 0.f;
+    for (int kt = 0; kt < nunits; kt += 32 * kChunks) {
+      float acc[kChunks][H][V];
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
+
+      for (int n = warp; n < a.N; n += nwarps) {
+        int64_t id = cand[n];
+        if ((uint64_t)id >= (uint64_t)a.nentity) id = 0;
+        const float g = gsrc[n];
+        const float go = dsum_of<MODEL>(g, modulus);
+        const float *x = a.E + id * a.De;
+        float *gx = a.gE + id * a.De;
+        float vsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+          const int u = kt + lane + 32 * i;
+          if (u < nunits) {
+            float x0[V], x1[V], q0[V], q1[V], dx0[V], dx1[V];
+            load_global<V>(x0, x + u * V);
+            load_shared<V>(q0, q + u * V);
+            if constexpr (CPLX) {
+              load_global<V>(x1, x + a.d + u * V);
+              load_shared<V>(q1, q + a.d + u * V);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              float dq0 = 0.f, dq1 = 0.f, ex0 = 0.f, ex1 = 0.f;
+              vsum += op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, go,
+                                      dq0, dq1, ex0, ex1);
+              acc[i][0][j] += dq0;
+              dx0[j] = ex0;
+              if constexpr (CPLX) { acc[i][1][j] += dq1; dx1[j] = ex1; }
+            }
+            red_global<V>(gx + u * V, dx0);
+            if constexpr (CPLX) red_global<V>(gx + a.d + u * V, dx1);
+          }
+        }
+        if constexpr (MODEL == KGE_PROTATE) {
+          vsum = warp_sum(vsum);
+          gmod += -g * vsum;                               // d/dmodulus of gamma - modulus * sum
+        }
+      }
+      // phase 4: fixed-order fold of the per-warp partial dL/dq into shared memory
+      for (int w = 0; w < nwarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+          for (int i = 0; i < kChunks; ++i) {
+            const int u = kt + lane + 32 * i;
+            if (u < nunits) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                dq[u * V + j] += acc[i][0][j];
+                if constexpr (CPLX) dq[a.d + u * V + j] += acc[i][1][j];
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
+    float *gF = a.gE + fid * a.De;
+    float *gRr = a.gR + rid * a.Dr;
+    for (int k = tid; k < a.d; k += blockDim.x) {
+      float dF0, dF1, dR0, dR1;
+      chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
+      red_add1(gF + k, dF0);
+      red_add1(gRr + k, dR0);
+      if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
+      if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
+    }
+    if constexpr (MODEL == KGE_PROTATE) {
+      if (lane == 0 && gmod != 0.f && a.gM) red_add1(a.gM, gmod);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+template <int MODEL, bool HEAD>
+static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, cudaStream_t st) {
+  int grid = a.row_count;
+  if (vec4) {
+    auto k = row_kernel<MODEL, HEAD, 4>;
+    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, threads, smem, st>>>(a);
+  } else {
+    auto k = row_kernel<MODEL, HEAD, 1>;
+    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, threads, smem, st>>>(a);
+  }
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t st) {
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  a.E = m->entity; a.R = m->relation; a.modulus = m->modulus;
+  a.nentity = m->nentity; a.nrelation = m->nrelation;
+  a.De = (int)m->entity_dim; a.Dr = (int)m->relation_dim;
+  a.d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
+  a.gamma = m->gamma;
+  a.scale = phase_scale(m);
+  if (a.row_count <= 0 || a.N <= 0) return KGE_OK;
+  const bool aligned = (((uintptr_t)m->entity | (uintptr_t)a.gE) & 15) == 0;
+  const bool vec4 = aligned && (a.d % 4 == 0) && (m->entity_dim % 4 == 0);
+  const int Dq = (int)m->entity_dim;
+  size_t smem = sizeof(float) * (2 * (size_t)((Dq + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
+  KGE_REQUIRE(smem <= 227 * 1024, "entity_dim=%d with %d candidates per row needs %zu B of shared memory (max 232448)",
+              Dq, a.N, smem);
+  // one warp per candidate in flight; a single-candidate pass ('single' mode) only needs a few warps for q
+  int threads = a.N >= 16 ? 512 : (a.N >= 4 ? 256 : 128);
+#define KGE_ROWS(MODEL)                                                            \
+  case MODEL:                                                                      \
+    return head ? launch_rows_v<MODEL, true>(a, vec4, threads, smem, st)           \
+                : launch_rows_v<MODEL, false>(a, vec4, threads, smem, st);
+  switch (m->model) {
+    KGE_ROWS(KGE_TRANSE)
+    KGE_ROWS(KGE_DISTMULT)
+    KGE_ROWS(KGE_COMPLEX)
+    KGE_ROWS(KGE_ROTATE)
+    KGE_ROWS(KGE_PROTATE)
+  }
+#undef KGE_ROWS
+  set_error("model %d not supported", m->model);
+  return KGE_ERR_INVALID;
+}
+
+static int resolve_mode(int mode, const int64_t *positive, const int64_t *negative, int64_t N, RowArgs &a,
+                        bool &head) {
+  if (mode == KGE_SINGLE) {                 // model.py:83-102: candidate = the positive tail, N = 1
+    KGE_REQUIRE(N == 1, "single mode scores one triple per row (N=%lld)", (long long)N);
+    a.cand = positive + 2; a.cand_stride = 3; head = false;
+  } else if (mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH) {
+    KGE_REQUIRE(negative != nullptr, "mode needs the negative sample");
+    a.cand = negative; a.cand_stride = N; head = mode == KGE_HEAD_BATCH;
+  } else {
+    set_error("mode %d not supported", mode);        // model.py:149
+    return KGE_ERR_INVALID;
+  }
+  return KGE_OK;
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_score_forward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
+                                 int64_t B, int64_t N, float *score, int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(positive && score, "null pointer");
+  RowArgs a{};
+  bool head;
+  if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
+  if ((rc = set_device(m))) return rc;
+  a.positive = positive; a.row_begin = 0; a.row_count = (int)B; a.N = (int)N;
+  a.score_out = score; a.err = err_flag;
+  return launch_rows(m, head, a, (cudaStream_t)stream);
+}
+
+extern "C" int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
+                                  int64_t B, int64_t N, const float *dscore, float *grad_entity,
+                                  float *grad_relation, float *grad_modulus, int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(positive && dscore && grad_entity && grad_relation, "null pointer");
+  KGE_REQUIRE(m->model != KGE_PROTATE || grad_modulus, "pRotatE needs grad_modulus");
+  RowArgs a{};
+  bool head;
+  if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
+  if ((rc = set_device(m))) return rc;
+  a.positive = positive; a.row_begin = 0; a.row_count = (int)B; a.N = (int)N;
+  a.dscore = dscore; a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
+  return launch_rows(m, head, a, (cudaStream_t)stream);
+}
+
+extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                              const int64_t *positive, const int64_t *negative, const float *weight,
+                              const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
+                              int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
+                              float *grad_modulus, float *score_out, int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(positive && row_loss && grad_entity && grad_relation, "null pointer");
+  KGE_REQUIRE(m->model != KGE_PROTATE || grad_modulus, "pRotatE needs grad_modulus");
+  KGE_REQUIRE(loss_kind >= KGE_LOSS_NEG_ADVERSARIAL && loss_kind <= KGE_LOSS_POSITIVE, "bad loss_kind %d", loss_kind);
+  KGE_REQUIRE(!weight || weight_sum, "subsampling weights need their sum (kge_weight_sum)");
+  KGE_REQUIRE(row_begin >= 0 && row_begin + row_count <= B_total, "row slice [%lld,+%lld) outside batch of %lld",
+              (long long)row_begin, (long long)row_count, (long long)B_total);
+  RowArgs a{};
+  bool head;
+  if (loss_kind == KGE_LOSS_POSITIVE) { mode = KGE_SINGLE; N = 1; }
+  if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
+  if ((rc = set_device(m))) return rc;
+  a.positive = positive; a.row_begin = row_begin; a.row_count = (int)row_count; a.N = (int)N;
+  a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
+  a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
+  a.row_loss = row_loss; a.score_out = score_out;
+  a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
+  return launch_rows(m, head, a, (cudaStream_t)stream);
+}

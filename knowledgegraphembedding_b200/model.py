@@ -1,0 +1,511 @@
+"""Drop-in `KGEModel` for the RotatE toolkit (reference: codes/model.py:22-429), B200-native.
+
+Same constructor, parameters, state_dict keys, `forward(sample, mode)`, the five public score methods and
+the static `train_step` / `test_step` that `codes/run.py` calls (run.py:227-235, 311, 341-363) -- but every
+arithmetic step runs in the hand-written sm_100a kernels of libkge_b200.so (include/kge_b200.h).  PyTorch is
+used for device memory, streams, `nn.Module` bookkeeping and NCCL only.  There is no CPU / eager fallback:
+calling the scoring paths with parameters that are not on a B200 raises.
+"""
+import ctypes
+import logging
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .filter_index import FilterIndex
+
+_MODELS = ('TransE', 'DistMult', 'ComplEx', 'RotatE', 'pRotatE')
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dist():
+    """(rank, world_size) of the data-parallel group, (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous balanced slice [begin, end) of `total` items for `rank` (batch rows / entity ids)."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class _ScoreFunction(torch.autograd.Function):
+    """forward(sample, mode) with autograd: the backward is kge_score_backward (model.py:301 through :86-146)."""
+
+    @staticmethod
+    def forward(ctx, model, entity, relation, modulus, positive, negative, mode):
+        B = positive.shape[0]
+        N = 1 if mode == 'single' else negative.shape[1]
+        score = torch.empty((B, N), dtype=torch.float32, device=entity.device)
+        desc = model._descriptor(entity, relation, modulus)
+        err = model._err_flag()
+        _lib.call("kge_score_forward", ctypes.byref(desc), _lib.MODE_IDS[mode], _ptr(positive), _ptr(negative),
+                  B, N, _ptr(score), _ptr(err), _stream(entity.device))
+        ctx.model, ctx.mode = model, mode
+        ctx.save_for_backward(entity, relation, modulus if modulus is not None else entity.new_empty(0),
+                              positive, negative if negative is not None else positive.new_empty(0))
+        return score
+
+    @staticmethod
+    def backward(ctx, dscore):
+        entity, relation, modulus, positive, negative = ctx.saved_tensors
+        model, mode = ctx.model, ctx.mode
+        modulus = modulus if modulus.numel() else None
+        negative = negative if negative.numel() else None
+        B = positive.shape[0]
+        N = 1 if mode == 'single' else negative.shape[1]
+        dscore = dscore.contiguous().float()
+        gE, gR = torch.zeros_like(entity), torch.zeros_like(relation)
+        gM = torch.zeros_like(modulus) if modulus is not None else None
+        desc = model._descriptor(entity, relation, modulus)
+        _lib.call("kge_score_backward", ctypes.byref(desc), _lib.MODE_IDS[mode], _ptr(positive), _ptr(negative),
+                  B, N, _ptr(dscore), _ptr(gE), _ptr(gR), _ptr(gM), None, _stream(entity.device))
+        return None, gE, gR, gM, None, None, None
+
+
+class KGEModel(nn.Module):
+    def __init__(self, model_name, nentity, nrelation, hidden_dim, gamma,
+                 double_entity_embedding=False, double_relation_embedding=False):
+        super(KGEModel, self).__init__()
+        self.model_name = model_name
+        self.nentity = nentity
+        self.nrelation = nrelation
+        self.hidden_dim = hidden_dim
+        self.epsilon = 2.0
+
+        # registration order = the reference's (model.py:32-60), so optimizer param order is [E, R, (modulus)]
+        self.gamma = nn.Parameter(torch.Tensor([gamma]), requires_grad=False)
+        self.embedding_range = nn.Parameter(
+            torch.Tensor([(self.gamma.item() + self.epsilon) / hidden_dim]), requires_grad=False)
+
+        self.entity_dim = hidden_dim * 2 if double_entity_embedding else hidden_dim
+        self.relation_dim = hidden_dim * 2 if double_relation_embedding else hidden_dim
+
+        rho = self.embedding_range.item()
+        self.entity_embedding = nn.Parameter(torch.zeros(nentity, self.entity_dim))
+        nn.init.uniform_(tensor=self.entity_embedding, a=-rho, b=rho)
+        self.relation_embedding = nn.Parameter(torch.zeros(nrelation, self.relation_dim))
+        nn.init.uniform_(tensor=self.relation_embedding, a=-rho, b=rho)
+        if model_name == 'pRotatE':
+            self.modulus = nn.Parameter(torch.Tensor([[0.5 * rho]]))
+
+        if model_name not in _MODELS:
+            raise ValueError('model %s not supported' % model_name)
+        if model_name == 'RotatE' and (not double_entity_embedding or double_relation_embedding):
+            raise ValueError('RotatE should use --double_entity_embedding')
+        if model_name == 'ComplEx' and (not double_entity_embedding or not double_relation_embedding):
+            raise ValueError('ComplEx should use --double_entity_embedding and --double_relation_embedding')
+
+        self._ws = {}           # lazily allocated device workspaces (not part of state_dict)
+        self._filter_cache = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _device(self):
+        dev = self.entity_embedding.device
+        if dev.type != 'cuda':
+            raise RuntimeError('KGEModel (B200-native) computes only on a CUDA device: call .cuda() first; '
+                               'there is no CPU fallback')
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        return dev
+
+    def _scalars(self):
+        """(gamma.item(), embedding_range.item()) without a device sync per call (the reference syncs in every
+        score function, model.py:172,209,...); refreshed when the parameters are modified in place."""
+        key = (self.gamma._version, self.embedding_range._version, self.gamma.data_ptr())
+        if self._ws.get('scalars_key') != key:
+            self._ws['scalars_key'] = key
+            self._ws['scalars'] = (self.gamma.item(), self.embedding_range.item())
+        return self._ws['scalars']
+
+    def _descriptor(self, entity=None, relation=None, modulus=None, name=None):
+        entity = self.entity_embedding if entity is None else entity
+        relation = self.relation_embedding if relation is None else relation
+        if modulus is None and hasattr(self, 'modulus') and name is None:
+            modulus = self.modulus
+        for t in (entity, relation):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('embedding tables must be contiguous float32')
+        dev = entity.device
+        return _lib.KgeModelStruct(
+            model=_lib.MODEL_IDS[name or self.model_name], device=dev.index or 0,
+            nentity=entity.shape[0], nrelation=relation.shape[0],
+            hidden_dim=entity.shape[1] // 2 if (name or self.model_name) in ('RotatE', 'ComplEx') else entity.shape[1],
+            entity_dim=entity.shape[1], relation_dim=relation.shape[1],
+            gamma=self._scalars()[0], embedding_range=self._scalars()[1],
+            entity=entity.data_ptr(), relation=relation.data_ptr(),
+            modulus=modulus.data_ptr() if modulus is not None else None)
+
+    def _buffer(self, key, numel, dtype, device):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < numel or buf.device != device or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
+            self._ws[key] = buf
+        return buf
+
+    def _err_flag(self):
+        """int32 device flag set by the kernels on an out-of-range id; it is slot 4 of the 8-float loss buffer so
+        that train_step reads losses and flag back in one copy."""
+        dev = self.entity_embedding.device
+        flag = self._ws.get('err')
+        if flag is None or flag.device != dev:
+            out = torch.zeros(8, dtype=torch.float32, device=dev)
+            self._ws['loss_out'] = out
+            flag = out.view(torch.int32)[4:5]
+            self._ws['err'] = flag
+        return flag
+
+    def _raise_if_bad_index(self):
+        flag = self._ws.get('err')
+        if flag is not None and int(flag.item()) != 0:
+            flag.zero_()
+            raise IndexError('index out of range in sample (entity/relation id outside the embedding table)')
+
+    def _apply(self, fn, *args, **kwargs):      # .cuda()/.to(): workspaces belong to the old device
+        self._ws = {}
+        return super(KGEModel, self)._apply(fn, *args, **kwargs)
+
+    # ------------------------------------------------------------------------------------------ scoring
+    def forward(self, sample, mode='single'):
+        '''
+        Score a batch of triples (reference: model.py:72-164).
+        'single': sample is a LongTensor [B,3] -> [B,1].
+        'head-batch' / 'tail-batch': sample = (positive [B,3], negative entities [B,N]) -> [B,N].
+        '''
+        dev = self._device()
+        if mode == 'single':
+            positive, negative = sample, None
+        elif mode in ('head-batch', 'tail-batch'):
+            positive, negative = sample
+            negative = negative.to(device=dev, dtype=torch.int64).contiguous()
+            if negative.dim() != 2 or negative.shape[0] != positive.shape[0]:
+                raise ValueError('negative sample must be [batch, negative_sample_size]')
+        else:
+            raise ValueError('mode %s not supported' % mode)
+        positive = positive.to(device=dev, dtype=torch.int64).contiguous()
+        if positive.dim() != 2 or positive.shape[1] != 3:
+            raise ValueError('positive sample must be [batch, 3]')
+        if self.model_name not in _MODELS:
+            raise ValueError('model %s not supported' % self.model_name)
+        modulus = self.modulus if self.model_name == 'pRotatE' else None
+        return _ScoreFunction.apply(self, self.entity_embedding, self.relation_embedding, modulus,
+                                    positive, negative, mode)
+
+    def _score_rows(self, name, head, relation, tail, mode):
+        """Public score-function signature of the reference (model.py:166-249): gathered rows
+        head/relation/tail [B, 1|N, D] -> [B, N].  The rows are stacked into temporary tables and sent
+        through the same kernels, so the arithmetic is identical to forward()."""
+        dev = self._device()
+        B = head.shape[0]
+        hb = mode == 'head-batch'               # every other mode string takes the else-branch, as in the reference
+        cand, fixed = (head, tail) if hb else (tail, head)
+        if fixed.shape[1] != 1 or relation.shape[1] != 1:
+            raise ValueError('only the candidate side may have more than one row per batch element')
+        N = cand.shape[1]
+        table = torch.cat([fixed.reshape(B, -1), cand.reshape(B * N, -1)], dim=0).float().contiguous()
+        rel = relation.reshape(B, -1).float().contiguous()
+        ar = torch.arange(B, device=dev, dtype=torch.int64)
+        positive = torch.stack([ar, ar, ar], dim=1)          # row b of the temporary tables is the fixed side
+        negative = (B + torch.arange(B * N, device=dev, dtype=torch.int64)).reshape(B, N)
+        modulus = self.modulus if name == 'pRotatE' else None
+        return _ScoreFunction.apply(_NamedView(self, name), table, rel, modulus, positive, negative,
+                                    'head-batch' if hb else 'tail-batch')
+
+    def TransE(self, head, relation, tail, mode):
+        return self._score_rows('TransE', head, relation, tail, mode)
+
+    def DistMult(self, head, relation, tail, mode):
+        return self._score_rows('DistMult', head, relation, tail, mode)
+
+    def ComplEx(self, head, relation, tail, mode):
+        return self._score_rows('ComplEx', head, relation, tail, mode)
+
+    def RotatE(self, head, relation, tail, mode):
+        return self._score_rows('RotatE', head, relation, tail, mode)
+
+    def pRotatE(self, head, relation, tail, mode):
+        return self._score_rows('pRotatE', head, relation, tail, mode)
+
+    # ------------------------------------------------------------------------------------------ training
+    def _trainable(self):
+        ps = [self.entity_embedding, self.relation_embedding]
+        if self.model_name == 'pRotatE':
+            ps.append(self.modulus)
+        return ps
+
+    def _grad_workspace(self, B):
+        """One flat fp32 buffer [dE | dR | dModulus(4) | pos_row[B] | neg_row[B]] so that the multi-GPU
+        exchange is a single all-reduce, plus the small scalar buffers."""
+        dev = self.entity_embedding.device
+        nE, nR = self.entity_embedding.numel(), self.relation_embedding.numel()
+        nE4, nR4 = (nE + 3) // 4 * 4, (nR + 3) // 4 * 4
+        total = nE4 + nR4 + 4 + 2 * B
+        flat = self._buffer('grad_flat', total, torch.float32, dev)[:total]
+        views = {
+            'flat': flat,
+            'gE': flat[:nE].view_as(self.entity_embedding),
+            'gR': flat[nE4:nE4 + nR].view_as(self.relation_embedding),
+            'gM': flat[nE4 + nR4:nE4 + nR4 + 1].view(1, 1),
+            'pos_row': flat[nE4 + nR4 + 4:nE4 + nR4 + 4 + B],
+            'neg_row': flat[nE4 + nR4 + 4 + B:total],
+            'wsum': self._buffer('wsum', 1, torch.float32, dev),
+            'reg': self._buffer('reg_partials', 148 * 8, torch.float64, dev),
+        }
+        return views
+
+    @staticmethod
+    def _fusable_adam(model, optimizer):
+        if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        if g.get('amsgrad') or g.get('maximize') or g.get('weight_decay', 0) != 0 or g.get('capturable') \
+                or g.get('differentiable') or g.get('decoupled_weight_decay'):
+            return False
+        if isinstance(g['lr'], torch.Tensor) or any(isinstance(b, torch.Tensor) for b in g['betas']):
+            return False
+        want = model._trainable()
+        have = [p for p in g['params'] if p.requires_grad]       # run.py:266 filters; tolerate unfiltered lists
+        return len(have) == len(want) and all(a is b for a, b in zip(have, want))
+
+    @staticmethod
+    def train_step(model, optimizer, train_iterator, args):
+        '''
+        A single train step (reference: model.py:251-312): next batch -> negative scores ->
+        self-adversarial / uniform loss -> positive scores -> weighted loss (+ L3) -> backward -> Adam.
+        Returns the same log dict of python floats.
+        '''
+        model.train()
+        optimizer.zero_grad()
+        out = model.train_step_async(optimizer, next(train_iterator), args)
+        reg = float(getattr(args, 'regularization', 0.0))
+        out = out.tolist()                        # the step's single device->host sync (model.py:305-310 has 3-4)
+        if out[4] != 0.0:
+            model._err_flag().zero_()
+            raise IndexError('index out of range in sample (entity/relation id outside the embedding table)')
+        regularization_log = {'regularization': out[3]} if reg != 0.0 else {}
+        log = {
+            **regularization_log,
+            'positive_sample_loss': out[0],
+            'negative_sample_loss': out[1],
+            'loss': out[2]
+        }
+        return log
+
+    def train_step_async(self, optimizer, batch, args):
+        """Everything train_step does on the device, without the final read-back: returns the device buffer
+        [positive_sample_loss, negative_sample_loss, loss, regularization, err_flag(int32 bits), ...]."""
+        model = self
+        dev = model._device()
+        st = _stream(dev)
+
+        positive_sample, negative_sample, subsampling_weight, mode = batch
+        if mode not in ('head-batch', 'tail-batch'):
+            raise ValueError('mode %s not supported' % mode)
+        positive = positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        negative = negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        B, N = negative.shape
+        uni = bool(getattr(args, 'uni_weight', False))
+        weight = None if uni else subsampling_weight.to(device=dev, dtype=torch.float32,
+                                                        non_blocking=True).contiguous()
+        reg = float(getattr(args, 'regularization', 0.0))
+        adversarial = bool(args.negative_adversarial_sampling)
+        alpha = float(args.adversarial_temperature) if adversarial else 1.0
+
+        ws = model._grad_workspace(B)
+        err = model._err_flag()
+        ws['out'] = model._ws['loss_out']
+        desc = model._descriptor()
+        events = model._ws.get('kernel_events')       # bench.py: CUDA events around the dominant kernel
+        rank, world = _dist()
+        row_begin, row_end = shard_bounds(B, rank, world)
+
+        _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
+        if weight is not None:
+            _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
+        gM = ws['gM'] if model.model_name == 'pRotatE' else None
+        common = (_ptr(positive), _ptr(negative), _ptr(weight), _ptr(ws['wsum']) if weight is not None else None,
+                  B, row_begin, row_end - row_begin, N)
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode],
+                  _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM, alpha, *common,
+                  _ptr(ws['neg_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(err), st)
+        if events is not None:
+            ev1.record()
+            events.append((ev0, ev1))
+        _lib.call("kge_train_rows", ctypes.byref(desc), _lib.SINGLE, _lib.LOSS_POSITIVE, 1.0, *common,
+                  _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(err), st)
+        if world > 1:
+            # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
+            torch.distributed.all_reduce(ws['flat'])
+
+        params = model._trainable()
+        grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
+        if KGEModel._fusable_adam(model, optimizer):
+            group = optimizer.param_groups[0]
+            tensors = (_lib.KgeAdamTensor * len(params))()
+            for i, (p, g) in enumerate(zip(params, grads)):
+                state = optimizer.state[p]
+                if len(state) == 0:             # same lazy state as torch/optim/adam.py _init_group
+                    state['step'] = torch.tensor(0.0, dtype=torch.float32)
+                    state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state['step'] += 1
+                tensors[i] = _lib.KgeAdamTensor(p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(),
+                                                state['exp_avg_sq'].data_ptr(), p.numel(), int(state['step'].item()),
+                                                1 if (reg != 0.0 and i < 2) else 0)
+            _lib.call("kge_adam_step", tensors, len(params), float(group['lr']), float(group['betas'][0]),
+                      float(group['betas'][1]), float(group['eps']), reg,
+                      _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
+            reg_partials = ws['reg'] if reg != 0.0 else None
+            for p, g in zip(params, grads):
+                p.grad = g
+        else:
+            # any other optimizer object: hand it our gradients and let it do its own update
+            reg_partials = None
+            if reg != 0.0:
+                with torch.no_grad():
+                    parts = ws['reg']
+                    parts.zero_()
+                    for i, (p, g) in enumerate(zip(params[:2], grads[:2])):
+                        parts[i] = p.detach().abs().pow(3).sum(dtype=torch.float64)
+                        g.add_(3.0 * reg * p.detach() * p.detach().abs())
+                reg_partials = parts
+            for p, g in zip(params, grads):
+                p.grad = g
+            optimizer.step()
+
+        _lib.call("kge_loss_finalize", _ptr(ws['pos_row']), _ptr(ws['neg_row']), _ptr(weight),
+                  _ptr(ws['wsum']) if weight is not None else None, B, reg,
+                  _ptr(reg_partials) if reg_partials is not None else None,
+                  reg_partials.numel() if reg_partials is not None else 0, _ptr(ws['out']), st)
+        return ws['out']
+
+    # ------------------------------------------------------------------------------------------ evaluation
+    def _filter_index(self, all_true_triples, nentity, nrelation):
+        key = (id(all_true_triples), len(all_true_triples), nentity, nrelation)
+        if self._filter_cache is None or self._filter_cache[0] != key:
+            self._filter_cache = (key, FilterIndex(all_true_triples, nentity, nrelation))
+        return self._filter_cache[1]
+
+    def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False):
+        """Filtered rank of every test triple in `mode` (model.py:382-418 without the sort): int64 [len].
+        Entities are sharded across the ranks of an initialised process group; the integer counts are
+        all-reduced (bit-exact)."""
+        dev = self._device()
+        st = _stream(dev)
+        nentity, nrelation = self.entity_embedding.shape[0], self.relation_embedding.shape[0]
+        index = self._filter_index(all_true_triples, nentity, nrelation)
+        queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
+        rank, world = _dist()
+        ent_begin, ent_end = shard_bounds(nentity, rank, world)
+        desc = self._descriptor()
+        err = self._err_flag()
+        words = (nentity + 31) // 32
+        phase = None
+        if self.model_name == 'pRotatE':
+            phase = self._buffer('phase_table', self.entity_embedding.numel(), torch.float32, dev)
+            _lib.call("kge_eval_phase_table", ctypes.byref(desc), _ptr(phase), st)
+        counts_all = torch.zeros(queries_all.shape[0], dtype=torch.int32, device=dev)
+        scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
+        m = _lib.MODE_IDS[mode]
+        for lo in range(0, queries_all.shape[0], query_chunk):
+            q_np = queries_all[lo:lo + query_chunk]
+            Q = q_np.shape[0]
+            offsets, ents = index.csr(q_np, mode)
+            queries = torch.from_numpy(q_np).to(dev, non_blocking=True)
+            d_off = torch.from_numpy(offsets).to(dev, non_blocking=True)
+            d_ent = torch.from_numpy(ents).to(dev, non_blocking=True) if ents.size else \
+                torch.zeros(1, dtype=torch.int32, device=dev)
+            bits = self._buffer('filter_bits', Q * words, torch.int32, dev)
+            qvec = self._buffer('qvec', Q * self.entity_dim, torch.float32, dev)
+            pos = self._buffer('pos_score', Q, torch.float32, dev)
+            counts = counts_all[lo:lo + Q]
+            _lib.call("kge_eval_filter_bits", _ptr(d_off), _ptr(d_ent), Q, nentity, _ptr(bits), st)
+            _lib.call("kge_eval_query_vectors", ctypes.byref(desc), m, _ptr(queries), Q, _ptr(qvec), _ptr(err), st)
+            _lib.call("kge_eval_positive_scores", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
+                      _ptr(pos), st)
+            _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
+                      _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
+                      _ptr(scores[lo:lo + Q]) if scores is not None else None, st)
+        if world > 1:
+            torch.distributed.all_reduce(counts_all)
+        ranks = (counts_all.to(torch.int64) + 1).cpu().numpy()
+        self._raise_if_bad_index()
+        return (ranks, scores) if return_scores else ranks
+
+    @staticmethod
+    def test_step(model, test_triples, all_true_triples, args):
+        '''
+        Evaluate the model on test or valid datasets (reference: model.py:314-429).
+        '''
+        model.eval()
+
+        if args.countries:
+            # Countries S* are evaluated on AUC-PR (model.py:322-344); 5 regions x |test| scores, sklearn on host
+            from sklearn.metrics import average_precision_score
+            sample = list()
+            y_true = list()
+            for head, relation, tail in test_triples:
+                for candidate_region in args.regions:
+                    y_true.append(1 if candidate_region == tail else 0)
+                    sample.append((head, relation, candidate_region))
+            sample = torch.LongTensor(sample)
+            with torch.no_grad():
+                y_score = model(sample).squeeze(1).cpu().numpy()
+            y_true = np.array(y_true)
+            auc_pr = average_precision_score(y_true, y_score)
+            return {'auc_pr': auc_pr}
+
+        # filtered MRR / MR / HITS@1,3,10 (model.py:346-427)
+        batch = max(1, int(getattr(args, 'test_batch_size', 1)))
+        steps_per_mode = (len(test_triples) + batch - 1) // batch
+        total_steps = 2 * steps_per_mode
+        log_every = max(1, int(getattr(args, 'test_log_steps', 1000)))
+        logs = []
+        step = 0
+        with torch.no_grad():
+            for mode in ('head-batch', 'tail-batch'):
+                ranks = model.filtered_ranks(test_triples, all_true_triples, mode)
+                for _ in range(steps_per_mode):          # same progress lines as model.py:420-423
+                    if step % log_every == 0:
+                        logging.info('Evaluating the model... (%d/%d)' % (step, total_steps))
+                    step += 1
+                for ranking in ranks.tolist():
+                    logs.append({
+                        'MRR': 1.0 / ranking,
+                        'MR': float(ranking),
+                        'HITS@1': 1.0 if ranking <= 1 else 0.0,
+                        'HITS@3': 1.0 if ranking <= 3 else 0.0,
+                        'HITS@10': 1.0 if ranking <= 10 else 0.0,
+                    })
+        metrics = {}
+        for metric in logs[0].keys():
+            metrics[metric] = sum([log[metric] for log in logs]) / len(logs)
+        return metrics
+
+
+class _NamedView:
+    """Descriptor provider for the public score methods: same scalars as the owning model, another model name."""
+
+    def __init__(self, owner, name):
+        self.owner, self.name = owner, name
+
+    def _descriptor(self, entity, relation, modulus):
+        return self.owner._descriptor(entity, relation, modulus, name=self.name)
+
+    def _err_flag(self):
+        return self.owner._err_flag()

@@ -1,0 +1,417 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the KGEModel drop-in) against
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  * the CPU oracles (oracle/kge_oracle.py numpy, oracle/kge_oracle.c) on seeded inputs,
+  * at BASELINE.json's full sizes: bit-exact evaluation scores/ranks vs the C oracle, and size-independent
+    properties for the train path.
+Tolerance (north_star): scores, loss, updated embeddings within 1e-5 relative (fp32); ranks bit-exact.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, outlier_fraction, relinf
+from oracle import c_oracle as C
+from oracle import kge_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+MODELS = ["TransE", "DistMult", "ComplEx", "RotatE", "pRotatE"]
+FLAGS = {"TransE": (False, False), "DistMult": (False, False), "ComplEx": (True, True),
+         "RotatE": (True, False), "pRotatE": (False, False)}
+DIST = ("TransE", "RotatE", "pRotatE")       # score = gamma - distance: tolerance is relative to the distance
+
+
+def KGE():
+    from knowledgegraphembedding_b200 import KGEModel
+    return KGEModel
+
+
+def make_model(model, nentity, nrelation, d, gamma, state=None):
+    de, dr = FLAGS[model]
+    m = KGE()(model_name=model, nentity=nentity, nrelation=nrelation, hidden_dim=d, gamma=gamma,
+              double_entity_embedding=de, double_relation_embedding=dr)
+    if state is not None:
+        with torch.no_grad():
+            m.entity_embedding.copy_(torch.from_numpy(np.asarray(state["entity_embedding"])))
+            m.relation_embedding.copy_(torch.from_numpy(np.asarray(state["relation_embedding"])))
+            if model == "pRotatE" and "modulus" in state:
+                m.modulus.copy_(torch.from_numpy(np.asarray(state["modulus"])))
+    return m.cuda()
+
+
+def score_err(model, got, want, gamma):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    if model in DIST:
+        return float(np.max(np.abs(got - want)) / max(np.max(np.abs(gamma - want)), 1e-30))
+    return relinf(got, want)
+
+
+def ns(**kw):
+    base = dict(cuda=True, negative_adversarial_sampling=False, adversarial_temperature=1.0, uni_weight=False,
+                regularization=0.0, countries=False, regions=None, test_batch_size=4, cpu_num=2,
+                test_log_steps=100000, nentity=0, nrelation=0)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def golden_state(g, prefix="init_"):
+    st = {"entity_embedding": g[prefix + "entity_embedding"], "relation_embedding": g[prefix + "relation_embedding"]}
+    if prefix + "modulus" in g.files:
+        st["modulus"] = g[prefix + "modulus"]
+    return st
+
+
+# ------------------------------------------------------------------------------------------------ forward / autograd
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d", [12, 10])
+def test_forward_and_autograd_vs_reference_golden(model, d):
+    g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
+    gamma = float(g["gamma"])
+    m = make_model(model, int(g["nentity"]), int(g["nrelation"]), d, gamma, golden_state(g))
+    pos, neg = torch.from_numpy(g["positive"]), torch.from_numpy(g["negative"])
+    cot = torch.from_numpy(g["cotangent"]).cuda()
+    for mode in O.MODES:
+        m.zero_grad()
+        s = m(pos) if mode == "single" else m((pos, neg), mode)
+        assert s.shape == g["score_" + mode].shape and s.dtype == torch.float32
+        assert score_err(model, s.detach().cpu().numpy(), g["score_" + mode], gamma) < TOL, (model, mode)
+        (s * cot[:, :s.shape[1]]).sum().backward()
+        assert relinf(m.entity_embedding.grad.cpu().numpy(), g["dE_" + mode]) < TOL, (model, mode)
+        assert relinf(m.relation_embedding.grad.cpu().numpy(), g["dR_" + mode]) < TOL, (model, mode)
+        if model == "pRotatE":
+            assert relinf(m.modulus.grad.cpu().numpy(), g["dM_" + mode]) < TOL
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_public_score_methods(model):
+    """KGEModel.TransE/.../pRotatE(head, relation, tail, mode) on gathered rows == forward() (model.py:166-249)."""
+    g = np.load(os.path.join(GOLDEN, f"small_{model}_d12.npz"))
+    gamma = float(g["gamma"])
+    m = make_model(model, int(g["nentity"]), int(g["nrelation"]), 12, gamma, golden_state(g))
+    pos, neg = torch.from_numpy(g["positive"]).cuda(), torch.from_numpy(g["negative"]).cuda()
+    E, R = m.entity_embedding.detach(), m.relation_embedding.detach()
+    fn = getattr(m, model)
+    for mode in ("head-batch", "tail-batch"):
+        if mode == "head-batch":
+            head, tail = E[neg.view(-1)].view(neg.shape[0], neg.shape[1], -1), E[pos[:, 2]].unsqueeze(1)
+        else:
+            head, tail = E[pos[:, 0]].unsqueeze(1), E[neg.view(-1)].view(neg.shape[0], neg.shape[1], -1)
+        s = fn(head, R[pos[:, 1]].unsqueeze(1), tail, mode)
+        assert score_err(model, s.cpu().numpy(), g["score_" + mode], gamma) < TOL
+    s = fn(E[pos[:, 0]].unsqueeze(1), R[pos[:, 1]].unsqueeze(1), E[pos[:, 2]].unsqueeze(1), "single")
+    assert score_err(model, s.cpu().numpy(), g["score_single"], gamma) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ train_step
+CFGS = {
+    "adv_sub": dict(negative_adversarial_sampling=True, adversarial_temperature=0.7, uni_weight=False),
+    "adv_uni": dict(negative_adversarial_sampling=True, adversarial_temperature=1.0, uni_weight=True),
+    "mean_sub": dict(negative_adversarial_sampling=False, uni_weight=False),
+    "adv_sub_reg": dict(negative_adversarial_sampling=True, adversarial_temperature=1.0, uni_weight=False,
+                        regularization=1e-3),
+}
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d", [12, 10])
+@pytest.mark.parametrize("cfg", list(CFGS))
+def test_train_steps_vs_reference_golden(model, d, cfg):
+    """4 train_steps with the run.py call sequence (incl. the Adam re-creation of run.py:315-322)."""
+    g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
+    m = make_model(model, int(g["nentity"]), int(g["nrelation"]), d, float(g["gamma"]), golden_state(g))
+    lr = 1e-3
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+    batches = [(torch.from_numpy(g[f"train_{cfg}_pos{i}"]), torch.from_numpy(g[f"train_{cfg}_neg{i}"]),
+                torch.from_numpy(g[f"train_{cfg}_w{i}"]), "tail-batch" if i % 2 == 0 else "head-batch")
+               for i in range(4)]
+    it = iter(batches)
+    args = ns(**CFGS[cfg])
+    for step in range(4):
+        if step == 2:
+            lr /= 10
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+        log = KGE().train_step(m, opt, it, args)
+        ref = g[f"train_{cfg}_logs"][step]
+        keys = (["regularization"] if "reg" in cfg else []) + ["positive_sample_loss", "negative_sample_loss", "loss"]
+        assert list(log.keys()) == keys and all(isinstance(v, float) for v in log.values())
+        got = [log.get("regularization", 0.0), log["positive_sample_loss"], log["negative_sample_loss"], log["loss"]]
+        np.testing.assert_allclose(got, ref, rtol=TOL, atol=1e-7)
+        if step == 0:
+            assert relinf(m.entity_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gE0"]) < TOL
+            assert relinf(m.relation_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gR0"]) < TOL
+            if model == "pRotatE":
+                assert relinf(m.modulus.grad.cpu().numpy(), g[f"train_{cfg}_gM0"]) < TOL
+    assert relinf(m.entity_embedding.detach().cpu().numpy(), g[f"train_{cfg}_E"]) < TOL
+    assert relinf(m.relation_embedding.detach().cpu().numpy(), g[f"train_{cfg}_R"]) < TOL
+    if model == "pRotatE":
+        assert relinf(m.modulus.detach().cpu().numpy(), g[f"train_{cfg}_M"]) < TOL
+    # the optimizer state is torch's own layout: it round-trips through a stock Adam (run.py:106,283)
+    sd = opt.state_dict()
+    assert [float(sd["state"][k]["step"]) for k in sorted(sd["state"])] == list(g[f"train_{cfg}_adam_steps"])
+    torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr).load_state_dict(sd)
+
+
+def test_train_step_matches_autograd_path_full_width():
+    """cfg-3 row shape (RotatE, d=1000, N=256, 14,951 entities): fused train grads vs (a) the numpy oracle,
+    (b) forward() + torch loss + the autograd backward kernel."""
+    import torch.nn.functional as F
+    nentity, nrel, d, gamma, B, N = 14951, 1345, 1000, 24.0, 48, 256
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=0)
+    rng = np.random.RandomState(1)
+    pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
+    neg = rng.randint(nentity, size=(B, N))
+    w = np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)
+    for mode in ("tail-batch", "head-batch"):
+        m = make_model("RotatE", nentity, nrel, d, gamma, st)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+        args = ns(negative_adversarial_sampling=True, adversarial_temperature=1.0)
+        log = KGE().train_step(m, opt, iter([(torch.from_numpy(pos), torch.from_numpy(neg), torch.from_numpy(w), mode)]), args)
+        gE, gR = m.entity_embedding.grad.cpu().numpy(), m.relation_embedding.grad.cpu().numpy()
+        # (a) numpy oracle
+        ts = O.TrainState("RotatE", st, gamma, d)
+        olog, og = O.train_step(ts, (pos, neg, w, mode), lr=1e-4, adversarial=True, alpha=1.0, return_grads=True)
+        for k in ("positive_sample_loss", "negative_sample_loss", "loss"):
+            assert abs(log[k] - olog[k]) <= TOL * abs(olog[k])
+        assert relinf(gE, og["entity_embedding"]) < TOL and relinf(gR, og["relation_embedding"]) < TOL
+        assert outlier_fraction(m.entity_embedding.detach().cpu().numpy(), ts.state["entity_embedding"]) < 1e-4
+        # (b) the differentiable forward() path of the same library
+        m2 = make_model("RotatE", nentity, nrel, d, gamma, st)
+        tp, tn, tw = torch.from_numpy(pos).cuda(), torch.from_numpy(neg).cuda(), torch.from_numpy(w).cuda()
+        sneg = m2((tp, tn), mode)
+        nl = (F.softmax(sneg, dim=1).detach() * F.logsigmoid(-sneg)).sum(dim=1)
+        pl = F.logsigmoid(m2(tp)).squeeze(1)
+        loss = (-(tw * pl).sum() / tw.sum() - (tw * nl).sum() / tw.sum()) / 2
+        loss.backward()
+        assert abs(loss.item() - log["loss"]) <= TOL * abs(log["loss"])
+        assert relinf(m2.entity_embedding.grad.cpu().numpy(), gE) < TOL
+        assert relinf(m2.relation_embedding.grad.cpu().numpy(), gR) < TOL
+
+
+def test_adam_kernel_vs_torch_adam():
+    """kge_adam_step == torch.optim.Adam (foreach CUDA path) over 5 steps of random gradients."""
+    torch.manual_seed(0)
+    m = make_model("TransE", 5000, 11, 36, 9.0)
+    ref = [p.detach().clone().requires_grad_(True) for p in (m.entity_embedding, m.relation_embedding)]
+    ropt = torch.optim.Adam(ref, lr=3e-4)
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4)
+    args = ns(negative_adversarial_sampling=True)
+    B, N = 64, 32
+    for step in range(5):
+        pos = torch.stack([torch.randint(5000, (B,)), torch.randint(11, (B,)), torch.randint(5000, (B,))], 1)
+        neg = torch.randint(5000, (B, N))
+        w = torch.rand(B) + 0.1
+        KGE().train_step(m, opt, iter([(pos, neg, w, "tail-batch" if step % 2 == 0 else "head-batch")]), args)
+        for r, p in zip(ref, (m.entity_embedding, m.relation_embedding)):
+            r.grad = p.grad.detach().clone()          # same gradients into stock Adam
+        ropt.step()
+        for r, p in zip(ref, (m.entity_embedding, m.relation_embedding)):
+            assert relinf(p.detach().cpu().numpy(), r.detach().cpu().numpy()) < 1e-6
+    for r, p in zip(ref, (m.entity_embedding, m.relation_embedding)):
+        for key in ("exp_avg", "exp_avg_sq"):
+            assert relinf(opt.state[p][key].cpu().numpy(), ropt.state[r][key].cpu().numpy()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ filtered ranking
+def as_triples(a):
+    return [tuple(int(v) for v in row) for row in a]
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d", [12, 10])
+def test_filtered_ranks_vs_reference_golden(model, d):
+    g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
+    gamma, nentity = float(g["gamma"]), int(g["nentity"])
+    st = {"entity_embedding": g["eval_E"], "relation_embedding": g["eval_R"]}
+    if model == "pRotatE":
+        st["modulus"] = g["init_modulus"]
+    m = make_model(model, nentity, int(g["nrelation"]), d, gamma, st)
+    test, all_true = as_triples(g["eval_test"]), as_triples(g["eval_all_true"])
+    rows, ranks = [], []
+    for mode in ("head-batch", "tail-batch"):
+        r, s = m.filtered_ranks(test, all_true, mode, return_scores=True)
+        s = s.cpu().numpy()
+        # identical score matrix => identical ranks: the reference procedure (argsort) on OUR matrix
+        pos_col = [t[0] if mode == "head-batch" else t[2] for t in test]
+        np.testing.assert_array_equal(r, [O.rank_from_scores(row, p) for row, p in zip(s, pos_col)])
+        # bit-exact against the C oracle (same IEEE op sequence)
+        from knowledgegraphembedding_b200 import FilterIndex
+        off, ent = FilterIndex(all_true, nentity, int(g["nrelation"])).csr(test, mode)
+        cs = C.eval_scores(model, st, test, mode, gamma, O.embedding_range(gamma, d), off, ent)
+        np.testing.assert_array_equal(s.view(np.uint32), cs.view(np.uint32))
+        rows.append(s)
+        ranks.append(r)
+    assert score_err(model, np.concatenate(rows), g["eval_scores"], gamma) < TOL
+    np.testing.assert_array_equal(np.concatenate(ranks), g["eval_ranks"])        # ranks bit-exact vs the reference
+    metrics = KGE().test_step(m, test, all_true, ns(nentity=nentity, nrelation=int(g["nrelation"])))
+    assert list(metrics.keys()) == ["MRR", "MR", "HITS@1", "HITS@3", "HITS@10"]
+    np.testing.assert_allclose([metrics[k] for k in metrics], g["eval_metrics"], rtol=0, atol=1e-12)
+
+
+def test_countries_s1_end_to_end():
+    """Real dataset, reference-sampled batches: 4 train steps, AUC-PR (model.py:322-344) and filtered ranks."""
+    g = np.load(os.path.join(GOLDEN, "countries_S1.npz"))
+    d, gamma, nentity, nrel = int(g["d"]), float(g["gamma"]), int(g["nentity"]), int(g["nrelation"])
+    m = make_model("RotatE", nentity, nrel, d, gamma, {"entity_embedding": g["init_E"], "relation_embedding": g["init_R"]})
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+    regions = [int(r) for r in g["regions"]]
+    args = ns(negative_adversarial_sampling=True, countries=True, regions=regions, nentity=nentity, nrelation=nrel)
+    for step in range(4):
+        batch = (torch.from_numpy(g[f"pos{step}"].astype(np.int64)), torch.from_numpy(g[f"neg{step}"].astype(np.int64)),
+                 torch.from_numpy(g[f"w{step}"]), "tail-batch" if step % 2 == 0 else "head-batch")
+        log = KGE().train_step(m, opt, iter([batch]), args)
+        np.testing.assert_allclose([log["positive_sample_loss"], log["negative_sample_loss"], log["loss"]],
+                                   g["logs"][step], rtol=TOL)
+    E = m.entity_embedding.detach().cpu().numpy()
+    assert outlier_fraction(E, g["final_E"], TOL) < 1e-3
+    assert relinf(m.relation_embedding.detach().cpu().numpy(), g["final_R"]) < TOL
+    test = as_triples(g["test"])
+    all_true = as_triples(np.concatenate([g["train"], g["valid"], g["test"]]))
+    with torch.no_grad():
+        m.entity_embedding.copy_(torch.from_numpy(g["final_E"]))
+        m.relation_embedding.copy_(torch.from_numpy(g["final_R"]))
+    auc = KGE().test_step(m, test, all_true, args)["auc_pr"]
+    assert abs(auc - float(g["auc_pr"])) < 1e-6
+    args.countries = False
+    metrics = KGE().test_step(m, test, all_true, args)
+    ranks = np.concatenate([m.filtered_ranks(test, all_true, mode) for mode in ("head-batch", "tail-batch")])
+    np.testing.assert_array_equal(ranks, g["ranks"])
+    np.testing.assert_allclose([metrics[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")], g["metrics"],
+                               rtol=0, atol=1e-12)
+
+
+def test_wn18rr_real_dataset_ranks():
+    """wn18rr (40,943 entities, full train+valid+test filter): ranks vs the reference's and vs the C oracle."""
+    g = np.load(os.path.join(GOLDEN, "wn18rr_eval.npz"))
+    d, gamma, nentity, nrel = int(g["d"]), float(g["gamma"]), int(g["nentity"]), int(g["nrelation"])
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=int(g["seed"]))
+    st["entity_embedding"] = (st["entity_embedding"] * float(g["scale"])).astype(np.float32)
+    assert float(st["entity_embedding"].astype(np.float64).sum()) == float(g["table_checksum"])
+    m = make_model("RotatE", nentity, nrel, d, gamma, st)
+    test, all_true = as_triples(g["test"]), as_triples(g["all_true"])
+    from knowledgegraphembedding_b200 import FilterIndex
+    index = FilterIndex(all_true, nentity, nrel)
+    got = []
+    for mode in ("head-batch", "tail-batch"):
+        r = m.filtered_ranks(test, all_true, mode)
+        off, ent = index.csr(test, mode)
+        cs = C.eval_scores("RotatE", st, test, mode, gamma, O.embedding_range(gamma, d), off, ent)
+        np.testing.assert_array_equal(r, C.ranks_from_scores(cs, test, mode))           # bit-exact vs the oracle
+        got.append(r)
+    got = np.concatenate(got)
+    want = g["ranks"]
+    # vs the torch reference: libm sin/cos and reduction order differ, so a rank may move across a near tie only
+    assert np.max(np.abs(got - want)) <= 2 and np.mean(got != want) < 0.02
+    metrics = KGE().test_step(m, test, all_true, ns(nentity=nentity, nrelation=nrel))
+    np.testing.assert_allclose([metrics[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")], g["metrics"], rtol=2e-4)
+
+
+FULL = [("TransE", 14541, 237, 1000, 9.0), ("RotatE", 14951, 1345, 1000, 24.0), ("ComplEx", 40943, 11, 500, 200.0),
+        ("RotatE", 123182, 37, 500, 24.0), ("pRotatE", 14951, 1345, 1000, 24.0), ("DistMult", 14951, 1345, 2000, 500.0)]
+
+
+@pytest.mark.parametrize("model,nentity,nrel,d,gamma", FULL)
+def test_full_size_eval_bit_exact_vs_c_oracle(model, nentity, nrel, d, gamma):
+    """BASELINE.json config shapes: all-entity scores (+filter bias) and ranks of a query sample are bit-identical
+    to the C oracle; ranks also equal the argsort procedure on the same matrix."""
+    de, dr = FLAGS[model]
+    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
+    st["entity_embedding"] = (st["entity_embedding"] * 3.0).astype(np.float32)
+    rng = np.random.RandomState(2)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(200))) for _ in range(30000)})
+    test = [all_true[i] for i in rng.choice(len(all_true), 24, replace=False)]
+    m = make_model(model, nentity, nrel, d, gamma, st)
+    from knowledgegraphembedding_b200 import FilterIndex
+    index = FilterIndex(all_true, nentity, nrel)
+    rho = O.embedding_range(gamma, d)
+    for mode in ("head-batch", "tail-batch"):
+        r, s = m.filtered_ranks(test, all_true, mode, return_scores=True)
+        s = s.cpu().numpy()
+        off, ent = index.csr(test, mode)
+        cs = C.eval_scores(model, st, test, mode, gamma, rho, off, ent)
+        np.testing.assert_array_equal(s.view(np.uint32), cs.view(np.uint32))
+        np.testing.assert_array_equal(r, C.ranks_from_scores(cs, test, mode))
+        pos_col = [t[0] if mode == "head-batch" else t[2] for t in test]
+        np.testing.assert_array_equal(r[:6], [O.rank_from_scores(row, p) for row, p in zip(s[:6], pos_col[:6])])
+
+
+def test_entity_sharded_counts_sum_to_full():
+    """The multi-GPU eval path: counts over disjoint entity slices add up to the single-GPU ranks (bit-exact)."""
+    import ctypes
+    from knowledgegraphembedding_b200 import _lib, FilterIndex, shard_bounds
+    from knowledgegraphembedding_b200.model import _ptr, _stream
+    model, nentity, nrel, d, gamma = "RotatE", 5003, 17, 64, 12.0
+    st = O.init_tables(model, nentity, nrel, d, gamma, True, False, seed=4)
+    m = make_model(model, nentity, nrel, d, gamma, st)
+    rng = np.random.RandomState(0)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(50))) for _ in range(4000)})
+    test = all_true[:100]
+    for mode in ("head-batch", "tail-batch"):
+        full = m.filtered_ranks(test, all_true, mode)
+        dev = m.entity_embedding.device
+        q = torch.tensor(test, dtype=torch.int64, device=dev)
+        off, ent = FilterIndex(all_true, nentity, nrel).csr(test, mode)
+        d_off, d_ent = torch.from_numpy(off).to(dev), torch.from_numpy(ent).to(dev)
+        words = (nentity + 31) // 32
+        bits = torch.zeros(len(test) * words, dtype=torch.int32, device=dev)
+        qvec = torch.empty(len(test) * m.entity_dim, device=dev)
+        pos = torch.empty(len(test), device=dev)
+        desc, mid, stt = m._descriptor(), _lib.MODE_IDS[mode], _stream(dev)
+        _lib.call("kge_eval_filter_bits", _ptr(d_off), _ptr(d_ent), len(test), nentity, _ptr(bits), stt)
+        _lib.call("kge_eval_query_vectors", ctypes.byref(desc), mid, _ptr(q), len(test), _ptr(qvec), None, stt)
+        _lib.call("kge_eval_positive_scores", ctypes.byref(desc), mid, _ptr(qvec), _ptr(q), len(test), None, _ptr(pos), stt)
+        total = torch.zeros(len(test), dtype=torch.int32, device=dev)
+        for rank in range(8):
+            b, e = shard_bounds(nentity, rank, 8)
+            part = torch.zeros(len(test), dtype=torch.int32, device=dev)
+            _lib.call("kge_eval_count_ranks", ctypes.byref(desc), mid, _ptr(qvec), _ptr(q), len(test), None, _ptr(pos),
+                      _ptr(bits), b, e, _ptr(part), None, stt)
+            total += part
+        np.testing.assert_array_equal(total.cpu().numpy() + 1, full)
+
+
+# ------------------------------------------------------------------------------------------------ API behaviour
+def test_api_errors_and_state_dict():
+    K = KGE()
+    with pytest.raises(ValueError, match="model Foo not supported"):
+        K("Foo", 10, 2, 4, 1.0)
+    with pytest.raises(ValueError, match="RotatE should use --double_entity_embedding"):
+        K("RotatE", 10, 2, 4, 1.0)
+    with pytest.raises(ValueError, match="ComplEx should use"):
+        K("ComplEx", 10, 2, 4, 1.0, double_entity_embedding=True)
+    m = K("pRotatE", 10, 2, 4, 6.0).cuda()
+    assert list(m.state_dict().keys()) == ["gamma", "embedding_range", "entity_embedding", "relation_embedding", "modulus"]
+    assert [n for n, p in m.named_parameters() if p.requires_grad] == ["entity_embedding", "relation_embedding", "modulus"]
+    with pytest.raises(ValueError, match="mode sideways not supported"):
+        m((torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 4, dtype=torch.long)), "sideways")
+    m2 = K("pRotatE", 10, 2, 4, 6.0)
+    m2.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    m2 = m2.cuda()
+    s = torch.tensor([[1, 0, 2], [3, 1, 4]])
+    assert torch.equal(m(s), m2(s))
+    with pytest.raises(IndexError):
+        m(torch.tensor([[1, 0, 10]]))          # entity id == nentity
+        m._raise_if_bad_index()
+    cpu = K("TransE", 10, 2, 4, 6.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cpu(s)
+
+
+def test_ragged_last_batch_and_non_adam_optimizer():
+    """The last batch of an epoch is smaller than -b (run.py:246-260 has no drop_last); any optimizer object works."""
+    torch.manual_seed(1)
+    m = make_model("RotatE", 300, 5, 20, 6.0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    args = ns(negative_adversarial_sampling=True)
+    for B in (16, 5, 1):
+        pos = torch.stack([torch.randint(300, (B,)), torch.randint(5, (B,)), torch.randint(300, (B,))], 1)
+        log = KGE().train_step(m, opt, iter([(pos, torch.randint(300, (B, 7)), torch.rand(B) + 0.1, "head-batch")]), args)
+        assert np.isfinite(log["loss"])
+    before = m.entity_embedding.detach().clone()
+    sgd = torch.optim.SGD(m.parameters(), lr=0.1)
+    pos = torch.stack([torch.randint(300, (8,)), torch.randint(5, (8,)), torch.randint(300, (8,))], 1)
+    KGE().train_step(m, sgd, iter([(pos, torch.randint(300, (8, 7)), torch.rand(8) + 0.1, "tail-batch")]), args)
+    torch.testing.assert_close(m.entity_embedding.detach(), before - 0.1 * m.entity_embedding.grad)

@@ -1,0 +1,126 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/kge_b200.h declares,
+argument errors map to the reference's exceptions, shard arithmetic, and the gloo world_size-2 data path."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from knowledgegraphembedding_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "kge_b200.h")).read()
+    declared = set(re.findall(r"\b(kge_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.kge_abi_version() == 1
+
+
+def test_abi_argument_errors_without_a_gpu():
+    from knowledgegraphembedding_b200 import _lib
+    lib = _lib.load()
+    desc = _lib.KgeModelStruct(model=7, device=0, nentity=4, nrelation=2, hidden_dim=4, entity_dim=4, relation_dim=4,
+                               gamma=1.0, embedding_range=0.1, entity=8, relation=8, modulus=None)
+    rc = lib.kge_score_forward(ctypes.byref(desc), 0, None, None, 1, 1, None, None, None)
+    assert rc == _lib.ERR_INVALID and b"model 7 not supported" in lib.kge_last_error()
+    desc.model = _lib.ROTATE
+    rc = lib.kge_score_forward(ctypes.byref(desc), 0, None, None, 1, 1, None, None, None)
+    assert rc == _lib.ERR_INVALID and b"RotatE should use --double_entity_embedding" in lib.kge_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+
+
+def test_model_shell_matches_reference_surface():
+    from knowledgegraphembedding_b200 import KGEModel
+    m = KGEModel(model_name="RotatE", nentity=7, nrelation=3, hidden_dim=4, gamma=12.0, double_entity_embedding=True)
+    assert [n for n, _ in m.named_parameters()] == ["gamma", "embedding_range", "entity_embedding", "relation_embedding"]
+    assert m.entity_embedding.shape == (7, 8) and m.relation_embedding.shape == (7 - 4, 4)
+    assert not m.gamma.requires_grad and not m.embedding_range.requires_grad
+    rho = (12.0 + 2.0) / 4
+    assert abs(m.embedding_range.item() - rho) < 1e-6 and m.entity_embedding.abs().max().item() <= rho
+    assert callable(m.train_step) and callable(m.test_step)
+    for name in ("TransE", "DistMult", "ComplEx", "RotatE", "pRotatE"):
+        assert callable(getattr(m, name))
+    p = KGEModel("pRotatE", 7, 3, 4, 12.0)
+    assert p.modulus.shape == (1, 1) and abs(p.modulus.item() - 0.5 * rho) < 1e-6
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, dtype=torch.long))
+
+
+def test_dropin_module_name():
+    code = ("import sys; sys.path.insert(0, %r); import model; "
+            "print(model.KGEModel.__module__)") % os.path.join(ROOT, "knowledgegraphembedding_b200", "dropin")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == "knowledgegraphembedding_b200.model"
+
+
+def test_shard_bounds_cover_exactly():
+    from knowledgegraphembedding_b200 import shard_bounds
+    for total in (0, 1, 7, 1024, 14951, 123182):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from knowledgegraphembedding_b200 import shard_bounds
+from knowledgegraphembedding_b200.model import _dist
+from oracle import kge_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank, world = _dist()
+assert (rank, world) == (int(sys.argv[1]), 2)
+# batch-sharded training: per-rank oracle gradients of the row slice, all-reduced, equal the full-batch gradients
+nentity, nrel, d, gamma, B, N = 60, 4, 8, 6.0, 10, 6
+st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=0)
+rng = np.random.RandomState(0)
+pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
+neg = rng.randint(nentity, size=(B, N)); w = (rng.rand(B) + 0.1).astype(np.float32)
+neg_s = O.forward("RotatE", st, (pos, neg), "tail-batch", gamma, d); pos_s = O.forward("RotatE", st, pos, "single", gamma, d)
+_, _, _, dneg, dpos = O.loss_and_dscore(neg_s, pos_s, w, True, 1.0, False)
+b, e = shard_bounds(B, rank, world)
+g = O.score_backward("RotatE", st, (pos[b:e], neg[b:e]), "tail-batch", dneg[b:e], gamma, d)
+g2 = O.score_backward("RotatE", st, pos[b:e], "single", dpos[b:e], gamma, d)
+flat = torch.from_numpy(np.concatenate([(g[k] + g2[k]).ravel() for k in ("entity_embedding", "relation_embedding")]))
+dist.all_reduce(flat)
+full = O.score_backward("RotatE", st, (pos, neg), "tail-batch", dneg, gamma, d)
+full2 = O.score_backward("RotatE", st, pos, "single", dpos, gamma, d)
+want = np.concatenate([(full[k] + full2[k]).ravel() for k in ("entity_embedding", "relation_embedding")])
+assert np.allclose(flat.numpy(), want, rtol=1e-9, atol=1e-12)
+# entity-sharded evaluation: integer counts over the two entity slices add up to rank - 1
+all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(nentity))) for _ in range(80)})
+test = all_true[:6]
+ranks, scores = O.filtered_ranks("RotatE", st, test, all_true, nentity, gamma, d, return_scores=True)
+eb, ee = shard_bounds(nentity, rank, world)
+cols = [t[0] for t in test] + [t[2] for t in test]
+cnt = torch.tensor([int(sum((row[j] > row[p]) or (row[j] == row[p] and j < p) for j in range(eb, ee)))
+                    for row, p in zip(scores, cols)], dtype=torch.int32)
+dist.all_reduce(cnt)
+assert np.array_equal(cnt.numpy() + 1, ranks)
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_world_size_2_gloo_data_path(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0 and out.strip().endswith("ok"), err[-2000:]
