@@ -101,9 +101,9 @@ def test_public_score_methods(model):
         else:
             head, tail = E[pos[:, 0]].unsqueeze(1), E[neg.view(-1)].view(neg.shape[0], neg.shape[1], -1)
         s = fn(head, R[pos[:, 1]].unsqueeze(1), tail, mode)
-        assert score_err(model, s.cpu().numpy(), g["score_" + mode], gamma) < TOL
+        assert score_err(model, s.detach().cpu().numpy(), g["score_" + mode], gamma) < TOL
     s = fn(E[pos[:, 0]].unsqueeze(1), R[pos[:, 1]].unsqueeze(1), E[pos[:, 2]].unsqueeze(1), "single")
-    assert score_err(model, s.cpu().numpy(), g["score_single"], gamma) < TOL
+    assert score_err(model, s.detach().cpu().numpy(), g["score_single"], gamma) < TOL
 
 
 # ------------------------------------------------------------------------------------------------ train_step
