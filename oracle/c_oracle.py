@@ -114,3 +114,43 @@ def ranks_from_scores(scores, queries, mode):
     load().ko_ranks_from_scores(_p(s), ctypes.c_int64(s.shape[0]), ctypes.c_int64(s.shape[1]), _p(q),
                                 int(mode == "head-batch"), _p(out))
     return out
+
+
+class TrainState:
+    """Tables + Adam moments for ko_train_step (mirrors oracle.kge_oracle.TrainState)."""
+
+    def __init__(self, model_name, state, gamma, hidden_dim):
+        from . import kge_oracle as O
+        self.model_name, self.gamma, self.hidden_dim = model_name, float(gamma), int(hidden_dim)
+        self.rho = O.embedding_range(gamma, hidden_dim)
+        self.state = {k: np.array(v, dtype=np.float32) for k, v in state.items()}
+        self.reset_optimizer()
+
+    def reset_optimizer(self):
+        self.step = 0
+        self.m = {k: np.zeros_like(v) for k, v in self.state.items()}
+        self.v = {k: np.zeros_like(v) for k, v in self.state.items()}
+        self.grads = {k: np.zeros_like(v) for k, v in self.state.items()}
+
+
+def train_step(ts, batch, *, lr, adversarial, alpha=1.0, uni_weight=False, regularization=0.0, return_grads=False):
+    positive, negative, weight, mode = batch
+    pos, neg = _i64(positive), _i64(negative)
+    w = None if uni_weight else _f32(weight)
+    E, R = ts.state["entity_embedding"], ts.state["relation_embedding"]
+    M = ts.state.get("modulus")
+    out = np.zeros(4, dtype=np.float32)
+    ts.step += 1
+    k = ("entity_embedding", "relation_embedding", "modulus")
+    load().ko_train_step(
+        MODEL_IDS[ts.model_name], MODE_IDS[mode], _p(E), _p(R), _p(M), ctypes.c_int64(E.shape[0]),
+        ctypes.c_int64(R.shape[0]), E.shape[1], R.shape[1], ctypes.c_float(ts.gamma), ctypes.c_float(ts.rho), _p(pos),
+        _p(neg), _p(w), ctypes.c_int64(pos.shape[0]), ctypes.c_int64(neg.shape[1]), int(bool(adversarial)),
+        ctypes.c_float(alpha), ctypes.c_double(regularization), ctypes.c_double(lr), int(ts.step),
+        _p(ts.m[k[0]]), _p(ts.v[k[0]]), _p(ts.m[k[1]]), _p(ts.v[k[1]]),
+        _p(ts.m.get(k[2])), _p(ts.v.get(k[2])), _p(ts.grads[k[0]]), _p(ts.grads[k[1]]), _p(ts.grads.get(k[2])), _p(out))
+    log = {}
+    if regularization != 0.0:
+        log["regularization"] = float(out[3])
+    log.update(positive_sample_loss=float(out[0]), negative_sample_loss=float(out[1]), loss=float(out[2]))
+    return (log, {n: g.copy() for n, g in ts.grads.items()}) if return_grads else log

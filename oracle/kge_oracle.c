@@ -224,3 +224,200 @@ void ko_ranks_from_scores(const float *scores, int64_t Q, int64_t nentity, const
     ranks[i] = 1 + c;
   }
 }
+
+/* ================================================================================================
+ * KGEModel.train_step (model.py:251-312) on one batch: scores, self-adversarial / uniform loss,
+ * closed-form backward (what autograd computes at model.py:301; formulas of SURVEY.md 8a row G1),
+ * optional L3 regulariser, dense Adam (torch/optim/adam.py defaults as built at run.py:266-269).
+ * Parallel over positive rows with OpenMP; gradient scatter uses atomic adds like index_add_.
+ * ================================================================================================ */
+static float logsigmoidf_(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+static float sigmoidf_(float x) { float e = expf(-fabsf(x)); return x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e); }
+
+static inline void atomic_addf(float *p, float v) {
+#pragma omp atomic
+  *p += v;
+}
+
+/* d(score)/d(sum over k) */
+static float dsum(int model, float g, float modulus) {
+  return (model == TRANSE || model == ROTATE) ? -g : (model == PROTATE ? -g * modulus : g);
+}
+
+/* backward of one candidate row: adds dL/dx into gx (atomically), accumulates dL/dq into dq; returns sum|sin| for
+ * pRotatE's modulus gradient */
+static float row_backward(int model, int head, const float *q, const float *x, int d, float scale, float go,
+                          float *dq, float *gx) {
+  float vs = 0.f;
+  for (int k = 0; k < d; ++k) {
+    switch (model) {
+      case TRANSE: {
+        float e = head ? x[k] + q[k] : q[k] - x[k];
+        float de = e > 0.f ? go : (e < 0.f ? -go : 0.f);              /* sign(0) = 0 */
+        dq[k] += de;
+        atomic_addf(gx + k, head ? de : -de);
+        break;
+      }
+      case DISTMULT:
+        dq[k] += go * x[k];
+        atomic_addf(gx + k, go * q[k]);
+        break;
+      case COMPLEX_:
+        dq[k] += go * x[k]; dq[d + k] += go * x[d + k];
+        atomic_addf(gx + k, go * q[k]); atomic_addf(gx + d + k, go * q[d + k]);
+        break;
+      case ROTATE: {
+        float a = q[k] - x[k], b = q[d + k] - x[d + k];
+        float m = sqrtf(a * a + b * b);
+        float da = m > 0.f ? go * a / m : 0.f, db = m > 0.f ? go * b / m : 0.f;   /* norm subgradient 0 at 0 */
+        dq[k] += da; dq[d + k] += db;
+        atomic_addf(gx + k, -da); atomic_addf(gx + d + k, -db);
+        break;
+      }
+      default: {
+        float px = x[k] / scale;
+        float e = head ? px + q[k] : q[k] - px;
+        float s = sinf(e), c = cosf(e);
+        float de = s > 0.f ? go * c : (s < 0.f ? -go * c : 0.f);
+        dq[k] += de;
+        atomic_addf(gx + k, (head ? de : -de) / scale);
+        vs += fabsf(s);
+      }
+    }
+  }
+  return vs;
+}
+
+/* chain rule dL/dq -> fixed entity row F and relation row Rr (atomically added) */
+static void chain_backward(int model, int head, const float *F, const float *Rr, const float *dq, int d, float scale,
+                           float *gF, float *gR) {
+  for (int k = 0; k < d; ++k) {
+    switch (model) {
+      case TRANSE:
+        atomic_addf(gR + k, dq[k]); atomic_addf(gF + k, head ? -dq[k] : dq[k]);
+        break;
+      case DISTMULT:
+        atomic_addf(gF + k, dq[k] * Rr[k]); atomic_addf(gR + k, dq[k] * F[k]);
+        break;
+      case COMPLEX_: {
+        float fr = F[k], fi = F[d + k], rr = Rr[k], ri = Rr[d + k], a = dq[k], b = dq[d + k];
+        if (head) {
+          atomic_addf(gR + k, a * fr + b * fi); atomic_addf(gR + d + k, a * fi - b * fr);
+          atomic_addf(gF + k, a * rr - b * ri); atomic_addf(gF + d + k, a * ri + b * rr);
+        } else {
+          atomic_addf(gF + k, a * rr + b * ri); atomic_addf(gF + d + k, -a * ri + b * rr);
+          atomic_addf(gR + k, a * fr + b * fi); atomic_addf(gR + d + k, -a * fi + b * fr);
+        }
+        break;
+      }
+      case ROTATE: {
+        float fr = F[k], fi = F[d + k], a = dq[k], b = dq[d + k], s, c, dc, ds;
+        sincos_cw(Rr[k] / scale, &s, &c);
+        if (head) {
+          atomic_addf(gF + k, a * c - b * s); atomic_addf(gF + d + k, a * s + b * c);
+          dc = a * fr + b * fi; ds = a * fi - b * fr;
+        } else {
+          atomic_addf(gF + k, a * c + b * s); atomic_addf(gF + d + k, -a * s + b * c);
+          dc = a * fr + b * fi; ds = -a * fi + b * fr;
+        }
+        atomic_addf(gR + k, (-dc * s + ds * c) / scale);
+        break;
+      }
+      default: {
+        float v = dq[k] / scale;
+        atomic_addf(gR + k, v); atomic_addf(gF + k, head ? -v : v);
+      }
+    }
+  }
+}
+
+static void adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int step, double lr, double b1,
+                       double b2, double eps) {
+  const float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2), feps = (float)eps;
+  const float step_size = (float)(-(lr / (1.0 - pow(b1, step)))), bc2s = (float)sqrt(1.0 - pow(b2, step));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    m[i] = m[i] + (g[i] - m[i]) * w1;
+    v[i] = v[i] * fb2 + w2 * g[i] * g[i];
+    p[i] = p[i] + step_size * (m[i] / (sqrtf(v[i]) / bc2s + feps));
+  }
+}
+
+/* One train step.  mode: 1 head-batch, 2 tail-batch.  weight may be NULL (--uni_weight).  Tables, moments and grads
+ * are updated in place; out[0..3] = positive_sample_loss, negative_sample_loss, loss, regularization. */
+void ko_train_step(int model, int mode, float *E, float *R, float *modulus, int64_t nentity, int64_t nrelation, int De,
+                   int Dr, float gamma, float rho, const int64_t *positive, const int64_t *negative,
+                   const float *weight, int64_t B, int64_t N, int adversarial, float alpha, double reg, double lr,
+                   int step, float *mE, float *vE, float *mR, float *vR, float *mM, float *vM, float *gE, float *gR,
+                   float *gM, float *out) {
+  const int d = kdim(model, De);
+  const int head = mode == 1;
+  const float scale = phase_scale(model, rho);
+  const float mod = modulus ? modulus[0] : 1.f;
+  memset(gE, 0, sizeof(float) * nentity * De);
+  memset(gR, 0, sizeof(float) * nrelation * Dr);
+  if (gM) gM[0] = 0.f;
+  double wsum = 0.0;
+  for (int64_t b = 0; b < B; ++b) wsum += weight ? weight[b] : 1.0;
+  double pos_acc = 0.0, neg_acc = 0.0, gmod_acc = 0.0;
+#pragma omp parallel reduction(+ : pos_acc, neg_acc, gmod_acc)
+  {
+    float *q = (float *)malloc(sizeof(float) * De), *dq = (float *)malloc(sizeof(float) * De);
+    float *s = (float *)malloc(sizeof(float) * N), *g = (float *)malloc(sizeof(float) * N);
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t b = 0; b < B; ++b) {
+      const int64_t h = positive[3 * b], r = positive[3 * b + 1], t = positive[3 * b + 2];
+      const float u = (float)((weight ? weight[b] : 1.0) / wsum);
+      /* negatives (model.py:268-275) */
+      const int64_t f = head ? t : h;
+      build_q(model, head, E + f * De, R + r * Dr, d, scale, q);
+      float zmax = -INFINITY;
+      for (int64_t n = 0; n < N; ++n) {
+        s[n] = score_row(model, head, q, E + negative[b * N + n] * De, d, gamma, scale, mod);
+        if (adversarial && s[n] * alpha > zmax) zmax = s[n] * alpha;
+      }
+      float zsum = 0.f;
+      for (int64_t n = 0; n < N; ++n) { g[n] = adversarial ? expf(s[n] * alpha - zmax) : 1.f; zsum += g[n]; }
+      float row = 0.f;
+      for (int64_t n = 0; n < N; ++n) {
+        const float w = g[n] / zsum;
+        row += w * logsigmoidf_(-s[n]);
+        g[n] = 0.5f * u * w * sigmoidf_(s[n]);
+      }
+      neg_acc += (double)((weight ? weight[b] : 1.f) * row);
+      memset(dq, 0, sizeof(float) * De);
+      for (int64_t n = 0; n < N; ++n) {
+        const int64_t c = negative[b * N + n];
+        const float vs = row_backward(model, head, q, E + c * De, d, scale, dsum(model, g[n], mod), dq, gE + c * De);
+        gmod_acc += (double)(-g[n] * vs);
+      }
+      chain_backward(model, head, E + f * De, R + r * Dr, dq, d, scale, gE + f * De, gR + r * Dr);
+      /* positive triple, 'single' mode = the non-head-batch association (model.py:277-279) */
+      build_q(model, 0, E + h * De, R + r * Dr, d, scale, q);
+      const float sp = score_row(model, 0, q, E + t * De, d, gamma, scale, mod);
+      pos_acc += (double)((weight ? weight[b] : 1.f) * logsigmoidf_(sp));
+      const float gp = -0.5f * u * sigmoidf_(-sp);
+      memset(dq, 0, sizeof(float) * De);
+      const float vs = row_backward(model, 0, q, E + t * De, d, scale, dsum(model, gp, mod), dq, gE + t * De);
+      gmod_acc += (double)(-gp * vs);
+      chain_backward(model, 0, E + h * De, R + r * Dr, dq, d, scale, gE + h * De, gR + r * Dr);
+    }
+    free(q); free(dq); free(s); free(g);
+  }
+  if (gM) gM[0] = (float)gmod_acc;
+  const float pl = (float)(-pos_acc / wsum), nl = (float)(-neg_acc / wsum);
+  float regv = 0.f;
+  if (reg != 0.0) {                                  /* model.py:290-296 */
+    double r3 = 0.0;
+    const int64_t nE = nentity * De, nR = nrelation * Dr;
+#pragma omp parallel for reduction(+ : r3) schedule(static)
+    for (int64_t i = 0; i < nE; ++i) { float ax = fabsf(E[i]); r3 += (double)(ax * ax * ax); gE[i] += (float)(3.0 * reg) * E[i] * ax; }
+#pragma omp parallel for reduction(+ : r3) schedule(static)
+    for (int64_t i = 0; i < nR; ++i) { float ax = fabsf(R[i]); r3 += (double)(ax * ax * ax); gR[i] += (float)(3.0 * reg) * R[i] * ax; }
+    regv = (float)(reg * r3);
+  }
+  out[0] = pl; out[1] = nl; out[2] = (pl + nl) / 2.f + regv; out[3] = regv;
+  adam_dense(E, gE, mE, vE, nentity * De, step, lr, 0.9, 0.999, 1e-8);      /* model.py:303 */
+  adam_dense(R, gR, mR, vR, nrelation * Dr, step, lr, 0.9, 0.999, 1e-8);
+  if (modulus) adam_dense(modulus, gM, mM, vM, 1, step, lr, 0.9, 0.999, 1e-8);
+}

@@ -97,3 +97,44 @@ def test_full_width_rows_agree_with_numpy_oracle():
             a = C.forward(model, st, (pos, neg), mode, gamma, rho)
             b = O.forward(model, st, (pos, neg), mode, gamma, d)
             assert relinf(a, b) < 1e-5, (model, mode)
+
+
+CFGS = {
+    "adv_sub": dict(adversarial=True, alpha=0.7, uni_weight=False),
+    "adv_uni": dict(adversarial=True, alpha=1.0, uni_weight=True),
+    "mean_sub": dict(adversarial=False, uni_weight=False),
+    "adv_sub_reg": dict(adversarial=True, alpha=1.0, uni_weight=False, regularization=1e-3),
+}
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("d", [12, 10])
+@pytest.mark.parametrize("cfg", list(CFGS))
+def test_train_steps_match_reference_golden(model, d, cfg):
+    """ko_train_step over the 4 golden steps (losses, first-step grads, final tables) -- the function bench.py times
+    as the CPU baseline."""
+    g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
+    st = {"entity_embedding": g["init_entity_embedding"], "relation_embedding": g["init_relation_embedding"]}
+    if model == "pRotatE":
+        st["modulus"] = g["init_modulus"]
+    ts = C.TrainState(model, st, float(g["gamma"]), d)
+    lr = 1e-3
+    for step in range(4):
+        if step == 2:
+            lr /= 10
+            ts.reset_optimizer()
+        batch = (g[f"train_{cfg}_pos{step}"], g[f"train_{cfg}_neg{step}"], g[f"train_{cfg}_w{step}"],
+                 "tail-batch" if step % 2 == 0 else "head-batch")
+        log, grads = C.train_step(ts, batch, lr=lr, return_grads=True, **CFGS[cfg])
+        ref = g[f"train_{cfg}_logs"][step]
+        got = [log.get("regularization", 0.0), log["positive_sample_loss"], log["negative_sample_loss"], log["loss"]]
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7)
+        if step == 0:
+            assert relinf(grads["entity_embedding"], g[f"train_{cfg}_gE0"]) < 1e-5
+            assert relinf(grads["relation_embedding"], g[f"train_{cfg}_gR0"]) < 1e-5
+            if model == "pRotatE":
+                assert relinf(grads["modulus"], g[f"train_{cfg}_gM0"]) < 1e-5
+    assert relinf(ts.state["entity_embedding"], g[f"train_{cfg}_E"]) < 1e-5
+    assert relinf(ts.state["relation_embedding"], g[f"train_{cfg}_R"]) < 1e-5
+    if model == "pRotatE":
+        assert relinf(ts.state["modulus"], g[f"train_{cfg}_M"]) < 1e-5
