@@ -438,9 +438,16 @@ class KGEModel(nn.Module):
             _lib.call("kge_eval_query_vectors", ctypes.byref(desc), m, _ptr(queries), Q, _ptr(qvec), _ptr(err), st)
             _lib.call("kge_eval_positive_scores", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), st)
+            events = self._ws.get('eval_events')            # bench.py: CUDA events around the dominant kernel
+            if events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
                       _ptr(scores[lo:lo + Q]) if scores is not None else None, st)
+            if events is not None:
+                ev1.record()
+                events.append((ev0, ev1))
         if world > 1:
             torch.distributed.all_reduce(counts_all)
         ranks = (counts_all.to(torch.int64) + 1).cpu().numpy()
