@@ -73,7 +73,7 @@ int kge_score_forward(const kge_model_t *m, int mode, const int64_t *positive, c
 int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
                        int64_t B, int64_t N, const float *dscore,
                        float *grad_entity, float *grad_relation, float *grad_modulus,
-                       int32_t *err_flag, void *stream);
+                       void *workspace, int64_t workspace_bytes, int32_t *err_flag, void *stream);
 
 /* ---- fused train pass: model.py:268-288 (scores, self-adversarial / uniform loss) + model.py:301 ----
  * One launch per call: gather+score the N candidates of each positive row, softmax-weighted
@@ -82,12 +82,19 @@ int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, 
  *   weight: subsampling_weight [B_total] or NULL (= --uni_weight);  weight_sum: device scalar sum(weight)
  *   row_begin/row_count: this rank's slice of the batch (row_count == B_total on one GPU)
  *   row_loss [B_total]: per-row  sum_j w_ij logsig(-s_ij)  (NEG) or logsig(s_i) (POSITIVE)
- *   score_out: optional [row_count, N] copy of the scores (tests), may be NULL                   */
+ *   score_out: optional [row_count, N] copy of the scores (tests), may be NULL
+ *   workspace: kge_train_workspace_bytes(m, row_count, N) bytes of device scratch, or NULL        */
 int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
                    const int64_t *positive, const int64_t *negative, const float *weight,
                    const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
                    int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
-                   float *grad_modulus, float *score_out, int32_t *err_flag, void *stream);
+                   float *grad_modulus, float *score_out, void *workspace, int64_t workspace_bytes,
+                   int32_t *err_flag, void *stream);
+
+/* Device scratch for the single-read backward (kge_train_rows / kge_score_backward): per-pair dL/ds, the query
+ * table, and the counting-sort arrays of the entity-major pass.  With workspace == NULL (or too small) the
+ * two-sweep atomic kernel is used instead; results agree to rounding.                                        */
+int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N);
 
 /* cudaMemsetAsync(ptr, 0, bytes): clears the gradient workspace at the top of a train step (the
  * reference's optimizer.zero_grad() at model.py:259 drops the grads, autograd re-creates zero tables). */

@@ -7,9 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libkge_b200.so")
 SOURCES = ["kge_train.cu", "kge_optim.cu", "kge_eval.cu"]
-HEADERS = ["kge_common.cuh", "kge_rows.cuh", "kge_math.h", os.path.join("..", "..", "include", "kge_b200.h")]
+HEADERS = ["kge_common.cuh", "kge_rows.cuh", "kge_train_split.cuh", "kge_math.h", os.path.join("..", "..", "include", "kge_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886"]
 
 
 def _nvcc():

@@ -91,9 +91,17 @@ __device__ __forceinline__ void red_add1(float *p, float a) {
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+
+// 1/sqrt(x) on the MUFU pipe, one instruction (flush-to-zero: callers guard x >= FLT_MIN)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+constexpr float kFltMin = 1.17549435e-38f;
 
 __device__ __forceinline__ float log_sigmoid(float x) {     // F.logsigmoid: min(x,0) - log1p(exp(-|x|))
   return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));

@@ -85,7 +85,7 @@ __device__ __forceinline__ float op_backward(float q0, float q1, float x0, float
   } else if constexpr (OP == OP_CDIST) {
     float a = q0 - x0, b = q1 - x1;
     float m2 = a * a + b * b;
-    float inv = m2 > 0.f ? go * rsqrtf(m2) : 0.f;          // norm subgradient is 0 at the origin
+    float inv = m2 >= kFltMin ? go * rsqrt_fast(m2) : 0.f; // norm subgradient is 0 at the origin
     dq0 = a * inv; dq1 = b * inv; dx0 = -dq0; dx1 = -dq1;
     return 0.f;
   } else {
@@ -99,6 +99,38 @@ __device__ __forceinline__ float op_backward(float q0, float q1, float x0, float
     return fabsf(s);
   }
 }
+
+// forward element value together with u = d(value)/dq, so that dL/dq = (dL/dsum) * u.  Used by the single-read
+// path: sweep 1 computes value and u once, u is parked in the shared-memory slot, sweep 2 only does acc += c * u.
+template <int OP>
+__device__ __forceinline__ float op_unit(float q0, float q1, float x0, float x1, float scale, float &u0, float &u1) {
+  u1 = 0.f;
+  if constexpr (OP == OP_SUBABS || OP == OP_ADDABS) {
+    const float e = OP == OP_SUBABS ? q0 - x0 : x0 + q0;
+    u0 = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+    return fabsf(e);
+  } else if constexpr (OP == OP_MUL) {
+    u0 = x0;
+    return q0 * x0;
+  } else if constexpr (OP == OP_CMUL) {
+    u0 = x0; u1 = x1;
+    return q0 * x0 + q1 * x1;
+  } else if constexpr (OP == OP_CDIST) {
+    const float a = q0 - x0, b = q1 - x1;
+    const float m2 = a * a + b * b;
+    const float inv = m2 >= kFltMin ? rsqrt_fast(m2) : 0.f; // norm subgradient 0 at the origin
+    u0 = a * inv; u1 = b * inv;
+    return m2 * inv;                                       // = sqrt(m2)
+  } else {
+    const float px = x0 / scale;
+    const float e = OP == OP_SUBSIN ? q0 - px : px + q0;
+    float sn, cs;
+    sincosf(e, &sn, &cs);
+    u0 = sn > 0.f ? cs : (sn < 0.f ? -cs : 0.f);
+    return fabsf(sn);
+  }
+}
+__host__ __device__ constexpr bool op_unit_is_x(int op) { return op == OP_MUL || op == OP_CMUL; }
 
 template <int MODEL>
 __device__ __forceinline__ float finish_score(float acc, float gamma, float modulus) {

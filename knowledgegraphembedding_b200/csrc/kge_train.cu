@@ -318,15 +318,16 @@ __global__ void __launch_bounds__(512, 1) row_kernel_tma(const RowArgs a) {
   const int Dq = a.De;
   const int Dq4 = (Dq + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  float *q = smem;
+  // layout: [slots: nwarps x 2 x De | q | dq | sc | gg | scratch(32) | mbarriers]; every pointer is derived from
+  // `smem` by element offsets so that the compiler keeps the shared address space (LDS, not generic LD)
+  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;
+  float *q = smem + (size_t)(2 * nwarps) * a.De;
   float *dq = q + Dq4;
   float *sc = dq + Dq4;
   float *gg = sc + (a.do_loss ? a.N : 0);
   float *scratch = gg + (a.do_loss ? a.N : 0);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32 + ((a.do_loss ? 2 * a.N : 0) & 1));   // 8-byte aligned
-  float *slots = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(bars + 2 * nwarps) + 127) & ~(uintptr_t)127);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
   const uint32_t rowbytes = (uint32_t)a.De * 4u;
-  float *slot0 = slots + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
   uint32_t par0 = 0, par1 = 0;
   int64_t id0 = 0, id1 = 0;
@@ -539,25 +540,90 @@ __global__ void __launch_bounds__(512, 1) row_kernel_tma(const RowArgs a) {
   }
 }
 
+}  // namespace kge
+
+#include "kge_train_split.cuh"
+
+namespace kge {
+
 // ---- host side ---------------------------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
+  return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 4) +
+         align256(rows * N * 4);
+}
+
 template <int MODEL, bool HEAD>
-static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, cudaStream_t st) {
+static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, void *workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
   int grid = a.row_count;
-  // TMA ring variant: rows are 16-byte multiples, one k-tile covers the row, and >= 4 warps get a double buffer
+  // TMA ring variants: rows are 16-byte multiples, one k-tile covers the row, and >= 4 warps get a double buffer
   constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
   const int nunits = a.d / 4;
   if (vec4 && nunits <= 32 * (CPLX ? 8 : 16) && !getenv("KGE_NO_TMA")) {
     const size_t rowbytes = (size_t)a.De * 4;
-    const size_t fixed = smem + 128 + 8;                              // + mbarrier alignment + slot alignment
+    const bool split = workspace && a.gE && a.N >= 8 && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
+                       workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
+                       a.nentity < (1ll << 31) && (int64_t)a.row_count * a.N < (1ll << 31) && !getenv("KGE_NO_SPLIT");
+    const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + ((a.do_loss || split) ? 2 * (size_t)a.N : 0) + 32);
+    const size_t fixed = base + 16;
     int W = (int)((227 * 1024 - fixed) / (2 * rowbytes + 16));
     if (W > 16) W = 16;
     if (a.N < 4 * W) W = a.N >= 16 ? (a.N + 3) / 4 : 4;                // short candidate lists: fewer, busier warps
     if (W >= 4 && fixed + W * (2 * rowbytes + 16) <= 227 * 1024) {
       const size_t total = fixed + W * (2 * rowbytes + 16);
-      auto k = row_kernel_tma<MODEL, HEAD>;
-      KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-      k<<<grid, W * 32, total, st>>>(a);
+      if (!split) {
+        auto k = row_kernel_tma<MODEL, HEAD>;
+        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+        k<<<grid, W * 32, total, st>>>(a);
+        KGE_CUDA_OK(cudaGetLastError());
+        return KGE_OK;
+      }
+      // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
+      char *wp = (char *)workspace;
+      SplitWs ws;
+      ws.G = (float *)wp;      wp += align256((size_t)a.row_count * a.N * 4);
+      ws.Qtab = (float *)wp;   wp += align256((size_t)a.row_count * a.De * 4);
+      ws.cnt = (int *)wp;
+      ws.cursor = ws.cnt + (a.nentity + 1);
+      ws.queue = ws.cursor + a.nentity;
+      wp += align256((size_t)(a.nentity + 1) * 4 + (size_t)a.nentity * 4 + 4);
+      ws.perm = (int *)wp;
+      KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 1) * 4, st));
+      {
+        auto k = row_kernel_split<MODEL, HEAD>;
+        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+        k<<<grid, W * 32, total, st>>>(a, ws);
+        KGE_CUDA_OK(cudaGetLastError());
+      }
+      scan_offsets_kernel<<<1, 1024, 0, st>>>(ws.cnt, ws.cursor, a.nentity);
       KGE_CUDA_OK(cudaGetLastError());
+      {
+        const int64_t pairs = (int64_t)a.row_count * a.N;
+        int g2 = (int)((pairs + 255) / 256);
+        if (g2 > 148 * 16) g2 = 148 * 16;
+        scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
+                                                 ws.cursor, ws.perm);
+        KGE_CUDA_OK(cudaGetLastError());
+      }
+      {
+        EntArgs e{};
+        e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.G = ws.G; e.Qtab = ws.Qtab;
+        e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue; e.nentity = a.nentity;
+        e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
+        e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
+        int We = (int)((227 * 1024 - 16) / (2 * rowbytes + 16));
+        if (We > 12) We = 12;
+        const size_t esmem = 16 + (size_t)We * (2 * rowbytes + 16);
+        auto k = entity_kernel<MODEL, HEAD>;
+        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        k<<<sms, We * 32, esmem, st>>>(e);
+        KGE_CUDA_OK(cudaGetLastError());
+      }
       return KGE_OK;
     }
   }
@@ -574,7 +640,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
   return KGE_OK;
 }
 
-static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t st) {
+static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t st, void *workspace = nullptr,
+                       size_t workspace_bytes = 0) {
   const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
   a.E = m->entity; a.R = m->relation; a.modulus = m->modulus;
   a.nentity = m->nentity; a.nrelation = m->nrelation;
@@ -593,8 +660,8 @@ static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t
   int threads = a.N >= 16 ? 512 : (a.N >= 4 ? 256 : 128);
 #define KGE_ROWS(MODEL)                                                            \
   case MODEL:                                                                      \
-    return head ? launch_rows_v<MODEL, true>(a, vec4, threads, smem, st)           \
-                : launch_rows_v<MODEL, false>(a, vec4, threads, smem, st);
+    return head ? launch_rows_v<MODEL, true>(a, vec4, threads, smem, workspace, workspace_bytes, st)           \
+                : launch_rows_v<MODEL, false>(a, vec4, threads, smem, workspace, workspace_bytes, st);
   switch (m->model) {
     KGE_ROWS(KGE_TRANSE)
     KGE_ROWS(KGE_DISTMULT)
@@ -642,7 +709,8 @@ extern "C" int kge_score_forward(const kge_model_t *m, int mode, const int64_t *
 
 extern "C" int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, const int64_t *negative,
                                   int64_t B, int64_t N, const float *dscore, float *grad_entity,
-                                  float *grad_relation, float *grad_modulus, int32_t *err_flag, void *stream) {
+                                  float *grad_relation, float *grad_modulus, void *workspace, int64_t workspace_bytes,
+                                  int32_t *err_flag, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(positive && dscore && grad_entity && grad_relation, "null pointer");
@@ -653,14 +721,15 @@ extern "C" int kge_score_backward(const kge_model_t *m, int mode, const int64_t 
   if ((rc = set_device(m))) return rc;
   a.positive = positive; a.row_begin = 0; a.row_count = (int)B; a.N = (int)N;
   a.dscore = dscore; a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
-  return launch_rows(m, head, a, (cudaStream_t)stream);
+  return launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
 }
 
 extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
                               const int64_t *positive, const int64_t *negative, const float *weight,
                               const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
                               int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
-                              float *grad_modulus, float *score_out, int32_t *err_flag, void *stream) {
+                              float *grad_modulus, float *score_out, void *workspace, int64_t workspace_bytes,
+                              int32_t *err_flag, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(positive && row_loss && grad_entity && grad_relation, "null pointer");
@@ -679,5 +748,10 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
   a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
   a.row_loss = row_loss; a.score_out = score_out;
   a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
-  return launch_rows(m, head, a, (cudaStream_t)stream);
+  return launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
+}
+
+extern "C" int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N) {
+  if (!m || rows <= 0 || N <= 0) return 0;
+  return (int64_t)split_workspace_bytes(rows, N, m->entity_dim, m->nentity);
 }

@@ -1,0 +1,444 @@
+// kge_train_split.cuh -- single-read train path: row-major forward + dL/dq, entity-major dL/dx.
+//
+// The two-sweep row kernel (kge_train.cu) reads every candidate row twice and scatters dL/dx with
+// 2.1 GB of atomics into a gradient table that does not fit L2 next to the entity table (ncu r1b:
+// 4.78 GB of DRAM traffic, L2 hit 33 %).  This path reads each candidate row ONCE from global memory:
+//
+//   row_kernel_split   (one CTA per positive row, TMA ring as before)
+//       per candidate: sweep 1 over the shared-memory slot -> score; sweep 2 over the same slot ->
+//       dL/dq contribution, accumulated in registers with a *deferred* softmax normalisation (each warp
+//       keeps a running max M_w of alpha*s and rescales its accumulator when the max grows, exactly like
+//       an online softmax); after the row's loss is known the accumulators are brought to the common
+//       max, folded, scaled by  -/+ u/(2 Z)  and pushed through the chain rule.  It also writes q[b] and
+//       g[b,n] = dL/ds to a workspace and histograms the candidate ids.
+//   scan_offsets / scatter_pairs   counting sort of the (b,n) pairs by candidate entity
+//   entity_kernel      (one warp per entity, dynamic queue) the entity row x_e sits in registers; the q rows
+//       of its pairs (8 MB table, L2 resident) arrive through a TMA double buffer; dL/dx is summed in
+//       registers and added to the gradient row once -- no atomics, no second read of the entity table.
+//
+// DRAM traffic drops from ~1.1 x A to the first touch of the entity table plus one read-modify-write of the
+// gradient table; the passes become L2-bandwidth / issue bound.
+#pragma once
+
+namespace kge {
+
+struct SplitWs {             // carved from the caller's workspace
+  float *G;                  // [rows, N]   dL/ds of every negative pair
+  float *Qtab;               // [rows, De]  query vectors
+  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets
+  int *cursor;               // [nentity]   scatter cursors
+  int *queue;                // [1]         dynamic entity queue of entity_kernel
+  int *perm;                 // [rows * N]  pair indices grouped by entity
+};
+
+template <int MODEL, bool HEAD>
+__global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, const SplitWs ws) {
+  constexpr int OP = op_of(MODEL, HEAD);
+  constexpr bool CPLX = op_is_complex(OP);
+  constexpr int H = CPLX ? 2 : 1;
+  constexpr int V = 4;
+  constexpr int CH = CPLX ? 8 : 16;
+  extern __shared__ __align__(128) float smem[];
+  const int Dq = a.De;
+  const int Dq4 = (Dq + 3) & ~3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // layout: [slots: nwarps x 2 x De | q | dq | sc[N] | gg[N] | scratch(32) | mbarriers], all derived from `smem`
+  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;
+  float *q = smem + (size_t)(2 * nwarps) * a.De;
+  float *dq = q + Dq4;
+  float *sc = dq + Dq4;                         // [N]
+  float *gg = sc + a.N;                         // [N]
+  float *scratch = gg + a.N;                    // [32]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32 + (a.N & 1) * 0);
+  const uint32_t rowbytes = (uint32_t)a.De * 4u;
+  uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
+  uint32_t par0 = 0, par1 = 0;
+
+  const int nunits = a.d / V;
+  const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
+  const bool adversarial = a.do_loss && a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL;
+
+  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
+    const int64_t b = a.row_begin + rl;
+    int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
+    int64_t fid = HEAD ? tidx : hid;
+    if ((uint64_t)fid >= (uint64_t)a.nentity || (uint64_t)rid >= (uint64_t)a.nrelation) {
+      if (tid == 0 && a.err) *a.err = 1;
+      fid = 0; rid = 0;
+    }
+    const float *F = a.E + fid * a.De;
+    const float *Rr = a.R + rid * a.Dr;
+    const int64_t *cand = a.cand + b * a.cand_stride;
+
+    auto issue = [&](int s, int n) {
+      int64_t id = cand[n];
+      if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
+      if (lane == 0) {
+        atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
+        uint64_t *bar = s ? bar1 : bar0;
+        mbar_expect_tx(bar, rowbytes);
+        bulk_g2s(s ? slot1 : slot0, a.E + id * a.De, rowbytes, bar);
+      }
+    };
+    if (warp < a.N) issue(0, warp);
+    if (warp + nwarps < a.N) issue(1, warp + nwarps);
+
+    // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
+    float *qout = ws.Qtab + (size_t)rl * a.De;
+    for (int k = tid; k < a.d; k += blockDim.x) {
+      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q);
+      qout[k] = q[k];
+      dq[k] = 0.f;
+      if (CPLX) { qout[a.d + k] = q[a.d + k]; dq[a.d + k] = 0.f; }
+    }
+    __syncthreads();
+
+    // ---- phase 1: per candidate, score (sweep 1) and deferred-normalised dL/dq (sweep 2) ------------------
+    float acc[CH][H][V];
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
+    float Mw = -INFINITY;                                  // running max of alpha * s over this warp's rows
+    {
+      int it = 0;
+      for (int n = warp; n < a.N; n += nwarps, ++it) {
+        const int s = it & 1;
+        if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
+        float *x = s ? slot1 : slot0;
+        // sweep 1: element values -> score; u = d(value)/dq is parked in the slot (in place of x)
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int u = lane + 32 * i;
+          if (u < nunits) {
+            float x0[V], x1[V], q0[V], q1[V], u0[V], u1[V];
+            load_shared<V>(x0, x + u * V);
+            load_shared<V>(q0, q + u * V);
+            if constexpr (CPLX) {
+              load_shared<V>(x1, x + a.d + u * V);
+              load_shared<V>(q1, q + a.d + u * V);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              part += op_unit<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, u0[j], u1[j]);
+            if constexpr (!op_unit_is_x(OP)) {
+              *reinterpret_cast<float4 *>(x + u * V) = make_float4(u0[0], u0[1], u0[2], u0[3]);
+              if constexpr (CPLX) *reinterpret_cast<float4 *>(x + a.d + u * V) = make_float4(u1[0], u1[1], u1[2], u1[3]);
+            }
+          }
+        }
+        float coef;
+        if (a.do_loss) {
+          part = warp_sum(part);
+          const float sv = finish_score<MODEL>(part, a.gamma, modulus);
+          if (lane == 0) {
+            sc[n] = sv;
+            if (a.score_out) a.score_out[(int64_t)rl * a.N + n] = sv;
+          }
+          if (adversarial) {                               // online softmax: weight relative to the running max
+            const float z = sv * a.alpha;
+            if (z > Mw) {
+              const float r = expf(Mw - z);                // 0 on the first row (Mw = -inf)
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+#pragma unroll
+                for (int h = 0; h < H; ++h)
+#pragma unroll
+                  for (int j = 0; j < V; ++j) acc[i][h][j] *= r;
+              Mw = z;
+            }
+            coef = expf(z - Mw) * sigmoid(sv);
+          } else {
+            coef = sigmoid(sv);                            // uniform negatives: w = 1/N applied at the end
+          }
+        } else {
+          coef = a.dscore[(int64_t)rl * a.N + n];          // autograd backward: dL/ds is given
+        }
+        // sweep 2: acc += coef * u  (each lane re-reads exactly the slot words it wrote)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int u = lane + 32 * i;
+          if (u < nunits) {
+            float u0[V], u1[V];
+            load_shared<V>(u0, x + u * V);
+            if constexpr (CPLX) load_shared<V>(u1, x + a.d + u * V);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              acc[i][0][j] = fmaf(coef, u0[j], acc[i][0][j]);
+              if constexpr (CPLX) acc[i][1][j] = fmaf(coef, u1[j], acc[i][1][j]);
+            }
+          }
+        }
+        // the slot was rewritten with generic stores: order them before the bulk engine's next write to it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (n + 2 * nwarps < a.N) issue(s, n + 2 * nwarps);
+      }
+    }
+
+    // ---- phase 2: loss of this row (model.py:270-288), dL/ds to the workspace ---------------------------------
+    float factor;                                           // dL/dq = factor * (folded accumulators)
+    if (a.do_loss) {
+      __syncthreads();
+      const float u = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
+      float zmax = 0.f;
+      if (adversarial) {
+        zmax = -INFINITY;
+        for (int n = tid; n < a.N; n += blockDim.x) zmax = fmaxf(zmax, sc[n] * a.alpha);
+        zmax = block_reduce(zmax, scratch, true);
+      }
+      float zsum = 0.f;
+      for (int n = tid; n < a.N; n += blockDim.x) {
+        const float e = adversarial ? expf(sc[n] * a.alpha - zmax) : 1.f;
+        gg[n] = e;
+        zsum += e;
+      }
+      zsum = block_reduce(zsum, scratch, false);
+      float lacc = 0.f, gmod = 0.f;
+      float *gout = ws.G + (size_t)rl * a.N;
+      for (int n = tid; n < a.N; n += blockDim.x) {
+        const float w = gg[n] / zsum;
+        const float sv = sc[n];
+        lacc += w * log_sigmoid(-sv);
+        const float g = 0.5f * u * w * sigmoid(sv);
+        gout[n] = g;
+        if constexpr (MODEL == KGE_PROTATE) gmod += -g * (a.gamma - sv) / modulus;   // -g * sum|sin|
+      }
+      const float row_val = block_reduce(lacc, scratch, false);
+      if (tid == 0) a.row_loss[b] = row_val;
+      if constexpr (MODEL == KGE_PROTATE) {
+        gmod = block_reduce(gmod, scratch, false);
+        if (tid == 0 && a.gM) red_add1(a.gM, gmod);
+      }
+      // bring this warp's accumulator to the row's max, then the common scale  (dL/dsum) * u / (2 Z)
+      const float r = adversarial ? (Mw == -INFINITY ? 0.f : expf(Mw - zmax)) : 1.f;
+      factor = dsum_of<MODEL>(0.5f * u / zsum, modulus) * r;
+    } else {
+      float *gout = ws.G + (size_t)rl * a.N;
+      for (int n = tid; n < a.N; n += blockDim.x) gout[n] = a.dscore[(int64_t)rl * a.N + n];
+      if constexpr (MODEL == KGE_PROTATE) {
+        // d/dmodulus needs sum|sin| per pair; the backward-only call recomputes it in entity_kernel (rare path)
+      }
+      factor = dsum_of<MODEL>(1.f, modulus);
+      __syncthreads();
+    }
+
+    // ---- phase 4: fold the per-warp partial dL/dq.  Each warp parks its (scaled) accumulators in its own idle
+    // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int u = lane + 32 * i;
+      if (u < nunits) {
+        *reinterpret_cast<float4 *>(slot0 + u * V) =
+            make_float4(acc[i][0][0] * factor, acc[i][0][1] * factor, acc[i][0][2] * factor, acc[i][0][3] * factor);
+        if constexpr (CPLX)
+          *reinterpret_cast<float4 *>(slot0 + a.d + u * V) =
+              make_float4(acc[i][1][0] * factor, acc[i][1][1] * factor, acc[i][1][2] * factor, acc[i][1][3] * factor);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < a.De; k += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(2 * w) * a.De + k];
+      dq[k] = t;
+    }
+    __syncthreads();
+    // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
+    float *gF = a.gE + fid * a.De;
+    float *gRr = a.gR + rid * a.Dr;
+    for (int k = tid; k < a.d; k += blockDim.x) {
+      float dF0, dF1, dR0, dR1;
+      chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
+      red_add1(gF + k, dF0);
+      red_add1(gRr + k, dR0);
+      if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
+      if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staging stores vs the next row's bulk copies
+    __syncthreads();
+  }
+}
+
+// exclusive scan of the histogram: cnt[0..n] -> offsets (in place), cursor = copy.  One CTA.
+__global__ void __launch_bounds__(1024) scan_offsets_kernel(int *cnt, int *cursor, int64_t n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + tid;
+    const int v = i < n ? cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int s = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += s;
+      }
+      warp_tot[lane] = t;                                  // inclusive totals of the warps
+    }
+    __syncthreads();
+    const int before = carry + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    if (i < n) { cnt[i] = before; cursor[i] = before; }
+    __syncthreads();
+    if (tid == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (tid == 0) cnt[n] = carry;
+}
+
+__global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
+                                     int N, int64_t nentity, int *__restrict__ cursor, int *__restrict__ perm) {
+  const int64_t total = (int64_t)rows * N;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int rl = (int)(p / N), n = (int)(p % N);
+    int64_t id = cand[(row_begin + rl) * cand_stride + n];
+    if ((uint64_t)id >= (uint64_t)nentity) id = 0;
+    const int pos = atomicAdd(cursor + id, 1);
+    perm[pos] = (int)p;
+  }
+}
+
+struct EntArgs {
+  const float *E;
+  const float *modulus;
+  float *gE, *gM;
+  const float *G, *Qtab;
+  const int *off, *perm;
+  int *queue;
+  int64_t nentity;
+  int N, d, De;
+  float scale;
+  int need_gmod;             // backward-only pRotatE: accumulate d/dmodulus here
+};
+
+template <int MODEL, bool HEAD>
+__global__ void __launch_bounds__(384, 1) entity_kernel(const EntArgs a) {
+  constexpr int OP = op_of(MODEL, HEAD);
+  constexpr bool CPLX = op_is_complex(OP);
+  constexpr int H = CPLX ? 2 : 1;
+  constexpr int V = 4;
+  constexpr int CH = CPLX ? 8 : 16;
+  extern __shared__ __align__(128) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;     // [slots | mbarriers]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * nwarps) * a.De);
+  const uint32_t rowbytes = (uint32_t)a.De * 4u;
+  uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
+  uint32_t par0 = 0, par1 = 0;
+  float g0 = 0.f, g1 = 0.f;
+  const int nunits = a.d / V;
+  const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
+
+  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  float gmod = 0.f;
+  for (;;) {
+    int e = 0;
+    if (lane == 0) e = atomicAdd(a.queue, 1);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= a.nentity) break;
+    const int beg = a.off[e], end = a.off[e + 1];
+    if (beg == end) continue;
+
+    auto issue = [&](int s, int i) {
+      const int p = a.perm[i];
+      const float g = a.G[p];
+      if (s) g1 = g; else g0 = g;
+      if (lane == 0) {
+        uint64_t *bar = s ? bar1 : bar0;
+        mbar_expect_tx(bar, rowbytes);
+        bulk_g2s(s ? slot1 : slot0, a.Qtab + (size_t)(p / a.N) * a.De, rowbytes, bar);
+      }
+    };
+    issue(0, beg);
+    if (beg + 1 < end) issue(1, beg + 1);
+
+    const float *xrow = a.E + (size_t)e * a.De;
+    float x0[CH][V], x1[CPLX ? CH : 1][V], acc[CH][H][V];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int u = lane + 32 * i;
+#pragma unroll
+      for (int j = 0; j < V; ++j) { x0[i][j] = 0.f; acc[i][0][j] = 0.f; if constexpr (CPLX) { x1[i][j] = 0.f; acc[i][1][j] = 0.f; } }
+      if (u < nunits) {
+        load_global<V>(x0[i], xrow + u * V);
+        if constexpr (CPLX) load_global<V>(x1[i], xrow + a.d + u * V);
+      }
+    }
+
+    int it = 0;
+    for (int i = beg; i < end; ++i, ++it) {
+      const int s = it & 1;
+      if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
+      const float *q = s ? slot1 : slot0;
+      const float g = s ? g1 : g0;
+      const float go = dsum_of<MODEL>(g, modulus);
+      float vsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int u = lane + 32 * c;
+        if (u < nunits) {
+          float q0[V], q1[V];
+          load_shared<V>(q0, q + u * V);
+          if constexpr (CPLX) load_shared<V>(q1, q + a.d + u * V);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float dq0, dq1, ex0 = 0.f, ex1 = 0.f;
+            float xb = 0.f;
+            if constexpr (CPLX) xb = x1[c][j];
+            vsum += op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[c][j], xb, a.scale, go, dq0, dq1, ex0, ex1);
+            acc[c][0][j] += ex0;
+            if constexpr (CPLX) acc[c][1][j] += ex1;
+          }
+        }
+      }
+      __syncwarp();
+      if (i + 2 < end) issue(s, i + 2);
+      if constexpr (MODEL == KGE_PROTATE) {
+        if (a.need_gmod) gmod += -g * warp_sum(vsum);
+      }
+    }
+    // the warp owns gradient row e during this kernel: plain read-modify-write, no atomics
+    float *grow = a.gE + (size_t)e * a.De;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int u = lane + 32 * c;
+      if (u < nunits) {
+        float4 *p0 = reinterpret_cast<float4 *>(grow + u * V);
+        float4 v = *p0;
+        v.x += acc[c][0][0]; v.y += acc[c][0][1]; v.z += acc[c][0][2]; v.w += acc[c][0][3];
+        *p0 = v;
+        if constexpr (CPLX) {
+          float4 *p1 = reinterpret_cast<float4 *>(grow + a.d + u * V);
+          float4 w = *p1;
+          w.x += acc[c][1][0]; w.y += acc[c][1][1]; w.z += acc[c][1][2]; w.w += acc[c][1][3];
+          *p1 = w;
+        }
+      }
+    }
+  }
+  if constexpr (MODEL == KGE_PROTATE) {
+    if (a.need_gmod && lane == 0 && gmod != 0.f && a.gM) red_add1(a.gM, gmod);
+  }
+}
+
+}  // namespace kge

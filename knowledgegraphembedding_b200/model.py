@@ -71,8 +71,10 @@ class _ScoreFunction(torch.autograd.Function):
         gE, gR = torch.zeros_like(entity), torch.zeros_like(relation)
         gM = torch.zeros_like(modulus) if modulus is not None else None
         desc = model._descriptor(entity, relation, modulus)
+        wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), B, N) if mode != 'single' else 0
+        wsp = torch.empty(wbytes, dtype=torch.uint8, device=entity.device) if wbytes else None
         _lib.call("kge_score_backward", ctypes.byref(desc), _lib.MODE_IDS[mode], _ptr(positive), _ptr(negative),
-                  B, N, _ptr(dscore), _ptr(gE), _ptr(gR), _ptr(gM), None, _stream(entity.device))
+                  B, N, _ptr(dscore), _ptr(gE), _ptr(gR), _ptr(gM), _ptr(wsp), wbytes, None, _stream(entity.device))
         return None, gE, gR, gM, None, None, None
 
 
@@ -337,17 +339,19 @@ class KGEModel(nn.Module):
         gM = ws['gM'] if model.model_name == 'pRotatE' else None
         common = (_ptr(positive), _ptr(negative), _ptr(weight), _ptr(ws['wsum']) if weight is not None else None,
                   B, row_begin, row_end - row_begin, N)
+        wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), row_end - row_begin, N)
+        wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode],
                   _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM, alpha, *common,
-                  _ptr(ws['neg_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(err), st)
+                  _ptr(ws['neg_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp), wbytes, _ptr(err), st)
         if events is not None:
             ev1.record()
             events.append((ev0, ev1))
         _lib.call("kge_train_rows", ctypes.byref(desc), _lib.SINGLE, _lib.LOSS_POSITIVE, 1.0, *common,
-                  _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(err), st)
+                  _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, None, 0, _ptr(err), st)
         if world > 1:
             # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
             torch.distributed.all_reduce(ws['flat'])

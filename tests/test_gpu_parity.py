@@ -415,3 +415,40 @@ def test_ragged_last_batch_and_non_adam_optimizer():
     pos = torch.stack([torch.randint(300, (8,)), torch.randint(5, (8,)), torch.randint(300, (8,))], 1)
     KGE().train_step(m, sgd, iter([(pos, torch.randint(300, (8, 7)), torch.rand(8) + 0.1, "tail-batch")]), args)
     torch.testing.assert_close(m.entity_embedding.detach(), before - 0.1 * m.entity_embedding.grad)
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("mode", ["head-batch", "tail-batch"])
+def test_single_read_path_matches_two_sweep_kernel(model, mode, monkeypatch):
+    """The single-read path (row_kernel_split + entity_kernel) against the two-sweep atomic kernel and the numpy
+    oracle on a medium shape, adversarial and uniform losses."""
+    nentity, nrel, d, gamma, B, N = 3000, 7, 128, 6.0, 37, 50
+    de, dr = FLAGS[model]
+    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=5)
+    rng = np.random.RandomState(6)
+    pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
+    neg = rng.randint(60, size=(B, N))                  # few distinct candidates => long entity segments
+    w = np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)
+    for adv in (True, False):
+        args = ns(negative_adversarial_sampling=adv, adversarial_temperature=0.5)
+        out = {}
+        for tag in ("split", "two_sweep"):
+            if tag == "two_sweep":
+                monkeypatch.setenv("KGE_NO_SPLIT", "1")
+            else:
+                monkeypatch.delenv("KGE_NO_SPLIT", raising=False)
+            m = make_model(model, nentity, nrel, d, gamma, st)
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-4)
+            log = KGE().train_step(m, opt, iter([(torch.from_numpy(pos), torch.from_numpy(neg), torch.from_numpy(w), mode)]), args)
+            out[tag] = (log, m.entity_embedding.grad.cpu().numpy().copy(), m.relation_embedding.grad.cpu().numpy().copy(),
+                        m.modulus.grad.cpu().numpy().copy() if model == "pRotatE" else None)
+        monkeypatch.delenv("KGE_NO_SPLIT", raising=False)
+        ts = O.TrainState(model, st, gamma, d)
+        olog, og = O.train_step(ts, (pos, neg, w, mode), lr=1e-4, adversarial=adv, alpha=0.5, return_grads=True)
+        for tag in out:
+            log, gE, gR, gM = out[tag]
+            assert abs(log["loss"] - olog["loss"]) <= TOL * abs(olog["loss"]), tag
+            assert relinf(gE, og["entity_embedding"]) < TOL, (tag, adv)
+            assert relinf(gR, og["relation_embedding"]) < TOL, (tag, adv)
+            if gM is not None:
+                assert relinf(gM, og["modulus"]) < TOL, (tag, adv)
