@@ -551,7 +551,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
   return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 4) +
-         align256(rows * N * 4);
+         2 * align256(rows * N * 4);
 }
 
 template <int MODEL, bool HEAD>
@@ -589,7 +589,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       ws.cursor = ws.cnt + (a.nentity + 1);
       ws.queue = ws.cursor + a.nentity;
       wp += align256((size_t)(a.nentity + 1) * 4 + (size_t)a.nentity * 4 + 4);
-      ws.perm = (int *)wp;
+      ws.perm = (int *)wp;     wp += align256((size_t)a.row_count * a.N * 4);
+      ws.gsorted = (float *)wp;
       KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 1) * 4, st));
       {
         auto k = row_kernel_split<MODEL, HEAD>;
@@ -604,24 +605,34 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         int g2 = (int)((pairs + 255) / 256);
         if (g2 > 148 * 16) g2 = 148 * 16;
         scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
-                                                 ws.cursor, ws.perm);
+                                                 ws.G, ws.cursor, ws.perm, ws.gsorted);
         KGE_CUDA_OK(cudaGetLastError());
       }
       {
         EntArgs e{};
-        e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.G = ws.G; e.Qtab = ws.Qtab;
+        e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.gsorted = ws.gsorted; e.Qtab = ws.Qtab;
         e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue; e.nentity = a.nentity;
         e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
         e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
-        int We = (int)((227 * 1024 - 16) / (2 * rowbytes + 16));
-        if (We > 12) We = 12;
-        const size_t esmem = 16 + (size_t)We * (2 * rowbytes + 16);
-        auto k = entity_kernel<MODEL, HEAD>;
-        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        k<<<sms, We * 32, esmem, st>>>(e);
+        const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
+        e.upp = two ? (nunits + 1) / 2 : nunits;
+        const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * e.upp * 16;
+        int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
+        const int wmax = two ? 24 : 12;
+        if (We > wmax) We = wmax;
+        const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
+        if (two) {
+          auto k = entity_kernel<MODEL, HEAD, 2>;
+          KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+          k<<<sms, We * 32, esmem, st>>>(e);
+        } else {
+          auto k = entity_kernel<MODEL, HEAD, 1>;
+          KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+          k<<<sms, We * 32, esmem, st>>>(e);
+        }
         KGE_CUDA_OK(cudaGetLastError());
       }
       return KGE_OK;

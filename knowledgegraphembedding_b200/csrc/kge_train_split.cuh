@@ -28,7 +28,8 @@ struct SplitWs {             // carved from the caller's workspace
   int *cnt;                  // [nentity + 1] histogram -> exclusive offsets
   int *cursor;               // [nentity]   scatter cursors
   int *queue;                // [1]         dynamic entity queue of entity_kernel
-  int *perm;                 // [rows * N]  pair indices grouped by entity
+  int *perm;                 // [rows * N]  row index (b - row_begin) of every pair, grouped by entity
+  float *gsorted;            // [rows * N]  dL/ds of every pair in the same order
 };
 
 template <int MODEL, bool HEAD>
@@ -304,14 +305,16 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(int *cnt, int *curso
 }
 
 __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
-                                     int N, int64_t nentity, int *__restrict__ cursor, int *__restrict__ perm) {
+                                     int N, int64_t nentity, const float *__restrict__ G, int *__restrict__ cursor,
+                                     int *__restrict__ perm, float *__restrict__ gsorted) {
   const int64_t total = (int64_t)rows * N;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int rl = (int)(p / N), n = (int)(p % N);
     int64_t id = cand[(row_begin + rl) * cand_stride + n];
     if ((uint64_t)id >= (uint64_t)nentity) id = 0;
     const int pos = atomicAdd(cursor + id, 1);
-    perm[pos] = (int)p;
+    perm[pos] = rl;                                        // the entity pass only needs the q row and dL/ds
+    gsorted[pos] = G[p];
   }
 }
 
@@ -319,32 +322,37 @@ struct EntArgs {
   const float *E;
   const float *modulus;
   float *gE, *gM;
-  const float *G, *Qtab;
+  const float *gsorted, *Qtab;
   const int *off, *perm;
   int *queue;
   int64_t nentity;
   int N, d, De;
+  int upp;                   // units (float4) per part: ceil(nunits / S)
   float scale;
   int need_gmod;             // backward-only pRotatE: accumulate d/dmodulus here
 };
 
-template <int MODEL, bool HEAD>
-__global__ void __launch_bounds__(384, 1) entity_kernel(const EntArgs a) {
+// One warp per (entity, part) task, S parts per row.  dL/dx is element-wise (no row reduction), so splitting the
+// k axis needs no exchange between warps; S = 2 halves the per-thread registers (x and the accumulators) and the
+// slot size, which doubles the resident warps (24 per SM) for latency hiding.
+template <int MODEL, bool HEAD, int S>
+__global__ void __launch_bounds__(S == 1 ? 384 : 768, 1) entity_kernel(const EntArgs a) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
   constexpr int V = 4;
-  constexpr int CH = CPLX ? 8 : 16;
+  constexpr int CH = (CPLX ? 8 : 16) / S;
   extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;     // [slots | mbarriers]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * nwarps) * a.De);
-  const uint32_t rowbytes = (uint32_t)a.De * 4u;
+  const int slot_floats = H * a.upp * V;
+  float *slot0 = smem + (size_t)(2 * warp) * slot_floats, *slot1 = slot0 + slot_floats;     // [slots | mbarriers]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * nwarps) * slot_floats);
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
   uint32_t par0 = 0, par1 = 0;
   float g0 = 0.f, g1 = 0.f;
   const int nunits = a.d / V;
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
+  const int64_t ntasks = a.nentity * S;
 
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -352,34 +360,40 @@ __global__ void __launch_bounds__(384, 1) entity_kernel(const EntArgs a) {
 
   float gmod = 0.f;
   for (;;) {
-    int e = 0;
-    if (lane == 0) e = atomicAdd(a.queue, 1);
-    e = __shfl_sync(0xffffffffu, e, 0);
-    if (e >= a.nentity) break;
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.queue, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= ntasks) break;
+    const int e = t / S, part = t % S;
     const int beg = a.off[e], end = a.off[e + 1];
-    if (beg == end) continue;
+    const int ubeg = part * a.upp;                          // first unit of this part
+    const int ucnt = min(a.upp, nunits - ubeg);             // units in this part
+    if (beg == end || ucnt <= 0) continue;
+    const uint32_t segbytes = (uint32_t)ucnt * V * 4u;
 
     auto issue = [&](int s, int i) {
-      const int p = a.perm[i];
-      const float g = a.G[p];
+      const float g = a.gsorted[i];
       if (s) g1 = g; else g0 = g;
       if (lane == 0) {
         uint64_t *bar = s ? bar1 : bar0;
-        mbar_expect_tx(bar, rowbytes);
-        bulk_g2s(s ? slot1 : slot0, a.Qtab + (size_t)(p / a.N) * a.De, rowbytes, bar);
+        float *dst = s ? slot1 : slot0;
+        const float *src = a.Qtab + (size_t)a.perm[i] * a.De + ubeg * V;
+        mbar_expect_tx(bar, segbytes * H);
+        bulk_g2s(dst, src, segbytes, bar);
+        if constexpr (CPLX) bulk_g2s(dst + a.upp * V, src + a.d, segbytes, bar);
       }
     };
     issue(0, beg);
     if (beg + 1 < end) issue(1, beg + 1);
 
-    const float *xrow = a.E + (size_t)e * a.De;
+    const float *xrow = a.E + (size_t)e * a.De + ubeg * V;
     float x0[CH][V], x1[CPLX ? CH : 1][V], acc[CH][H][V];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int u = lane + 32 * i;
 #pragma unroll
       for (int j = 0; j < V; ++j) { x0[i][j] = 0.f; acc[i][0][j] = 0.f; if constexpr (CPLX) { x1[i][j] = 0.f; acc[i][1][j] = 0.f; } }
-      if (u < nunits) {
+      if (u < ucnt) {
         load_global<V>(x0[i], xrow + u * V);
         if constexpr (CPLX) load_global<V>(x1[i], xrow + a.d + u * V);
       }
@@ -396,10 +410,10 @@ __global__ void __launch_bounds__(384, 1) entity_kernel(const EntArgs a) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int u = lane + 32 * c;
-        if (u < nunits) {
+        if (u < ucnt) {
           float q0[V], q1[V];
           load_shared<V>(q0, q + u * V);
-          if constexpr (CPLX) load_shared<V>(q1, q + a.d + u * V);
+          if constexpr (CPLX) load_shared<V>(q1, q + a.upp * V + u * V);
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             float dq0, dq1, ex0 = 0.f, ex1 = 0.f;
@@ -417,12 +431,12 @@ __global__ void __launch_bounds__(384, 1) entity_kernel(const EntArgs a) {
         if (a.need_gmod) gmod += -g * warp_sum(vsum);
       }
     }
-    // the warp owns gradient row e during this kernel: plain read-modify-write, no atomics
-    float *grow = a.gE + (size_t)e * a.De;
+    // the warp owns this part of gradient row e during the kernel: plain read-modify-write, no atomics
+    float *grow = a.gE + (size_t)e * a.De + ubeg * V;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int u = lane + 32 * c;
-      if (u < nunits) {
+      if (u < ucnt) {
         float4 *p0 = reinterpret_cast<float4 *>(grow + u * V);
         float4 v = *p0;
         v.x += acc[c][0][0]; v.y += acc[c][0][1]; v.z += acc[c][0][2]; v.w += acc[c][0][3];
