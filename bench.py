@@ -28,6 +28,7 @@ WORKLOADS = {
     "transe_fb15k237": ("TransE", 14541, 237, 1000, 9.0, 1024, 256, 5e-5, False, False),
     "rotate_yago310": ("RotatE", 123182, 37, 500, 24.0, 1024, 400, 2e-4, True, False),
     "complex_wn18rr": ("ComplEx", 40943, 11, 500, 200.0, 512, 1024, 2e-3, True, True),
+    "distmult_fb15k": ("DistMult", 14951, 1345, 2000, 500.0, 1024, 256, 1e-3, False, False),
 }
 METRIC = "rotate_negative_sample_scores_per_sec_train_step"
 

@@ -148,6 +148,22 @@ int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, cons
                          const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
                          int32_t *counts, float *scores_out, void *stream);
 
+/* ---- tcgen05 path for the dot-product models (DistMult model.py:175-182, ComplEx :184-199) in test_step ----
+ * The all-entity scores are one [Q, D_e] x [D_e, nentity] contraction.  Operands are split into two TF32-exact
+ * pieces (kge_eval_gemm_split: hi, lo and the row norms), a tcgen05.mma kind::tf32 kernel accumulates
+ * hi*hi + hi*lo + lo*hi in tensor memory, and its epilogue counts only the candidates whose order against the
+ * positive is certain under a rigorous error band; the ambiguous (q, j) pairs go to amb_pairs and are re-scored
+ * with the exact op sequence of kge_eval_count_ranks, so counts are identical to that kernel's.
+ * amb_count[0] = pairs appended, amb_count[1] = 1 if amb_capacity overflowed (caller falls back to
+ * kge_eval_count_ranks for that chunk).  ent_begin must be a multiple of 32.                                 */
+int kge_eval_gemm_supported(const kge_model_t *m);
+int kge_eval_gemm_split(const float *x, int64_t rows, int64_t cols, float *hi, float *lo, float *norm, void *stream);
+int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const float *qvec, const float *qhi, const float *qlo,
+                              const float *qnorm, const int64_t *queries, int64_t Q, const float *pos_score,
+                              const uint32_t *filter_bits, const float *ehi, const float *elo, const float *enorm,
+                              int64_t ent_begin, int64_t ent_end, int32_t *counts, void *amb_pairs,
+                              int64_t amb_capacity, int32_t *amb_count, void *stream);
+
 /* filter bitmap from a CSR of true entities per query (dataloader.py:138-144)                     */
 int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q,
                          int64_t nentity, uint32_t *filter_bits, void *stream);

@@ -1,0 +1,410 @@
+// kge_eval_gemm.cu -- tcgen05 (5th-gen tensor core) all-entity scoring for the dot-product models
+// (DistMult model.py:175-182, ComplEx model.py:184-199) in test_step, with ranks that stay bit-exact.
+//
+// For these two models  score(q, j) = <qvec_q, E_j>  is a real [Q, D_e] x [D_e, nentity] contraction -- the one
+// dense GEMM of the path.  fp32 has no tensor-core kind, so every operand is split once into two TF32-exact
+// pieces  x = hi + lo (+ r, |r| <= 2^-20 |x|)  and the kernel accumulates  hi*hi + hi*lo + lo*hi  (3xTF32) in
+// fp32 in tensor memory.  That result is only an *approximation* of the canonical fp32 score that defines the
+// ranks, with a rigorous bound  |approx - canonical| <= eps_qj = kBand * |q| * |E_j|.
+// The epilogue therefore classifies each (query, entity):
+//      approx - eps > s_pos  -> certainly ranked above the positive: count it
+//      approx + eps < s_pos  -> certainly below: ignore
+//      otherwise             -> ambiguous: append (q, j) to a list
+// and rescore_pairs_kernel re-scores the short ambiguous list with the canonical exact op sequence.  Counts (and
+// ranks) are therefore identical to the exact SIMT kernel's, whatever the tensor core's internal rounding is.
+//
+// Kernel anatomy (one CTA per 128-query tile, looping over 128-entity tiles):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128 rows x 32 fp32, SWIZZLE_128B) of the query and
+//            entity pieces into a 6-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) on
+//            shared-memory descriptors, accumulating in TMEM; tcgen05.commit frees ring slots / publishes tiles
+//   warp 2   TMEM allocator (256 columns = two accumulator buffers)
+//   warps 4-7  epilogue: tcgen05.ld 32x32b (lane = query row), band test, filter bitmap, counts, ambiguous list
+#include <cuda.h>
+
+#include "kge_rows.cuh"
+
+namespace kge {
+
+constexpr int GM = 128, GN = 128, GK = 32, GSTAGES = 6, GTHREADS = 256;
+constexpr uint32_t kTileBytes = GM * GK * 4;                  // 16 KB per operand tile
+constexpr float kBand = 6.0e-4f;                              // eps = kBand * |q| * |e|   (see header comment)
+
+struct GemmArgs {
+  const float *pos_score;        // [Q] canonical score of the positive
+  const float *qnorm, *enorm;    // [Q], [nentity] euclidean norms
+  const int64_t *queries;        // [Q,3]
+  const uint32_t *filter_bits;   // [Q, words]
+  int32_t *counts;               // [Q]
+  int2 *amb;                     // ambiguous (q, j) pairs
+  int *amb_count;                // [0] = number appended, [1] = overflow flag
+  int amb_capacity;
+  int Q, pos_col, words;
+  int64_t nentity, ent_begin, ent_end;
+  int K;                         // contraction length (entity_dim)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mb_init(uint64_t *b, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mb_expect(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a broken pipeline fails loudly, it never hangs
+  }
+}
+__device__ __forceinline__ void tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          s32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand tile (rows of 128 B, 8-row groups 1024 B apart): cute::UMMA::SmemDescriptor
+__device__ __forceinline__ uint64_t smem_desc(const void *tile) {
+  uint64_t d = 0;
+  d |= (uint64_t)((s32(tile) >> 4) & 0x3FFF);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(GTHREADS, 1)
+gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant__ CUtensorMap tmQlo,
+                  const __grid_constant__ CUtensorMap tmEhi, const __grid_constant__ CUtensorMap tmElo,
+                  const GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t gsm_raw[];
+  uint8_t *gsm = gsm_raw + ((1024u - (s32(gsm_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t *tilesA = gsm;                                        // [GSTAGES][16 KB]
+  uint8_t *tilesB = gsm + GSTAGES * kTileBytes;                 // [GSTAGES][16 KB]
+  uint64_t *full = reinterpret_cast<uint64_t *>(gsm + 2 * GSTAGES * kTileBytes);
+  uint64_t *empty = full + GSTAGES;
+  uint64_t *tfull = empty + GSTAGES;                            // [2] accumulator ready
+  uint64_t *tempty = tfull + 2;                                 // [2] accumulator drained
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *enorm_s = reinterpret_cast<float *>(tmem_slot + 4);    // [2][GN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * GM;
+  const int64_t ntiles_all = (a.ent_end - a.ent_begin + GN - 1) / GN;
+  const int kpb = (a.K + GK - 1) / GK;                          // k-blocks per operand pair
+  const int nkb = 3 * kpb;                                      // hi*hi, hi*lo, lo*hi
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < GSTAGES; ++i) { mb_init(full + i, 1); mb_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mb_init(tfull + i, 1); mb_init(tempty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmEhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmElo) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t jt = blockIdx.y; jt < ntiles_all; jt += gridDim.y) {
+        const int j0 = (int)(a.ent_begin + jt * GN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int seg = kb / kpb, kk = (kb % kpb) * GK;
+          mb_wait(empty + stage, phase ^ 1);
+          mb_expect(full + stage, 2 * kTileBytes);
+          tma_2d(tilesA + stage * kTileBytes, seg == 2 ? &tmQlo : &tmQhi, kk, q0, full + stage);
+          tma_2d(tilesB + stage * kTileBytes, seg == 1 ? &tmElo : &tmEhi, kk, j0, full + stage);
+          if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_tf32(GM, GN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int tile_it = 0;
+      for (int64_t jt = blockIdx.y; jt < ntiles_all; jt += gridDim.y, ++tile_it) {
+        const int as = tile_it & 1;
+        mb_wait(tempty + as, ((tile_it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * GN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mb_wait(full + stage, phase);
+          tc_fence_after();
+          const uint64_t ad = smem_desc(tilesA + stage * kTileBytes);
+          const uint64_t bd = smem_desc(tilesB + stage * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k)                      // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
+            umma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty + stage);                           // slot free once these MMAs have read it
+          if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull + as);                                // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ========================================
+    const int ew = warp - 4;                                    // TMEM lanes [32 ew, 32 ew + 32)
+    const int row = ew * 32 + lane;
+    const int qi = q0 + row;
+    const bool qvalid = qi < a.Q;
+    const float sp = qvalid ? a.pos_score[qi] : 0.f;
+    const float qn = qvalid ? a.qnorm[qi] * kBand : 0.f;
+    const int64_t pid = qvalid ? a.queries[(int64_t)qi * 3 + a.pos_col] : -1;
+    const uint32_t *frow = a.filter_bits + (int64_t)(qvalid ? qi : 0) * a.words;
+    int count = 0;
+    int tile_it = 0;
+    for (int64_t jt = blockIdx.y; jt < ntiles_all; jt += gridDim.y, ++tile_it) {
+      const int as = tile_it & 1;
+      const int64_t j0 = a.ent_begin + jt * GN;
+      // entity norms of this tile (threads 128..255 -> 128 values), visible after the named barrier
+      {
+        const int64_t j = j0 + (threadIdx.x - 128);
+        enorm_s[as * GN + (threadIdx.x - 128)] = j < a.ent_end ? a.enorm[j] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mb_wait(tfull + as, (tile_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+            "%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (qvalid) {
+          const int64_t jb = j0 + c * 32;
+          const uint32_t fw = jb < a.ent_end ? frow[jb >> 5] : 0u;    // tiles are 32-aligned: one bitmap word
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int64_t j = jb + i;
+            if (j >= a.ent_end || j == pid || ((fw >> i) & 1u)) continue;
+            const float s = __uint_as_float(v[i]);
+            const float eps = qn * enorm_s[as * GN + c * 32 + i];
+            if (s - eps > sp) {
+              ++count;
+            } else if (s + eps >= sp) {                        // cannot be decided from the approximation
+              const int slot = atomicAdd(a.amb_count, 1);
+              if (slot < a.amb_capacity) a.amb[slot] = make_int2(qi, (int)j);
+              else a.amb_count[1] = 1;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mb_arrive(tempty + as);                    // 4 epilogue warps -> accumulator free
+    }
+    if (qvalid && count) atomicAdd(a.counts + qi, count);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- operand preparation -----------------------------------------------------------------------------------
+// x = hi + lo + r with hi, lo exactly representable in TF32 (low 13 mantissa bits zero), |r| <= 2^-20 |x|.
+__global__ void split_tf32_kernel(const float *__restrict__ x, int64_t rows, int cols, float *__restrict__ hi,
+                                  float *__restrict__ lo, float *__restrict__ norm) {
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float v = x[r * cols + c];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const float l = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+      hi[r * cols + c] = h;
+      lo[r * cols + c] = l;
+      acc += v * v;
+    }
+    __shared__ float sh[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+      norm[r] = sqrtf(t) * 1.0001f;                          // rounded up: the band must never be too small
+    }
+    __syncthreads();
+  }
+}
+
+// exact canonical re-score of the ambiguous pairs (same op sequence and order as count_ranks_kernel)
+template <bool CPLX>
+__global__ void rescore_pairs_kernel(const int2 *__restrict__ amb, const int *__restrict__ amb_count, int capacity,
+                                     const float *__restrict__ qvec, const float *__restrict__ E, int d, int De,
+                                     const float *__restrict__ pos_score, const int64_t *__restrict__ queries,
+                                     int pos_col, int32_t *__restrict__ counts) {
+  int n = amb_count[0];
+  if (n > capacity) n = capacity;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 p = amb[i];
+    const float *q = qvec + (int64_t)p.x * De, *x = E + (int64_t)p.y * De;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < d; k0 += 32) {
+      float part = 0.f;
+      const int k1 = k0 + 32 < d ? k0 + 32 : d;
+      for (int k = k0; k < k1; ++k) {
+        const float v = CPLX ? fadd(fmul(q[k], x[k]), fmul(q[d + k], x[d + k])) : fmul(q[k], x[k]);
+        part = fadd(part, v);
+      }
+      acc = fadd(acc, part);
+    }
+    const float sp = pos_score[p.x];
+    const int64_t pid = queries[(int64_t)p.x * 3 + pos_col];
+    if (acc > sp || (acc == sp && p.y < pid)) atomicAdd(counts + p.x, 1);
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    KGE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    KGE_REQUIRE(p && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {GK, GM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KGE_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+  return KGE_OK;
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_eval_gemm_supported(const kge_model_t *m) {
+  if (!m) return 0;
+  return (m->model == KGE_DISTMULT || m->model == KGE_COMPLEX) && m->entity_dim % 4 == 0 &&
+         (((uintptr_t)m->entity) & 15) == 0 && m->nentity < (1ll << 31);
+}
+
+extern "C" int kge_eval_gemm_split(const float *x, int64_t rows, int64_t cols, float *hi, float *lo, float *norm,
+                                   void *stream) {
+  KGE_REQUIRE(x && hi && lo && norm && rows > 0 && cols > 0, "bad arguments");
+  const int grid = (int)(rows < 148 * 16 ? rows : 148 * 16);
+  split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)cols, hi, lo, norm);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const float *qvec, const float *qhi,
+                                         const float *qlo, const float *qnorm, const int64_t *queries, int64_t Q,
+                                         const float *pos_score, const uint32_t *filter_bits, const float *ehi,
+                                         const float *elo, const float *enorm, int64_t ent_begin, int64_t ent_end,
+                                         int32_t *counts, void *amb_pairs, int64_t amb_capacity, int32_t *amb_count,
+                                         void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(kge_eval_gemm_supported(m), "the tcgen05 path serves DistMult / ComplEx with 16-byte aligned rows");
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "negative batch mode %d not supported", mode);
+  KGE_REQUIRE(qvec && qhi && qlo && qnorm && queries && pos_score && filter_bits && ehi && elo && enorm && counts &&
+                  amb_pairs && amb_count && amb_capacity > 0,
+              "null pointer");
+  KGE_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= m->nentity && ent_begin % 32 == 0,
+              "entity slice must start on a multiple of 32");
+  if (Q <= 0 || ent_begin == ent_end) return KGE_OK;
+  if ((rc = set_device(m))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t K = m->entity_dim;
+  CUtensorMap tQhi, tQlo, tEhi, tElo;
+  if ((rc = make_map(&tQhi, qhi, Q, K))) return rc;
+  if ((rc = make_map(&tQlo, qlo, Q, K))) return rc;
+  if ((rc = make_map(&tEhi, ehi, m->nentity, K))) return rc;
+  if ((rc = make_map(&tElo, elo, m->nentity, K))) return rc;
+  GemmArgs a{};
+  a.pos_score = pos_score; a.qnorm = qnorm; a.enorm = enorm; a.queries = queries; a.filter_bits = filter_bits;
+  a.counts = counts; a.amb = (int2 *)amb_pairs; a.amb_count = amb_count; a.amb_capacity = (int)amb_capacity;
+  a.Q = (int)Q; a.pos_col = mode == KGE_HEAD_BATCH ? 0 : 2; a.words = (int)((m->nentity + 31) / 32);
+  a.nentity = m->nentity; a.ent_begin = ent_begin; a.ent_end = ent_end; a.K = (int)K;
+  KGE_CUDA_OK(cudaMemsetAsync(amb_count, 0, 2 * sizeof(int), st));
+  const size_t smem = 2 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
+  KGE_CUDA_OK(cudaFuncSetAttribute(gemm_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int qtiles = (int)((Q + GM - 1) / GM);
+  const int64_t jtiles = (ent_end - ent_begin + GN - 1) / GN;
+  int ysplit = (148 + qtiles - 1) / qtiles;                       // fill the SMs when there are few query tiles
+  if (ysplit > jtiles) ysplit = (int)jtiles;
+  if (ysplit < 1) ysplit = 1;
+  gemm_count_kernel<<<dim3(qtiles, ysplit), GTHREADS, smem, st>>>(tQhi, tQlo, tEhi, tElo, a);
+  KGE_CUDA_OK(cudaGetLastError());
+  const bool cplx = m->model == KGE_COMPLEX;
+  const int d = cplx ? (int)(K / 2) : (int)K;
+  if (cplx)
+    rescore_pairs_kernel<true><<<148 * 4, 128, 0, st>>>(a.amb, amb_count, a.amb_capacity, qvec, m->entity, d, (int)K,
+                                                        pos_score, queries, a.pos_col, counts);
+  else
+    rescore_pairs_kernel<false><<<148 * 4, 128, 0, st>>>(a.amb, amb_count, a.amb_capacity, qvec, m->entity, d, (int)K,
+                                                         pos_score, queries, a.pos_col, counts);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}

@@ -35,11 +35,15 @@ def _dist():
     return 0, 1
 
 
-def shard_bounds(total, rank, world):
-    """Contiguous balanced slice [begin, end) of `total` items for `rank` (batch rows / entity ids)."""
-    base, rem = divmod(int(total), int(world))
+def shard_bounds(total, rank, world, align=1):
+    """Contiguous balanced slice [begin, end) of `total` items for `rank` (batch rows / entity ids); with `align`
+    the interior boundaries fall on multiples of it (entity tiles)."""
+    total, align = int(total), int(align)
+    units = (total + align - 1) // align
+    base, rem = divmod(units, int(world))
     begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    end = begin + base + (1 if rank < rem else 0)
+    return min(begin * align, total), min(end * align, total)
 
 
 class _ScoreFunction(torch.autograd.Function):
@@ -415,7 +419,7 @@ class KGEModel(nn.Module):
         index = self._filter_index(all_true_triples, nentity, nrelation)
         queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
         rank, world = _dist()
-        ent_begin, ent_end = shard_bounds(nentity, rank, world)
+        ent_begin, ent_end = shard_bounds(nentity, rank, world, align=128)
         desc = self._descriptor()
         err = self._err_flag()
         words = (nentity + 31) // 32
@@ -423,6 +427,18 @@ class KGEModel(nn.Module):
         if self.model_name == 'pRotatE':
             phase = self._buffer('phase_table', self.entity_embedding.numel(), torch.float32, dev)
             _lib.call("kge_eval_phase_table", ctypes.byref(desc), _ptr(phase), st)
+        # DistMult / ComplEx: the all-entity scores are a dense contraction -> tcgen05 path (exact SIMT re-score of
+        # the ambiguous band keeps the counts identical); KGE_EVAL_SIMT=1 forces the exact tile kernel
+        import os
+        gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not return_scores \
+            and not os.environ.get("KGE_EVAL_SIMT")
+        if gemm:
+            nE = self.entity_embedding.numel()
+            ehi = self._buffer('gemm_ehi', nE, torch.float32, dev)
+            elo = self._buffer('gemm_elo', nE, torch.float32, dev)
+            enorm = self._buffer('gemm_enorm', nentity, torch.float32, dev)
+            _lib.call("kge_eval_gemm_split", _ptr(self.entity_embedding), nentity, self.entity_dim, _ptr(ehi), _ptr(elo),
+                      _ptr(enorm), st)
         counts_all = torch.zeros(queries_all.shape[0], dtype=torch.int32, device=dev)
         scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
         m = _lib.MODE_IDS[mode]
@@ -446,6 +462,25 @@ class KGEModel(nn.Module):
             if events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            if gemm:
+                qhi = self._buffer('gemm_qhi', Q * self.entity_dim, torch.float32, dev)
+                qlo = self._buffer('gemm_qlo', Q * self.entity_dim, torch.float32, dev)
+                qnorm = self._buffer('gemm_qnorm', Q, torch.float32, dev)
+                cap = Q * 1024
+                amb = self._buffer('gemm_amb', cap * 2, torch.int32, dev)
+                amb_count = self._buffer('gemm_amb_count', 2, torch.int32, dev)
+                _lib.call("kge_eval_gemm_split", _ptr(qvec), Q, self.entity_dim, _ptr(qhi), _ptr(qlo), _ptr(qnorm), st)
+                _lib.call("kge_eval_gemm_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(qhi), _ptr(qlo),
+                          _ptr(qnorm), _ptr(queries), Q, _ptr(pos), _ptr(bits), _ptr(ehi), _ptr(elo), _ptr(enorm),
+                          ent_begin, ent_end, _ptr(counts), _ptr(amb), cap, _ptr(amb_count), st)
+                stats = amb_count[:2].tolist()
+                self._ws['gemm_last_ambiguous'] = stats[0]
+                if stats[1] == 0:
+                    if events is not None:
+                        ev1.record()
+                        events.append((ev0, ev1))
+                    continue
+                counts.zero_()                               # ambiguous list overflowed: exact kernel for this chunk
             _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
                       _ptr(scores[lo:lo + Q]) if scores is not None else None, st)

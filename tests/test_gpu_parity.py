@@ -452,3 +452,32 @@ def test_single_read_path_matches_two_sweep_kernel(model, mode, monkeypatch):
             assert relinf(gR, og["relation_embedding"]) < TOL, (tag, adv)
             if gM is not None:
                 assert relinf(gM, og["modulus"]) < TOL, (tag, adv)
+
+
+@pytest.mark.parametrize("model,nentity,nrel,d,gamma,nq", [
+    ("ComplEx", 40943, 11, 500, 200.0, 300),        # wn18rr shape (BASELINE.json configs[3]); K = 1000 is not a multiple of 32
+    ("DistMult", 14951, 1345, 2000, 500.0, 200),    # FB15k shape of best_config.sh
+    ("ComplEx", 517, 5, 12, 20.0, 130),             # tiles mostly out of bounds, Q and nentity not multiples of 128
+    ("DistMult", 4099, 3, 36, 20.0, 129),
+])
+def test_tcgen05_eval_ranks_identical_to_exact_kernel(model, nentity, nrel, d, gamma, nq, monkeypatch):
+    """DistMult/ComplEx all-entity scoring on the tcgen05 path (3xTF32 + exact re-score of the ambiguous band) gives
+    the same integer ranks as the exact SIMT tile kernel, which is bit-exact against the C oracle."""
+    de, dr = FLAGS[model]
+    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=3)
+    st["entity_embedding"] = (st["entity_embedding"] * 5.0).astype(np.float32)
+    rng = np.random.RandomState(4)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(min(nentity, 300))))
+                       for _ in range(20000)})
+    test = [all_true[i] for i in rng.choice(len(all_true), nq, replace=False)]
+    m = make_model(model, nentity, nrel, d, gamma, st)
+    for mode in ("head-batch", "tail-batch"):
+        monkeypatch.setenv("KGE_EVAL_SIMT", "1")
+        exact = m.filtered_ranks(test, all_true, mode)
+        monkeypatch.delenv("KGE_EVAL_SIMT")
+        m._ws.pop('gemm_last_ambiguous', None)
+        fast = m.filtered_ranks(test, all_true, mode)
+        assert 'gemm_last_ambiguous' in m._ws, "tcgen05 path was not taken"
+        np.testing.assert_array_equal(fast, exact)
+        # the band is narrow: only a small fraction of the Q x nentity pairs needs the exact re-score
+        assert m._ws['gemm_last_ambiguous'] < 0.05 * nq * nentity + 64
