@@ -28,7 +28,11 @@ namespace kge {
 
 constexpr int GM = 128, GN = 128, GK = 32, GSTAGES = 6, GTHREADS = 256;
 constexpr uint32_t kTileBytes = GM * GK * 4;                  // 16 KB per operand tile
-constexpr float kBand = 6.0e-4f;                              // eps = kBand * |q| * |e|   (see header comment)
+// eps = band * |q| * |e| with band = kBandSplit + kBandPerKBlock * (number of 32-wide k-blocks issued):
+//   kBandSplit      operand residuals (3 * 2^-20), the dropped lo*lo term, and the rounding of the canonical fp32 sum
+//   kBandPerKBlock  4 tcgen05.mma per k-block, each assumed to add at most 2^-22 of the magnitude bound |q||e| when it
+//                   folds 8 exact products into the fp32 accumulator (truncating accumulate with a guard bit)
+constexpr float kBandSplit = 1.0e-5f, kBandPerKBlock = 9.6e-7f;
 
 struct GemmArgs {
   const float *pos_score;        // [Q] canonical score of the positive
@@ -42,6 +46,7 @@ struct GemmArgs {
   int Q, pos_col, words;
   int64_t nentity, ent_begin, ent_end;
   int K;                         // contraction length (entity_dim)
+  float band;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -195,7 +200,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
     const int qi = q0 + row;
     const bool qvalid = qi < a.Q;
     const float sp = qvalid ? a.pos_score[qi] : 0.f;
-    const float qn = qvalid ? a.qnorm[qi] * kBand : 0.f;
+    const float qn = qvalid ? a.qnorm[qi] * a.band : 0.f;
     const int64_t pid = qvalid ? a.queries[(int64_t)qi * 3 + a.pos_col] : -1;
     const uint32_t *frow = a.filter_bits + (int64_t)(qvalid ? qi : 0) * a.words;
     int count = 0;
@@ -211,7 +216,8 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mb_wait(tfull + as, (tile_it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
+      uint32_t amask[GN / 32];                                  // ambiguous columns of this row, one word per chunk
+#pragma unroll
       for (int c = 0; c < GN / 32; ++c) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * GN + c * 32);
@@ -226,6 +232,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t am = 0;
         if (qvalid) {
           const int64_t jb = j0 + c * 32;
           const uint32_t fw = jb < a.ent_end ? frow[jb >> 5] : 0u;    // tiles are 32-aligned: one bitmap word
@@ -235,19 +242,42 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
             if (j >= a.ent_end || j == pid || ((fw >> i) & 1u)) continue;
             const float s = __uint_as_float(v[i]);
             const float eps = qn * enorm_s[as * GN + c * 32 + i];
-            if (s - eps > sp) {
-              ++count;
-            } else if (s + eps >= sp) {                        // cannot be decided from the approximation
-              const int slot = atomicAdd(a.amb_count, 1);
-              if (slot < a.amb_capacity) a.amb[slot] = make_int2(qi, (int)j);
-              else a.amb_count[1] = 1;
-            }
+            if (s - eps > sp) ++count;
+            else if (s + eps >= sp) am |= 1u << i;             // cannot be decided from the approximation
           }
         }
+        amask[c] = am;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mb_arrive(tempty + as);                    // 4 epilogue warps -> accumulator free
+      // one reservation per warp and tile in the ambiguous list, then every row writes its own pairs
+      int mine = 0;
+#pragma unroll
+      for (int c = 0; c < GN / 32; ++c) mine += __popc(amask[c]);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.amb_count, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
+#pragma unroll
+        for (int c = 0; c < GN / 32; ++c) {
+          uint32_t am = amask[c];
+          while (am) {
+            const int i = __ffs(am) - 1;
+            am &= am - 1;
+            if (base < a.amb_capacity) a.amb[base] = make_int2(qi, (int)(j0 + c * 32 + i));
+            else a.amb_count[1] = 1;
+            ++base;
+          }
+        }
+      }
     }
     if (qvalid && count) atomicAdd(a.counts + qi, count);
   }
@@ -287,32 +317,9 @@ __global__ void split_tf32_kernel(const float *__restrict__ x, int64_t rows, int
   }
 }
 
-// exact canonical re-score of the ambiguous pairs (same op sequence and order as count_ranks_kernel)
-template <bool CPLX>
-__global__ void rescore_pairs_kernel(const int2 *__restrict__ amb, const int *__restrict__ amb_count, int capacity,
-                                     const float *__restrict__ qvec, const float *__restrict__ E, int d, int De,
-                                     const float *__restrict__ pos_score, const int64_t *__restrict__ queries,
-                                     int pos_col, int32_t *__restrict__ counts) {
-  int n = amb_count[0];
-  if (n > capacity) n = capacity;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int2 p = amb[i];
-    const float *q = qvec + (int64_t)p.x * De, *x = E + (int64_t)p.y * De;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < d; k0 += 32) {
-      float part = 0.f;
-      const int k1 = k0 + 32 < d ? k0 + 32 : d;
-      for (int k = k0; k < k1; ++k) {
-        const float v = CPLX ? fadd(fmul(q[k], x[k]), fmul(q[d + k], x[d + k])) : fmul(q[k], x[k]);
-        part = fadd(part, v);
-      }
-      acc = fadd(acc, part);
-    }
-    const float sp = pos_score[p.x];
-    const int64_t pid = queries[(int64_t)p.x * 3 + pos_col];
-    if (acc > sp || (acc == sp && p.y < pid)) atomicAdd(counts + p.x, 1);
-  }
-}
+int launch_rescore_pairs(bool cplx, const void *amb, const int *amb_count, int capacity, const float *qvec,
+                         const float *E, int d, int De, const float *pos_score, const int64_t *queries, int pos_col,
+                         int32_t *counts, cudaStream_t st);                       // kge_eval.cu (exact op sequence)
 
 // ---- host ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -387,24 +394,21 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   a.counts = counts; a.amb = (int2 *)amb_pairs; a.amb_count = amb_count; a.amb_capacity = (int)amb_capacity;
   a.Q = (int)Q; a.pos_col = mode == KGE_HEAD_BATCH ? 0 : 2; a.words = (int)((m->nentity + 31) / 32);
   a.nentity = m->nentity; a.ent_begin = ent_begin; a.ent_end = ent_end; a.K = (int)K;
+  a.band = kBandSplit + kBandPerKBlock * (float)(3 * ((K + GK - 1) / GK));
   KGE_CUDA_OK(cudaMemsetAsync(amb_count, 0, 2 * sizeof(int), st));
   const size_t smem = 2 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
   KGE_CUDA_OK(cudaFuncSetAttribute(gemm_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int qtiles = (int)((Q + GM - 1) / GM);
   const int64_t jtiles = (ent_end - ent_begin + GN - 1) / GN;
-  int ysplit = (148 + qtiles - 1) / qtiles;                       // fill the SMs when there are few query tiles
+  int ysplit = 148 / qtiles;                                      // one wave: at most 148 CTAs (one per SM)
   if (ysplit > jtiles) ysplit = (int)jtiles;
   if (ysplit < 1) ysplit = 1;
   gemm_count_kernel<<<dim3(qtiles, ysplit), GTHREADS, smem, st>>>(tQhi, tQlo, tEhi, tElo, a);
   KGE_CUDA_OK(cudaGetLastError());
   const bool cplx = m->model == KGE_COMPLEX;
   const int d = cplx ? (int)(K / 2) : (int)K;
-  if (cplx)
-    rescore_pairs_kernel<true><<<148 * 4, 128, 0, st>>>(a.amb, amb_count, a.amb_capacity, qvec, m->entity, d, (int)K,
-                                                        pos_score, queries, a.pos_col, counts);
-  else
-    rescore_pairs_kernel<false><<<148 * 4, 128, 0, st>>>(a.amb, amb_count, a.amb_capacity, qvec, m->entity, d, (int)K,
-                                                         pos_score, queries, a.pos_col, counts);
-  KGE_CUDA_OK(cudaGetLastError());
+  if ((rc = launch_rescore_pairs(cplx, a.amb, amb_count, a.amb_capacity, qvec, m->entity, d, (int)K, pos_score, queries,
+                                 a.pos_col, counts, st)))
+    return rc;
   return KGE_OK;
 }
