@@ -168,6 +168,15 @@ int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const float *qvec,
 int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q,
                          int64_t nentity, uint32_t *filter_bits, void *stream);
 
+/* ---- negative sampling: TrainDataset.__getitem__ (dataloader.py:28-67) on the device ----
+ * For row b (train triple triple_index[b]) draw N entity ids uniformly from the entities that are NOT in the
+ * row's sorted true list true_entities[key_start[t] .. +key_len[t])  (the true heads of (r,t) for head-batch, the
+ * true tails of (h,r) for tail-batch).  Counter-based Philox4x32-10 keyed by (seed, step): the same (seed, step)
+ * gives the same negatives on any device, and oracle/kge_oracle.py restates the stream bit-for-bit.              */
+int kge_sample_negatives(const int64_t *triple_index, const int32_t *key_start, const int32_t *key_len,
+                         const int32_t *true_entities, int64_t B, int64_t N, int64_t nentity, uint64_t seed,
+                         uint64_t step, int64_t *negative, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "kge_eval_gemm_count_ranks": (c_int, [_M, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                           c_int64, c_void_p, c_void_p]),
+    "kge_sample_negatives": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.c_uint64,
+                                     ctypes.c_uint64, c_void_p, c_void_p]),
     "kge_eval_filter_bits": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
 }
 

@@ -437,3 +437,74 @@ def average_precision(y_true, y_score):
     precision = tps / (tps + fps)
     recall = tps / tps[-1]
     return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+# --------------------------------------------------------------------------------------------------
+# negative sampling (dataloader.py:13-119) -- distribution restated, plus the bit-exact Philox stream of
+# kge_sample_negatives so that device negatives can be compared with ==
+# --------------------------------------------------------------------------------------------------
+def count_frequency(triples, start=4):
+    """dataloader.py:77-93."""
+    count = {}
+    for h, r, t in triples:
+        count[(h, r)] = count.get((h, r), start - 1) + 1
+        count[(t, -r - 1)] = count.get((t, -r - 1), start - 1) + 1
+    return count
+
+
+def subsampling_weight(triples):
+    """dataloader.py:33-34: sqrt(1 / (count(h,r) + count(t,-r-1))) in fp32."""
+    count = count_frequency(triples)
+    c = np.array([count[(h, r)] + count[(t, -r - 1)] for h, r, t in triples], dtype=np.float32)
+    return np.sqrt(np.float32(1) / c)
+
+
+def true_head_and_tail(triples):
+    """dataloader.py:95-119."""
+    true_head, true_tail = {}, {}
+    for h, r, t in triples:
+        true_tail.setdefault((h, r), set()).add(t)
+        true_head.setdefault((r, t), set()).add(h)
+    return true_head, true_tail
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011) on uint32 numpy arrays."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)) & mask
+        n1 = p1 & mask
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)) & mask
+        n3 = p0 & mask
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def sample_negatives(triples, index, mode, nentity, N, seed, step):
+    """Bit-exact restatement of kge_sample_negatives: per (row, negative) pair p, candidates come from
+    Philox(counter=(p, 0, attempt, step), key=seed') four at a time, id = (u32 * nentity) >> 32, the first candidate
+    outside the row's true set is kept (dataloader.py:38-61 keeps the first survivors of a uniform stream)."""
+    true_head, true_tail = true_head_and_tail(triples)
+    seed = (int(seed) << 1) | (1 if mode == 'head-batch' else 0)
+    k0, k1 = seed & 0xFFFFFFFF, ((seed >> 32) ^ (int(step) >> 32)) & 0xFFFFFFFF
+    out = np.zeros((len(index), N), dtype=np.int64)
+    for b, ti in enumerate(index):
+        h, r, t = triples[int(ti)]
+        true = true_head[(r, t)] if mode == 'head-batch' else true_tail[(h, r)]
+        for n in range(N):
+            p = b * N + n
+            attempt = 0
+            while True:
+                r4 = _philox4x32_10([p & 0xFFFFFFFF], [p >> 32], [attempt], [int(step) & 0xFFFFFFFF], k0, k1)
+                cands = [int((int(x[0]) * nentity) >> 32) for x in r4]
+                ok = [c for c in cands if c not in true]
+                if ok:
+                    out[b, n] = ok[0]
+                    break
+                attempt += 1
+    return out
