@@ -281,7 +281,7 @@ def run_gpu(args):
                    "negative_sample_size": N, "batch_size_per_gpu": B, "global_batch": Bg, "gamma": gamma,
                    "adversarial": True, "double_entity_embedding": de, "parallelism": f"dp{world}",
                    "l2_policy": "no flush: each step streams 0.6 GB of tables+moments+grads (> 126 MB L2)"},
-        "clocks": clocks, "gpu_launches": 8 * args.steps,
+        "clocks": clocks, "gpu_launches": 7 * args.steps,
         "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "last_loss": last.get("loss")},
         "roofline": roofline, "cpu_baseline": cpu,

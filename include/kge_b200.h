@@ -82,12 +82,14 @@ int kge_score_backward(const kge_model_t *m, int mode, const int64_t *positive, 
  *   weight: subsampling_weight [B_total] or NULL (= --uni_weight);  weight_sum: device scalar sum(weight)
  *   row_begin/row_count: this rank's slice of the batch (row_count == B_total on one GPU)
  *   row_loss [B_total]: per-row  sum_j w_ij logsig(-s_ij)  (NEG) or logsig(s_i) (POSITIVE)
+ *   pos_row_loss [B_total] or NULL: with a NEG loss_kind, also run the positive triple of every row (model.py:277-279)
+ *                and write logsig(s_i+) here -- fused into the same launch when the single-read path is taken
  *   score_out: optional [row_count, N] copy of the scores (tests), may be NULL
  *   workspace: kge_train_workspace_bytes(m, row_count, N) bytes of device scratch, or NULL        */
 int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
                    const int64_t *positive, const int64_t *negative, const float *weight,
                    const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
-                   int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
+                   int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity, float *grad_relation,
                    float *grad_modulus, float *score_out, void *workspace, int64_t workspace_bytes,
                    int32_t *err_flag, void *stream);
 

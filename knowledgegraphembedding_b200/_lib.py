@@ -37,8 +37,8 @@ PROTOTYPES = {
     "kge_score_backward": (c_int, [_M, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "kge_train_rows": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                               c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                               c_void_p, c_void_p]),
+                               c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int64, c_void_p, c_void_p]),
     "kge_train_workspace_bytes": (c_int64, [_M, c_int64, c_int64]),
     "kge_zero": (c_int, [c_void_p, c_int64, c_void_p]),
     "kge_weight_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

@@ -35,10 +35,12 @@ struct RowArgs {
   const float *weight, *wsum;
   float uniform_u;
   float *row_loss;
+  float *pos_row_loss;         // split path only: also do the positive triple of each row (fused 'single' pass)
   float *score_out;
   const float *dscore;
   float *gE, *gR, *gM;
   int32_t *err;
+  int *fused_positive;         // host-side out flag: the launched variant handled pos_row_loss itself
 };
 
 constexpr int kChunks = 8;     // units per lane per k-tile: 8 x float4 x (re,im) = 64 accumulator registers
@@ -597,6 +599,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
         k<<<grid, W * 32, total, st>>>(a, ws);
         KGE_CUDA_OK(cudaGetLastError());
+        if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
       }
       scan_offsets_kernel<<<1, 1024, 0, st>>>(ws.cnt, ws.cursor, a.nentity);
       KGE_CUDA_OK(cudaGetLastError());
@@ -738,9 +741,9 @@ extern "C" int kge_score_backward(const kge_model_t *m, int mode, const int64_t 
 extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
                               const int64_t *positive, const int64_t *negative, const float *weight,
                               const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
-                              int64_t N, float *row_loss, float *grad_entity, float *grad_relation,
-                              float *grad_modulus, float *score_out, void *workspace, int64_t workspace_bytes,
-                              int32_t *err_flag, void *stream) {
+                              int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity,
+                              float *grad_relation, float *grad_modulus, float *score_out, void *workspace,
+                              int64_t workspace_bytes, int32_t *err_flag, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(positive && row_loss && grad_entity && grad_relation, "null pointer");
@@ -758,8 +761,16 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
   a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
   a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
   a.row_loss = row_loss; a.score_out = score_out;
+  a.pos_row_loss = loss_kind == KGE_LOSS_POSITIVE ? nullptr : pos_row_loss;
   a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
-  return launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
+  int fused_positive = 0;
+  a.fused_positive = &fused_positive;
+  rc = launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
+  if (rc || !a.pos_row_loss || fused_positive) return rc;
+  // the kernel variant that ran has no fused positive pass: run the 'single' pass as its own launch
+  return kge_train_rows(m, KGE_SINGLE, KGE_LOSS_POSITIVE, 1.0f, positive, negative, weight, weight_sum, B_total, row_begin,
+                        row_count, 1, pos_row_loss, nullptr, grad_entity, grad_relation, grad_modulus, nullptr, nullptr, 0,
+                        err_flag, stream);
 }
 
 extern "C" int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N) {

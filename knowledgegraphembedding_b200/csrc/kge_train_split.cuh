@@ -262,6 +262,48 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
       if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
       if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
     }
+    // ---- fused positive triple (model.py:277-279, 'single' mode = the non-head-batch association): the block
+    // rebuilds q = fold(h, r), scores the positive tail, and pushes dL/ds+ through the same element functions.
+    if (a.pos_row_loss) {
+      constexpr int OPS = op_of(MODEL, false);
+      __syncthreads();                                      // dq / q of the negatives are no longer needed
+      int64_t ph = hid, pt = tidx;
+      if ((uint64_t)ph >= (uint64_t)a.nentity) ph = 0;
+      if ((uint64_t)pt >= (uint64_t)a.nentity) pt = 0;
+      const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
+      for (int k = tid; k < a.d; k += blockDim.x) build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q);
+      __syncthreads();
+      float part = 0.f;
+      for (int k = tid; k < a.d; k += blockDim.x)
+        part += op_forward<OPS>(q[k], CPLX ? q[a.d + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale);
+      part = block_reduce(part, scratch, false);
+      const float sp = finish_score<MODEL>(part, a.gamma, modulus);
+      const float up = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
+      const float gp = -0.5f * up * sigmoid(-sp);
+      if (tid == 0) {
+        a.pos_row_loss[b] = log_sigmoid(sp);
+        if constexpr (MODEL == KGE_PROTATE) { if (a.gM) red_add1(a.gM, -gp * part); }
+      }
+      const float gop = dsum_of<MODEL>(gp, modulus);
+      float *gT = a.gE + pt * a.De;
+      for (int k = tid; k < a.d; k += blockDim.x) {
+        float dq0 = 0.f, dq1 = 0.f, dx0 = 0.f, dx1 = 0.f;
+        op_backward<OPS>(q[k], CPLX ? q[a.d + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale, gop, dq0, dq1, dx0, dx1);
+        dq[k] = dq0;
+        red_add1(gT + k, dx0);
+        if constexpr (CPLX) { dq[a.d + k] = dq1; red_add1(gT + a.d + k, dx1); }
+      }
+      __syncthreads();
+      float *gH = a.gE + ph * a.De;
+      for (int k = tid; k < a.d; k += blockDim.x) {
+        float dF0, dF1, dR0, dR1;
+        chain_q<MODEL, false>(Hrow, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
+        red_add1(gH + k, dF0);
+        red_add1(gRr + k, dR0);
+        if constexpr (CPLX) red_add1(gH + a.d + k, dF1);
+        if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staging stores vs the next row's bulk copies
     __syncthreads();
   }

@@ -350,12 +350,11 @@ class KGEModel(nn.Module):
             ev0.record()
         _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode],
                   _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM, alpha, *common,
-                  _ptr(ws['neg_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp), wbytes, _ptr(err), st)
+                  _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
+                  wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
         if events is not None:
             ev1.record()
             events.append((ev0, ev1))
-        _lib.call("kge_train_rows", ctypes.byref(desc), _lib.SINGLE, _lib.LOSS_POSITIVE, 1.0, *common,
-                  _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, None, 0, _ptr(err), st)
         if world > 1:
             # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
             torch.distributed.all_reduce(ws['flat'])

@@ -481,3 +481,40 @@ def test_tcgen05_eval_ranks_identical_to_exact_kernel(model, nentity, nrel, d, g
         np.testing.assert_array_equal(fast, exact)
         # the band is narrow: only a small fraction of the Q x nentity pairs needs the exact re-score
         assert m._ws['gemm_last_ambiguous'] < 0.05 * nq * nentity + 64
+
+
+def test_batch_sharded_rows_sum_to_full_batch():
+    """The multi-GPU train path: every rank runs kge_train_rows on its row slice with the global weight sum; the
+    gradient buffers and per-row losses add up to the single-GPU result (what the NCCL all-reduce then delivers)."""
+    import ctypes
+    from knowledgegraphembedding_b200 import _lib, shard_bounds
+    from knowledgegraphembedding_b200.model import _ptr, _stream
+    nentity, nrel, d, gamma, B, N = 4000, 9, 64, 9.0, 50, 40
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=8)
+    m = make_model("RotatE", nentity, nrel, d, gamma, st)
+    dev = m.entity_embedding.device
+    rng = np.random.RandomState(9)
+    pos = torch.from_numpy(np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)).to(dev)
+    neg = torch.from_numpy(rng.randint(nentity, size=(B, N))).to(dev)
+    w = torch.from_numpy(np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)).to(dev)
+    wsum = w.sum().reshape(1)
+    desc, stt = m._descriptor(), _stream(dev)
+
+    def run(world):
+        gE, gR = torch.zeros_like(m.entity_embedding), torch.zeros_like(m.relation_embedding)
+        rows = torch.zeros(2, B, device=dev)
+        for rank in range(world):
+            b, e = shard_bounds(B, rank, world)
+            nb = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), e - b, N)
+            wsp = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.call("kge_train_rows", ctypes.byref(desc), _lib.HEAD_BATCH, _lib.LOSS_NEG_ADVERSARIAL, 1.0, _ptr(pos),
+                      _ptr(neg), _ptr(w), _ptr(wsum), B, b, e - b, N, _ptr(rows[0]), _ptr(rows[1]), _ptr(gE), _ptr(gR),
+                      None, None, _ptr(wsp), nb, None, stt)
+        torch.cuda.synchronize()
+        return gE.cpu().numpy(), gR.cpu().numpy(), rows.cpu().numpy()
+
+    full = run(1)
+    for world in (2, 3, 8):
+        part = run(world)
+        assert relinf(part[0], full[0]) < 1e-6 and relinf(part[1], full[1]) < 1e-6
+        np.testing.assert_allclose(part[2], full[2], rtol=1e-6)
