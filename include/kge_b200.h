@@ -150,6 +150,16 @@ int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, cons
                          const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
                          int32_t *counts, float *scores_out, void *stream);
 
+/* Two-stage variant of step 3 (RotatE): a fast tile pass (approximate sqrt, free association) counts every candidate
+ * whose order against the positive is certain under a proven error band; the few undecidable (q, j) pairs are
+ * re-scored with the exact op sequence.  Counts are identical to kge_eval_count_ranks.  Models without a fast
+ * variant run the exact kernel.  amb_count[1] = 1 reports an overflow of amb_pairs (caller re-runs exact).       */
+int kge_eval_count_ranks_two_stage(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries,
+                                   int64_t Q, const float *phase_table, const float *pos_score,
+                                   const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
+                                   int32_t *counts, void *amb_pairs, int64_t amb_capacity, int32_t *amb_count,
+                                   void *stream);
+
 /* ---- tcgen05 path for the dot-product models (DistMult model.py:175-182, ComplEx :184-199) in test_step ----
  * The all-entity scores are one [Q, D_e] x [D_e, nentity] contraction.  Operands are split into two TF32-exact
  * pieces (kge_eval_gemm_split: hi, lo and the row norms), a tcgen05.mma kind::tf32 kernel accumulates

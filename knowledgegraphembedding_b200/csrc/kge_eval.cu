@@ -28,6 +28,19 @@ __device__ __forceinline__ float op_exact(float q0, float q1, float x0, float x1
   else return fabsf(sin_rep(fadd(x0, q0)));                                        // model.py:241
 }
 
+// Fast (non-canonical) element op of the two-stage RotatE evaluation: contraction allowed, one-instruction
+// approximate sqrt.  Per-term relative deviation from op_exact is below 2^-20 (sqrt.approx <= 2^-21, the a^2+b^2
+// association <= 2^-22, exact rounding <= 2^-24); see kFastBand.
+template <int OP>
+__device__ __forceinline__ float op_fast(float q0, float q1, float x0, float x1) {
+  static_assert(OP == OP_CDIST, "only the complex-modulus op has a fast variant");
+  const float a = q0 - x0, b = q1 - x1;
+  return sqrt_approx(fmaf(a, a, b * b));
+}
+// |s_fast - s_canonical| <= kFastBand * (gamma - s_fast): 2^-20 per term + two blocked fp32 sums of the same
+// blocks (each within (32 + d/32) * 2^-24 <= 6e-6 of the exact sum for d <= 2048), rounded up.
+constexpr float kFastBand = 1.6e-5f;
+
 template <int OP>
 __device__ __forceinline__ float finish_exact(float acc, float gamma, float modulus) {
   if constexpr (OP == OP_MUL || OP == OP_CMUL) return acc;
@@ -140,6 +153,9 @@ struct EvalArgs {
   int64_t Q, nentity, ent_begin, ent_end;
   int d, De, pos_col, words;
   float gamma;
+  int2 *amb;                    // two-stage mode: ambiguous (q, j) pairs for the exact re-score
+  int *amb_count;               // [0] appended, [1] overflow
+  int amb_capacity;
 };
 
 // Stage one k-chunk of the query tile and the entity tile:  smem[row][half][ST]
@@ -168,7 +184,7 @@ __device__ __forceinline__ void stage_tiles(const EvalArgs &a, float *sq, float 
   }
 }
 
-template <int OP, bool ALIGNED>
+template <int OP, bool ALIGNED, bool FAST = false>
 __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const EvalArgs a) {
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
@@ -224,10 +240,17 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {       // k ascending inside the group => index-order accumulation
-          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].x, qb[i].x, xa[j].x, xb[j].x));
-          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].y, qb[i].y, xa[j].y, xb[j].y));
-          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z));
-          part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].w, qb[i].w, xa[j].w, xb[j].w));
+          if constexpr (FAST) {
+            part[i][j] += op_fast<OP>(qa[i].x, qb[i].x, xa[j].x, xb[j].x);
+            part[i][j] += op_fast<OP>(qa[i].y, qb[i].y, xa[j].y, xb[j].y);
+            part[i][j] += op_fast<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z);
+            part[i][j] += op_fast<OP>(qa[i].w, qb[i].w, xa[j].w, xb[j].w);
+          } else {
+            part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].x, qb[i].x, xa[j].x, xb[j].x));
+            part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].y, qb[i].y, xa[j].y, xb[j].y));
+            part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z));
+            part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].w, qb[i].w, xa[j].w, xb[j].w));
+          }
         }
     }
 #pragma unroll
@@ -253,7 +276,19 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
       float s = finish_exact<OP>(acc[i][j], a.gamma, modulus);
       const bool filtered = ej != pid && ((a.filter_bits[qi * a.words + (ej >> 5)] >> (ej & 31)) & 1u);
       if (filtered) s = fadd(sp, -1.0f);                   // candidate replaced by the positive, bias -1
-      else if (ej != pid) c += (s > sp) || (s == sp && ej < pid);
+      else if (ej != pid) {
+        if constexpr (FAST) {                              // s is only within eps of the canonical score
+          const float eps = kFastBand * (a.gamma - s) + 1e-12f;
+          if (s - eps > sp) ++c;
+          else if (s + eps >= sp) {                        // undecidable here: exact re-score later
+            const int slot = atomicAdd(a.amb_count, 1);
+            if (slot < a.amb_capacity) a.amb[slot] = make_int2((int)qi, (int)ej);
+            else a.amb_count[1] = 1;
+          }
+        } else {
+          c += (s > sp) || (s == sp && ej < pid);
+        }
+      }
       if (a.scores_out) a.scores_out[qi * a.nentity + ej] = s;
     }
     if (c) atomicAdd(&cnt_sh[tq + 16 * i], c);
@@ -267,14 +302,15 @@ template <int OP>
 __global__ void rescore_pairs_kernel(const int2 *__restrict__ amb, const int *__restrict__ amb_count, int capacity,
                                      const float *__restrict__ qvec, const float *__restrict__ E, int d, int De,
                                      const float *__restrict__ pos_score, const int64_t *__restrict__ queries,
-                                     int pos_col, int32_t *__restrict__ counts) {
+                                     int pos_col, float gamma, int32_t *__restrict__ counts) {
   int n = amb_count[0];
   if (n > capacity) n = capacity;
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int i = wid; i < n; i += nw) {
     const int2 p = amb[i];
-    const float s = canonical_pair_score<OP>(qvec + (int64_t)p.x * De, E + (int64_t)p.y * De, d);   // gamma-free ops
+    const float s = finish_exact<OP>(canonical_pair_score<OP>(qvec + (int64_t)p.x * De, E + (int64_t)p.y * De, d),
+                                     gamma, 1.f);
     if (lane == 0) {
       const float sp = pos_score[p.x];
       const int64_t pid = queries[(int64_t)p.x * 3 + pos_col];
@@ -288,10 +324,10 @@ int launch_rescore_pairs(bool cplx, const void *amb, const int *amb_count, int c
                          int32_t *counts, cudaStream_t st) {
   if (cplx)
     rescore_pairs_kernel<OP_CMUL><<<148 * 8, 256, 0, st>>>((const int2 *)amb, amb_count, capacity, qvec, E, d, De,
-                                                           pos_score, queries, pos_col, counts);
+                                                           pos_score, queries, pos_col, 0.f, counts);
   else
     rescore_pairs_kernel<OP_MUL><<<148 * 8, 256, 0, st>>>((const int2 *)amb, amb_count, capacity, qvec, E, d, De,
-                                                          pos_score, queries, pos_col, counts);
+                                                          pos_score, queries, pos_col, 0.f, counts);
   KGE_CUDA_OK(cudaGetLastError());
   return KGE_OK;
 }
@@ -312,6 +348,19 @@ static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
   constexpr int H = op_is_complex(OP) ? 2 : 1;
   const size_t smem = sizeof(float) * 2 * (TQ + TJ) * H * ST;
   dim3 grid((unsigned)((a.ent_end - a.ent_begin + TJ - 1) / TJ), (unsigned)((a.Q + TQ - 1) / TQ));
+  if constexpr (OP == OP_CDIST) {
+    if (a.amb && aligned && !a.scores_out && a.d <= 2048) {          // two-stage: fast tile pass + exact re-score
+      KGE_CUDA_OK(cudaMemsetAsync(a.amb_count, 0, 2 * sizeof(int), st));
+      auto k = count_ranks_kernel<OP, true, true>;
+      KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, EVAL_THREADS, smem, st>>>(a);
+      KGE_CUDA_OK(cudaGetLastError());
+      rescore_pairs_kernel<OP><<<148 * 4, 256, 0, st>>>(a.amb, a.amb_count, a.amb_capacity, a.qvec, a.X, a.d, a.De,
+                                                        a.pos_score, a.queries, a.pos_col, a.gamma, a.counts);
+      KGE_CUDA_OK(cudaGetLastError());
+      return KGE_OK;
+    }
+  }
   if (aligned) {
     auto k = count_ranks_kernel<OP, true>;
     KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -432,10 +481,33 @@ extern "C" int kge_eval_positive_scores(const kge_model_t *m, int mode, const fl
   return KGE_OK;
 }
 
+static int count_ranks_impl(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries, int64_t Q,
+                            const float *phase_table, const float *pos_score, const uint32_t *filter_bits,
+                            int64_t ent_begin, int64_t ent_end, int32_t *counts, float *scores_out, void *amb_pairs,
+                            int64_t amb_capacity, int32_t *amb_count, void *stream);
+
 extern "C" int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries, int64_t Q,
                                     const float *phase_table, const float *pos_score, const uint32_t *filter_bits,
                                     int64_t ent_begin, int64_t ent_end, int32_t *counts, float *scores_out,
                                     void *stream) {
+  return count_ranks_impl(m, mode, qvec, queries, Q, phase_table, pos_score, filter_bits, ent_begin, ent_end, counts,
+                          scores_out, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int kge_eval_count_ranks_two_stage(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries,
+                                              int64_t Q, const float *phase_table, const float *pos_score,
+                                              const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
+                                              int32_t *counts, void *amb_pairs, int64_t amb_capacity,
+                                              int32_t *amb_count, void *stream) {
+  KGE_REQUIRE(amb_pairs && amb_count && amb_capacity > 0, "two-stage ranking needs the ambiguous-pair buffers");
+  return count_ranks_impl(m, mode, qvec, queries, Q, phase_table, pos_score, filter_bits, ent_begin, ent_end, counts,
+                          nullptr, amb_pairs, amb_capacity, amb_count, stream);
+}
+
+static int count_ranks_impl(const kge_model_t *m, int mode, const float *qvec, const int64_t *queries, int64_t Q,
+                            const float *phase_table, const float *pos_score, const uint32_t *filter_bits,
+                            int64_t ent_begin, int64_t ent_end, int32_t *counts, float *scores_out, void *amb_pairs,
+                            int64_t amb_capacity, int32_t *amb_count, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
   bool head;
@@ -450,6 +522,7 @@ extern "C" int kge_eval_count_ranks(const kge_model_t *m, int mode, const float 
   if ((rc = fill_eval_args(m, head, qvec, queries, Q, phase_table, a))) return rc;
   a.pos_score = pos_score; a.filter_bits = filter_bits; a.counts = counts; a.scores_out = scores_out;
   a.ent_begin = ent_begin; a.ent_end = ent_end;
+  a.amb = (int2 *)amb_pairs; a.amb_count = amb_count; a.amb_capacity = (int)amb_capacity;
   const bool aligned = (a.d % 4 == 0) && (a.De % 4 == 0) && ((((uintptr_t)a.qvec | (uintptr_t)a.X) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
 #define KGE_CR(OP) \

@@ -159,6 +159,7 @@ class KGEModel(nn.Module):
         if buf is None or buf.numel() < numel or buf.device != device or buf.dtype != dtype:
             buf = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
             self._ws[key] = buf
+            self._ws.pop('grad_views', None)
         return buf
 
     def _err_flag(self):
@@ -255,6 +256,9 @@ class KGEModel(nn.Module):
         """One flat fp32 buffer [dE | dR | dModulus(4) | pos_row[B] | neg_row[B]] so that the multi-GPU
         exchange is a single all-reduce, plus the small scalar buffers."""
         dev = self.entity_embedding.device
+        cached = self._ws.get('grad_views')
+        if cached is not None and cached[0] == (B, dev):
+            return dict(cached[1])
         nE, nR = self.entity_embedding.numel(), self.relation_embedding.numel()
         nE4, nR4 = (nE + 3) // 4 * 4, (nR + 3) // 4 * 4
         total = nE4 + nR4 + 4 + 2 * B
@@ -269,7 +273,8 @@ class KGEModel(nn.Module):
             'wsum': self._buffer('wsum', 1, torch.float32, dev),
             'reg': self._buffer('reg_partials', 148 * 8, torch.float64, dev),
         }
-        return views
+        self._ws['grad_views'] = ((B, dev), views)           # slicing costs ~10 us per view: do it once per batch size
+        return dict(views)
 
     @staticmethod
     def _fusable_adam(model, optimizer):
@@ -431,6 +436,8 @@ class KGEModel(nn.Module):
         import os
         gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not return_scores \
             and not os.environ.get("KGE_EVAL_SIMT")
+        two_stage = self.model_name == 'RotatE' and not return_scores and not os.environ.get("KGE_EVAL_SIMT") \
+            and self.entity_dim % 8 == 0
         if gemm:
             nE = self.entity_embedding.numel()
             ehi = self._buffer('gemm_ehi', nE, torch.float32, dev)
@@ -480,6 +487,21 @@ class KGEModel(nn.Module):
                         events.append((ev0, ev1))
                     continue
                 counts.zero_()                               # ambiguous list overflowed: exact kernel for this chunk
+            elif two_stage:
+                cap = Q * 256
+                amb = self._buffer('gemm_amb', cap * 2, torch.int32, dev)
+                amb_count = self._buffer('gemm_amb_count', 2, torch.int32, dev)
+                _lib.call("kge_eval_count_ranks_two_stage", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q,
+                          _ptr(phase), _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts), _ptr(amb), cap,
+                          _ptr(amb_count), st)
+                stats = amb_count[:2].tolist()
+                self._ws['two_stage_last_ambiguous'] = stats[0]
+                if stats[1] == 0:
+                    if events is not None:
+                        ev1.record()
+                        events.append((ev0, ev1))
+                    continue
+                counts.zero_()
             _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
                       _ptr(scores[lo:lo + Q]) if scores is not None else None, st)

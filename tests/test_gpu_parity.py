@@ -518,3 +518,30 @@ def test_batch_sharded_rows_sum_to_full_batch():
         part = run(world)
         assert relinf(part[0], full[0]) < 1e-6 and relinf(part[1], full[1]) < 1e-6
         np.testing.assert_allclose(part[2], full[2], rtol=1e-6)
+
+
+@pytest.mark.parametrize("nentity,nrel,d,gamma,nq,scale", [
+    (14951, 1345, 1000, 24.0, 160, 1.0),      # FB15k shape at random init: scores nearly tied (worst case for the band)
+    (14951, 1345, 1000, 24.0, 160, 4.0),
+    (123182, 37, 500, 24.0, 48, 2.0),         # YAGO3-10 shape
+    (1031, 5, 36, 6.0, 200, 3.0),
+])
+def test_two_stage_rotate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d, gamma, nq, scale, monkeypatch):
+    """RotatE filtered ranking through the fast tile pass + exact re-score of the undecidable band gives the same
+    integer ranks as the exact kernel (which is bit-exact against the C oracle)."""
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=12)
+    st["entity_embedding"] = (st["entity_embedding"] * scale).astype(np.float32)
+    rng = np.random.RandomState(13)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(min(nentity, 400))))
+                       for _ in range(20000)})
+    test = [all_true[i] for i in rng.choice(len(all_true), nq, replace=False)]
+    m = make_model("RotatE", nentity, nrel, d, gamma, st)
+    for mode in ("head-batch", "tail-batch"):
+        monkeypatch.setenv("KGE_EVAL_SIMT", "1")
+        exact = m.filtered_ranks(test, all_true, mode)
+        monkeypatch.delenv("KGE_EVAL_SIMT")
+        m._ws.pop('two_stage_last_ambiguous', None)
+        fast = m.filtered_ranks(test, all_true, mode)
+        assert 'two_stage_last_ambiguous' in m._ws, "two-stage path was not taken"
+        np.testing.assert_array_equal(fast, exact)
+        assert m._ws['two_stage_last_ambiguous'] < 0.02 * nq * nentity + 64
