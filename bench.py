@@ -83,6 +83,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(wl):
+    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1g.raw.csv:
+    dram__bytes_read.sum + dram__bytes_write.sum of row_kernel_split + entity_kernel); only for the captured workload."""
+    path = os.path.join(ROOT, "profiles", "prof_train_r1g.raw.csv")
+    if wl != "rotate_fb15k" or not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    total = 0.0
+    for r in rows[2:]:
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            total += float(r[i]) * scale
+    return total
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -264,8 +282,8 @@ def run_gpu(args):
     roofline = None
     if row_ms:
         ach = a_bytes / (row_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "row_kernel (negative pass)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes,
+        roofline = {"bound": "hbm", "kernel": "kge_train_rows: row_kernel_split + counting sort + entity_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": ncu_traffic(wl), "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes,
                     "avg_launch_ms": row_ms}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
