@@ -624,7 +624,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         e.upp = two ? (nunits + 1) / 2 : nunits;
         const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * e.upp * 16;
         int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
-        const int wmax = two ? 24 : 12;
+        const int wmax = two ? 20 : 12;
         if (We > wmax) We = wmax;
         const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
         if (two) {

@@ -378,7 +378,7 @@ struct EntArgs {
 // k axis needs no exchange between warps; S = 2 halves the per-thread registers (x and the accumulators) and the
 // slot size, which doubles the resident warps (24 per SM) for latency hiding.
 template <int MODEL, bool HEAD, int S>
-__global__ void __launch_bounds__(S == 1 ? 384 : 768, 1) entity_kernel(const EntArgs a) {
+__global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const EntArgs a) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
@@ -413,13 +413,25 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 768, 1) entity_kernel(const Ent
     if (beg == end || ucnt <= 0) continue;
     const uint32_t segbytes = (uint32_t)ucnt * V * 4u;
 
+    // (row index, dL/ds) of the entity's pairs are fetched 32 at a time, one coalesced load per lane, and handed out
+    // by shuffle: no dependent global load sits in front of a bulk copy
+    int prow = 0;
+    float pg = 0.f;
+    int pbase = beg - 32;                                   // first pair held in (prow, pg)
+    auto refill = [&](int i) {
+      pbase = i;
+      prow = i + lane < end ? a.perm[i + lane] : 0;
+      pg = i + lane < end ? a.gsorted[i + lane] : 0.f;
+    };
     auto issue = [&](int s, int i) {
-      const float g = a.gsorted[i];
+      if (i >= pbase + 32) refill(i);
+      const int row = __shfl_sync(0xffffffffu, prow, i - pbase);
+      const float g = __shfl_sync(0xffffffffu, pg, i - pbase);
       if (s) g1 = g; else g0 = g;
       if (lane == 0) {
         uint64_t *bar = s ? bar1 : bar0;
         float *dst = s ? slot1 : slot0;
-        const float *src = a.Qtab + (size_t)a.perm[i] * a.De + ubeg * V;
+        const float *src = a.Qtab + (size_t)row * a.De + ubeg * V;
         mbar_expect_tx(bar, segbytes * H);
         bulk_g2s(dst, src, segbytes, bar);
         if constexpr (CPLX) bulk_g2s(dst + a.upp * V, src + a.d, segbytes, bar);
@@ -473,22 +485,15 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 768, 1) entity_kernel(const Ent
         if (a.need_gmod) gmod += -g * warp_sum(vsum);
       }
     }
-    // the warp owns this part of gradient row e during the kernel: plain read-modify-write, no atomics
+    // one fire-and-forget 16-byte reduction per float4 of the (half) gradient row: this warp is the only writer of
+    // these words in this kernel, so the sum is as deterministic as a store, and no load latency is exposed
     float *grow = a.gE + (size_t)e * a.De + ubeg * V;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int u = lane + 32 * c;
       if (u < ucnt) {
-        float4 *p0 = reinterpret_cast<float4 *>(grow + u * V);
-        float4 v = *p0;
-        v.x += acc[c][0][0]; v.y += acc[c][0][1]; v.z += acc[c][0][2]; v.w += acc[c][0][3];
-        *p0 = v;
-        if constexpr (CPLX) {
-          float4 *p1 = reinterpret_cast<float4 *>(grow + a.d + u * V);
-          float4 w = *p1;
-          w.x += acc[c][1][0]; w.y += acc[c][1][1]; w.z += acc[c][1][2]; w.w += acc[c][1][3];
-          *p1 = w;
-        }
+        red_add4(grow + u * V, acc[c][0][0], acc[c][0][1], acc[c][0][2], acc[c][0][3]);
+        if constexpr (CPLX) red_add4(grow + a.d + u * V, acc[c][1][0], acc[c][1][1], acc[c][1][2], acc[c][1][3]);
       }
     }
   }
