@@ -299,7 +299,8 @@ class KGEModel(nn.Module):
         '''
         model.train()
         optimizer.zero_grad()
-        out = model.train_step_async(optimizer, next(train_iterator), args)
+        out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
+        model._prefetch_batch(train_iterator)     # next batch's next() + H2D overlap this step's kernels
         reg = float(getattr(args, 'regularization', 0.0))
         out = out.tolist()                        # the step's single device->host sync (model.py:305-310 has 3-4)
         if out[4] != 0.0:
@@ -313,6 +314,53 @@ class KGEModel(nn.Module):
             'loss': out[2]
         }
         return log
+
+    # ---- input pipelining: the reference pulls one batch per step (model.py:261) and copies it synchronously
+    # (model.py:263-266).  We pull the batch of step i+1 right after launching step i and copy it on a side stream,
+    # so next() and the H2D copy run under step i's kernels.  One batch is held ahead per iterator; exhaustion is
+    # re-raised at the call that would have hit it.  KGE_NO_PREFETCH=1 restores strict pull-at-call behaviour.
+    def _stage_batch(self, batch, stream=None):
+        positive_sample, negative_sample, subsampling_weight, mode = batch
+        dev = self.entity_embedding.device
+        if stream is None:
+            return batch
+        with torch.cuda.stream(stream):
+            staged = (positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True),
+                      negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True),
+                      subsampling_weight.to(device=dev, dtype=torch.float32, non_blocking=True), mode)
+        return staged
+
+    def _next_batch(self, iterator):
+        held = self._ws.pop('prefetched', None)
+        if held is not None and held[0] is iterator:
+            _, batch, error, stream = held
+            if error is not None:
+                raise error
+            if stream is not None:
+                cur = torch.cuda.current_stream(self.entity_embedding.device)
+                cur.wait_stream(stream)
+                for t in batch[:3]:
+                    if t.is_cuda:
+                        t.record_stream(cur)
+            return batch
+        return next(iterator)
+
+    def _prefetch_batch(self, iterator):
+        import os
+        if os.environ.get('KGE_NO_PREFETCH') or self.entity_embedding.device.type != 'cuda':
+            return
+        try:
+            batch = next(iterator)
+        except Exception as exc:                  # StopIteration (finite iterators) or a loader error: re-raise next call
+            self._ws['prefetched'] = (iterator, None, exc, None)
+            return
+        stream = None
+        if not batch[1].is_cuda:
+            stream = self._ws.get('copy_stream')
+            if stream is None:
+                stream = self._ws['copy_stream'] = torch.cuda.Stream(self.entity_embedding.device)
+            batch = self._stage_batch(batch, stream)
+        self._ws['prefetched'] = (iterator, batch, None, stream)
 
     def train_step_async(self, optimizer, batch, args):
         """Everything train_step does on the device, without the final read-back: returns the device buffer

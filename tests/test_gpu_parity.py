@@ -545,3 +545,34 @@ def test_two_stage_rotate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d,
         assert 'two_stage_last_ambiguous' in m._ws, "two-stage path was not taken"
         np.testing.assert_array_equal(fast, exact)
         assert m._ws['two_stage_last_ambiguous'] < 0.02 * nq * nentity + 64
+
+
+def test_train_step_input_prefetch_semantics():
+    """One batch is pulled ahead per iterator (copied on a side stream under the current step); a finite iterator of
+    K batches still yields exactly K steps and raises StopIteration at call K+1, like the reference's next() at
+    model.py:261; results do not depend on the prefetch."""
+    torch.manual_seed(0)
+    st = O.init_tables("RotatE", 500, 5, 16, 6.0, True, False, seed=2)
+    args = ns(negative_adversarial_sampling=True)
+    batches = []
+    for i in range(3):
+        pos = torch.stack([torch.randint(500, (32,)), torch.randint(5, (32,)), torch.randint(500, (32,))], 1)
+        batches.append((pos.pin_memory(), torch.randint(500, (32, 16)).pin_memory(), (torch.rand(32) + 0.1).pin_memory(),
+                        "tail-batch" if i % 2 == 0 else "head-batch"))
+    results = {}
+    for tag in ("prefetch", "strict"):
+        if tag == "strict":
+            os.environ["KGE_NO_PREFETCH"] = "1"
+        try:
+            m = make_model("RotatE", 500, 5, 16, 6.0, st)
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+            it = iter(batches)
+            logs = [KGE().train_step(m, opt, it, args) for _ in range(3)]
+            with pytest.raises(StopIteration):
+                KGE().train_step(m, opt, it, args)
+            results[tag] = (logs, m.entity_embedding.detach().cpu().numpy().copy())
+        finally:
+            os.environ.pop("KGE_NO_PREFETCH", None)
+    for a, b in zip(results["prefetch"][0], results["strict"][0]):
+        assert a.keys() == b.keys() and all(abs(a[k] - b[k]) <= 1e-6 * abs(b[k]) for k in a)
+    assert relinf(results["prefetch"][1], results["strict"][1]) < 1e-6
