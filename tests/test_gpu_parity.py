@@ -119,8 +119,12 @@ CFGS = {
 @pytest.mark.parametrize("model", MODELS)
 @pytest.mark.parametrize("d", [12, 10])
 @pytest.mark.parametrize("cfg", list(CFGS))
-def test_train_steps_vs_reference_golden(model, d, cfg):
-    """4 train_steps with the run.py call sequence (incl. the Adam re-creation of run.py:315-322)."""
+@pytest.mark.parametrize("path", ["default", "single_read"])
+def test_train_steps_vs_reference_golden(model, d, cfg, path, monkeypatch):
+    """4 train_steps with the run.py call sequence (incl. the Adam re-creation of run.py:315-322), through the kernel
+    variant the launcher would pick for this shape and through the single-read (split + entity-major) path."""
+    if path == "single_read":
+        monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
     g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
     m = make_model(model, int(g["nentity"]), int(g["nrelation"]), d, float(g["gamma"]), golden_state(g))
     lr = 1e-3
@@ -155,7 +159,14 @@ def test_train_steps_vs_reference_golden(model, d, cfg):
     torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr).load_state_dict(sd)
 
 
-def test_train_step_matches_autograd_path_full_width():
+@pytest.mark.parametrize("path", ["default", "single_read"])
+def test_train_step_matches_autograd_path_full_width(path, monkeypatch):
+    if path == "single_read":
+        monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
+    _full_width_case()
+
+
+def _full_width_case():
     """cfg-3 row shape (RotatE, d=1000, N=256, 14,951 entities): fused train grads vs (a) the numpy oracle,
     (b) forward() + torch loss + the autograd backward kernel."""
     import torch.nn.functional as F
@@ -435,14 +446,17 @@ def test_single_read_path_matches_two_sweep_kernel(model, mode, monkeypatch):
         for tag in ("split", "two_sweep"):
             if tag == "two_sweep":
                 monkeypatch.setenv("KGE_NO_SPLIT", "1")
+                monkeypatch.delenv("KGE_FORCE_SPLIT", raising=False)
             else:
                 monkeypatch.delenv("KGE_NO_SPLIT", raising=False)
+                monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
             m = make_model(model, nentity, nrel, d, gamma, st)
             opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-4)
             log = KGE().train_step(m, opt, iter([(torch.from_numpy(pos), torch.from_numpy(neg), torch.from_numpy(w), mode)]), args)
             out[tag] = (log, m.entity_embedding.grad.cpu().numpy().copy(), m.relation_embedding.grad.cpu().numpy().copy(),
                         m.modulus.grad.cpu().numpy().copy() if model == "pRotatE" else None)
         monkeypatch.delenv("KGE_NO_SPLIT", raising=False)
+        monkeypatch.delenv("KGE_FORCE_SPLIT", raising=False)
         ts = O.TrainState(model, st, gamma, d)
         olog, og = O.train_step(ts, (pos, neg, w, mode), lr=1e-4, adversarial=adv, alpha=0.5, return_grads=True)
         for tag in out:
@@ -483,7 +497,12 @@ def test_tcgen05_eval_ranks_identical_to_exact_kernel(model, nentity, nrel, d, g
         assert m._ws['gemm_last_ambiguous'] < 0.05 * nq * nentity + 64
 
 
-def test_batch_sharded_rows_sum_to_full_batch():
+def test_batch_sharded_rows_sum_to_full_batch(monkeypatch):
+    monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
+    _sharded_rows_case()
+
+
+def _sharded_rows_case():
     """The multi-GPU train path: every rank runs kge_train_rows on its row slice with the global weight sum; the
     gradient buffers and per-row losses add up to the single-GPU result (what the NCCL all-reduce then delivers)."""
     import ctypes
