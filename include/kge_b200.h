@@ -98,6 +98,19 @@ int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversar
  * two-sweep atomic kernel is used instead; results agree to rounding.                                        */
 int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N);
 
+/* Multi-GPU variant of kge_train_rows (negative loss kinds): identical work, but when the single-read path is taken
+ * the entity-major pass is left to the caller (*host_entity_pass_pending = 1), who launches it per entity range with
+ * kge_train_entity_pass and all-reduces each finished slice of grad_entity while the next range is computed.         */
+int kge_train_rows_begin(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                         const int64_t *positive, const int64_t *negative, const float *weight,
+                         const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count, int64_t N,
+                         float *row_loss, float *pos_row_loss, float *grad_entity, float *grad_relation,
+                         float *grad_modulus, void *workspace, int64_t workspace_bytes, int32_t *err_flag,
+                         int32_t *host_entity_pass_pending, void *stream);
+int kge_train_entity_pass(const kge_model_t *m, int mode, void *workspace, int64_t row_count, int64_t N,
+                          int64_t ent_begin, int64_t ent_end, int slice_index, float *grad_entity,
+                          float *grad_modulus, void *stream);
+
 /* cudaMemsetAsync(ptr, 0, bytes): clears the gradient workspace at the top of a train step (the
  * reference's optimizer.zero_grad() at model.py:259 drops the grads, autograd re-creates zero tables). */
 int kge_zero(void *ptr, int64_t bytes, void *stream);

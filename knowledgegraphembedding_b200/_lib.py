@@ -40,6 +40,11 @@ PROTOTYPES = {
                                c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p]),
     "kge_train_workspace_bytes": (c_int64, [_M, c_int64, c_int64]),
+    "kge_train_rows_begin": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                     c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_void_p, POINTER(c_int32), c_void_p]),
+    "kge_train_entity_pass": (c_int, [_M, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
     "kge_zero": (c_int, [c_void_p, c_int64, c_void_p]),
     "kge_weight_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "kge_loss_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int64,

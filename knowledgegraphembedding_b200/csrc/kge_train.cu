@@ -41,6 +41,8 @@ struct RowArgs {
   float *gE, *gR, *gM;
   int32_t *err;
   int *fused_positive;         // host-side out flag: the launched variant handled pos_row_loss itself
+  int defer_entity;            // host: do not launch the entity-major pass (caller slices it, kge_train_entity_pass)
+  int *entity_deferred;        // host out flag: the split path ran and its entity pass is still due
 };
 
 constexpr int kChunks = 8;     // units per lane per k-tile: 8 x float4 x (re,im) = 64 accumulator registers
@@ -552,8 +554,58 @@ namespace kge {
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
-  return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 4) +
+  return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 64) +
          2 * align256(rows * N * 4);
+}
+
+static SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity) {
+  char *wp = (char *)workspace;
+  SplitWs ws;
+  ws.G = (float *)wp;      wp += align256((size_t)rows * N * 4);
+  ws.Qtab = (float *)wp;   wp += align256((size_t)rows * De * 4);
+  ws.cnt = (int *)wp;
+  ws.cursor = ws.cnt + (nentity + 1);
+  ws.queue = ws.cursor + nentity;                          // 16 queue counters (one per entity slice)
+  wp += align256((size_t)(nentity + 1) * 4 + (size_t)nentity * 4 + 64);
+  ws.perm = (int *)wp;     wp += align256((size_t)rows * N * 4);
+  ws.gsorted = (float *)wp;
+  return ws;
+}
+
+template <int MODEL, bool HEAD>
+static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_begin, int64_t ent_end, int slot,
+                              cudaStream_t st, int reserve_sms = 0) {
+  constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
+  if (ent_end <= ent_begin) return KGE_OK;
+  const int nunits = a.d / 4;
+  EntArgs e{};
+  e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.gsorted = ws.gsorted; e.Qtab = ws.Qtab;
+  e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue + slot; e.nentity = a.nentity;
+  e.ent_begin = ent_begin; e.ent_count = ent_end - ent_begin;
+  e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
+  e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (reserve_sms > 0 && sms > 2 * reserve_sms) sms -= reserve_sms;   // leave SMs for the concurrent NCCL kernel
+  const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
+  e.upp = two ? (nunits + 1) / 2 : nunits;
+  const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * e.upp * 16;
+  int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
+  const int wmax = two ? 20 : 12;
+  if (We > wmax) We = wmax;
+  const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
+  if (two) {
+    auto k = entity_kernel<MODEL, HEAD, 2>;
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    k<<<sms, We * 32, esmem, st>>>(e);
+  } else {
+    auto k = entity_kernel<MODEL, HEAD, 1>;
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    k<<<sms, We * 32, esmem, st>>>(e);
+  }
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
 }
 
 template <int MODEL, bool HEAD>
@@ -587,17 +639,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         return KGE_OK;
       }
       // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
-      char *wp = (char *)workspace;
-      SplitWs ws;
-      ws.G = (float *)wp;      wp += align256((size_t)a.row_count * a.N * 4);
-      ws.Qtab = (float *)wp;   wp += align256((size_t)a.row_count * a.De * 4);
-      ws.cnt = (int *)wp;
-      ws.cursor = ws.cnt + (a.nentity + 1);
-      ws.queue = ws.cursor + a.nentity;
-      wp += align256((size_t)(a.nentity + 1) * 4 + (size_t)a.nentity * 4 + 4);
-      ws.perm = (int *)wp;     wp += align256((size_t)a.row_count * a.N * 4);
-      ws.gsorted = (float *)wp;
-      KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 1) * 4, st));
+      SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
+      KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
       {
         auto k = row_kernel_split<MODEL, HEAD>;
         KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
@@ -615,34 +658,11 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
                                                  ws.G, ws.cursor, ws.perm, ws.gsorted);
         KGE_CUDA_OK(cudaGetLastError());
       }
-      {
-        EntArgs e{};
-        e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.gsorted = ws.gsorted; e.Qtab = ws.Qtab;
-        e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue; e.nentity = a.nentity;
-        e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
-        e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
-        e.upp = two ? (nunits + 1) / 2 : nunits;
-        const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * e.upp * 16;
-        int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
-        const int wmax = two ? 20 : 12;
-        if (We > wmax) We = wmax;
-        const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
-        if (two) {
-          auto k = entity_kernel<MODEL, HEAD, 2>;
-          KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-          k<<<sms, We * 32, esmem, st>>>(e);
-        } else {
-          auto k = entity_kernel<MODEL, HEAD, 1>;
-          KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-          k<<<sms, We * 32, esmem, st>>>(e);
-        }
-        KGE_CUDA_OK(cudaGetLastError());
+      if (a.defer_entity) {
+        if (a.entity_deferred) *a.entity_deferred = 1;
+        return KGE_OK;
       }
-      return KGE_OK;
+      return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
     }
   }
   if (vec4) {
@@ -780,4 +800,79 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
 extern "C" int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N) {
   if (!m || rows <= 0 || N <= 0) return 0;
   return (int64_t)split_workspace_bytes(rows, N, m->entity_dim, m->nentity);
+}
+
+// ---- sliced variant for multi-GPU runs: the entity-major pass is launched per entity range so that the all-reduce of
+// a finished slice of the gradient table overlaps the computation of the next one --------------------------------------
+extern "C" int kge_train_rows_begin(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                                    const int64_t *positive, const int64_t *negative, const float *weight,
+                                    const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
+                                    int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity,
+                                    float *grad_relation, float *grad_modulus, void *workspace, int64_t workspace_bytes,
+                                    int32_t *err_flag, int32_t *host_entity_pass_pending, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(positive && negative && row_loss && pos_row_loss && grad_entity && grad_relation && host_entity_pass_pending,
+              "null pointer");
+  KGE_REQUIRE(m->model != KGE_PROTATE || grad_modulus, "pRotatE needs grad_modulus");
+  KGE_REQUIRE(loss_kind == KGE_LOSS_NEG_ADVERSARIAL || loss_kind == KGE_LOSS_NEG_UNIFORM, "bad loss_kind %d", loss_kind);
+  KGE_REQUIRE(!weight || weight_sum, "subsampling weights need their sum (kge_weight_sum)");
+  KGE_REQUIRE(row_begin >= 0 && row_begin + row_count <= B_total, "row slice outside the batch");
+  RowArgs a{};
+  bool head;
+  if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
+  if ((rc = set_device(m))) return rc;
+  a.positive = positive; a.row_begin = row_begin; a.row_count = (int)row_count; a.N = (int)N;
+  a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
+  a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
+  a.row_loss = row_loss; a.pos_row_loss = pos_row_loss;
+  a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
+  int fused_positive = 0, deferred = 0;
+  a.fused_positive = &fused_positive;
+  a.defer_entity = 1;
+  a.entity_deferred = &deferred;
+  rc = launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
+  *host_entity_pass_pending = deferred;
+  if (rc || fused_positive) return rc;
+  return kge_train_rows(m, KGE_SINGLE, KGE_LOSS_POSITIVE, 1.0f, positive, negative, weight, weight_sum, B_total, row_begin,
+                        row_count, 1, pos_row_loss, nullptr, grad_entity, grad_relation, grad_modulus, nullptr, nullptr, 0,
+                        err_flag, stream);
+}
+
+extern "C" int kge_train_entity_pass(const kge_model_t *m, int mode, void *workspace, int64_t row_count, int64_t N,
+                                     int64_t ent_begin, int64_t ent_end, int slice_index, float *grad_entity,
+                                     float *grad_modulus, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(workspace && grad_entity, "null pointer");
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "mode %d not supported", mode);
+  KGE_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= m->nentity && slice_index >= 0 && slice_index < 16,
+              "bad entity slice");
+  if ((rc = set_device(m))) return rc;
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  RowArgs a{};
+  a.E = m->entity; a.modulus = m->modulus; a.nentity = m->nentity;
+  a.De = (int)m->entity_dim; a.d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
+  a.scale = phase_scale(m); a.N = (int)N; a.row_count = (int)row_count;
+  a.gE = grad_entity; a.gM = grad_modulus; a.do_loss = 1;
+  const SplitWs ws = carve_split_ws(workspace, row_count, N, m->entity_dim, m->nentity);
+  const bool head = mode == KGE_HEAD_BATCH;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the persistent entity kernel would otherwise hold every SM and the all-reduce of the previous slice could not start
+  const char *rs = getenv("KGE_ENTITY_SMS_RESERVE");
+  const int reserve = rs ? atoi(rs) : 0;       // measured at 2 GPUs: 0, 8, 24 equal, 48 slower
+#define KGE_ENT(MODEL)                                                                            \
+  case MODEL:                                                                                     \
+    return head ? launch_entity_pass<MODEL, true>(a, ws, ent_begin, ent_end, slice_index, st, reserve)     \
+                : launch_entity_pass<MODEL, false>(a, ws, ent_begin, ent_end, slice_index, st, reserve);
+  switch (m->model) {
+    KGE_ENT(KGE_TRANSE)
+    KGE_ENT(KGE_DISTMULT)
+    KGE_ENT(KGE_COMPLEX)
+    KGE_ENT(KGE_ROTATE)
+    KGE_ENT(KGE_PROTATE)
+  }
+#undef KGE_ENT
+  set_error("model %d not supported", m->model);
+  return KGE_ERR_INVALID;
 }

@@ -368,6 +368,7 @@ struct EntArgs {
   const int *off, *perm;
   int *queue;
   int64_t nentity;
+  int64_t ent_begin, ent_count;   // entity range of this launch (slices overlap the NCCL all-reduce in multi-GPU runs)
   int N, d, De;
   int upp;                   // units (float4) per part: ceil(nunits / S)
   float scale;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
   float g0 = 0.f, g1 = 0.f;
   const int nunits = a.d / V;
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
-  const int64_t ntasks = a.nentity * S;
+  const int64_t ntasks = a.ent_count * S;
 
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
     if (lane == 0) t = atomicAdd(a.queue, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= ntasks) break;
-    const int e = t / S, part = t % S;
+    const int e = (int)a.ent_begin + t / S, part = t % S;
     const int beg = a.off[e], end = a.off[e + 1];
     const int ubeg = part * a.upp;                          // first unit of this part
     const int ucnt = min(a.upp, nunits - ubeg);             // units in this part

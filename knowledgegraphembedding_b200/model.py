@@ -401,22 +401,51 @@ class KGEModel(nn.Module):
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode],
-                  _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM, alpha, *common,
-                  _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
-                  wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
+        import os
+        params = model._trainable()
+        grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
+        fused_adam = KGEModel._fusable_adam(model, optimizer)
+        loss_kind = _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM
+        # multi-GPU: slice the entity-major pass so that the all-reduce of finished gradient slices (NCCL, its own
+        # stream) overlaps the computation of the next slice, and Adam runs slice by slice behind the all-reduces
+        sliced = (world > 1 or bool(os.environ.get('KGE_SLICED_TRAIN'))) and fused_adam and reg == 0.0
+        reductions = []                                      # (async work or None, first element, numel) of dE slices
+        tail_work = None
+        if sliced:
+            pending = ctypes.c_int32(0)
+            _lib.call("kge_train_rows_begin", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
+                      _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
+                      wbytes, _ptr(err), ctypes.byref(pending), st)
+            nE = model.entity_embedding.numel()
+            nE4 = (nE + 3) // 4 * 4
+            if world > 1:                                    # dR | dM | row losses are final already
+                tail_work = torch.distributed.all_reduce(ws['flat'][nE4:], async_op=True)
+            nslices = 4 if pending.value else 1
+            for k in range(nslices):
+                eb, ee = shard_bounds(model.nentity if pending.value else 1, k, nslices)
+                if pending.value:
+                    _lib.call("kge_train_entity_pass", ctypes.byref(desc), _lib.MODE_IDS[mode], _ptr(wsp),
+                              row_end - row_begin, N, eb, ee, k, _ptr(ws['gE']), _ptr(gM), st)
+                    lo, hi = eb * model.entity_dim, ee * model.entity_dim
+                else:
+                    lo, hi = 0, nE
+                work = torch.distributed.all_reduce(ws['flat'][lo:hi], async_op=True) if world > 1 else None
+                reductions.append((work, lo, hi - lo))
+        else:
+            _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
+                      _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
+                      wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
+            if world > 1:
+                # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
+                torch.distributed.all_reduce(ws['flat'])
         if events is not None:
             ev1.record()
             events.append((ev0, ev1))
-        if world > 1:
-            # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
-            torch.distributed.all_reduce(ws['flat'])
 
-        params = model._trainable()
-        grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
-        if KGEModel._fusable_adam(model, optimizer):
+        if fused_adam:
             group = optimizer.param_groups[0]
-            tensors = (_lib.KgeAdamTensor * len(params))()
+            hyper = (float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']))
+            entries = []
             for i, (p, g) in enumerate(zip(params, grads)):
                 state = optimizer.state[p]
                 if len(state) == 0:             # same lazy state as torch/optim/adam.py _init_group
@@ -424,12 +453,25 @@ class KGEModel(nn.Module):
                     state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state['step'] += 1
-                tensors[i] = _lib.KgeAdamTensor(p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(),
-                                                state['exp_avg_sq'].data_ptr(), p.numel(), int(state['step'].item()),
-                                                1 if (reg != 0.0 and i < 2) else 0)
-            _lib.call("kge_adam_step", tensors, len(params), float(group['lr']), float(group['betas'][0]),
-                      float(group['betas'][1]), float(group['eps']), reg,
-                      _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
+                entries.append((p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
+                                p.numel(), int(state['step'].item()), 1 if (reg != 0.0 and i < 2) else 0))
+
+            def adam(chunks):
+                tensors = (_lib.KgeAdamTensor * len(chunks))(*[_lib.KgeAdamTensor(*c) for c in chunks])
+                _lib.call("kge_adam_step", tensors, len(chunks), *hyper, reg,
+                          _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
+
+            if sliced:
+                pE, gE_, mE, vE, _, stepE, _ = entries[0]
+                for work, lo, n in reductions:              # Adam on a slice as soon as its all-reduce has landed
+                    if work is not None:
+                        work.wait()
+                    adam([(pE + 4 * lo, gE_ + 4 * lo, mE + 4 * lo, vE + 4 * lo, n, stepE, 0)])
+                if tail_work is not None:
+                    tail_work.wait()
+                adam(entries[1:])
+            else:
+                adam(entries)
             reg_partials = ws['reg'] if reg != 0.0 else None
             for p, g in zip(params, grads):
                 p.grad = g

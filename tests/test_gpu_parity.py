@@ -595,3 +595,33 @@ def test_train_step_input_prefetch_semantics():
     for a, b in zip(results["prefetch"][0], results["strict"][0]):
         assert a.keys() == b.keys() and all(abs(a[k] - b[k]) <= 1e-6 * abs(b[k]) for k in a)
     assert relinf(results["prefetch"][1], results["strict"][1]) < 1e-6
+
+
+def test_sliced_entity_pass_matches_single_launch(monkeypatch):
+    """The multi-GPU flow (kge_train_rows_begin + kge_train_entity_pass per entity slice + Adam per slice) gives the
+    same losses, gradients and updated tables as the single-call flow."""
+    nentity, nrel, d, gamma, B, N = 3001, 7, 64, 6.0, 64, 300
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=5)
+    rng = np.random.RandomState(6)
+    batches = []
+    for i in range(3):
+        pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
+        batches.append((torch.from_numpy(pos), torch.from_numpy(rng.randint(nentity, size=(B, N))),
+                        torch.from_numpy(np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)),
+                        "tail-batch" if i % 2 == 0 else "head-batch"))
+    args = ns(negative_adversarial_sampling=True)
+    out = {}
+    for tag in ("single", "sliced"):
+        if tag == "sliced":
+            monkeypatch.setenv("KGE_SLICED_TRAIN", "1")
+        m = make_model("RotatE", nentity, nrel, d, gamma, st)
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+        it = iter(batches)
+        logs = [KGE().train_step(m, opt, it, args) for _ in range(3)]
+        out[tag] = (logs, m.entity_embedding.detach().cpu().numpy().copy(), m.relation_embedding.detach().cpu().numpy().copy(),
+                    m.entity_embedding.grad.cpu().numpy().copy())
+    monkeypatch.delenv("KGE_SLICED_TRAIN")
+    for a, b in zip(out["single"][0], out["sliced"][0]):
+        assert all(abs(a[k] - b[k]) <= 1e-6 * abs(a[k]) for k in a)
+    assert relinf(out["sliced"][3], out["single"][3]) < 1e-6
+    assert outlier_fraction(out["sliced"][1], out["single"][1]) < 1e-4 and relinf(out["sliced"][2], out["single"][2]) < 1e-5
