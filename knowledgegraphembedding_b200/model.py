@@ -505,7 +505,7 @@ class KGEModel(nn.Module):
             self._filter_cache = (key, FilterIndex(all_true_triples, nentity, nrelation))
         return self._filter_cache[1]
 
-    def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False):
+    def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False, exact=False):
         """Filtered rank of every test triple in `mode` (model.py:382-418 without the sort): int64 [len].
         Entities are sharded across the ranks of an initialised process group; the integer counts are
         all-reduced (bit-exact)."""
@@ -513,7 +513,12 @@ class KGEModel(nn.Module):
         st = _stream(dev)
         nentity, nrelation = self.entity_embedding.shape[0], self.relation_embedding.shape[0]
         index = self._filter_index(all_true_triples, nentity, nrelation)
-        queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
+        cached = self._ws.get('queries_np')                  # test_step ranks the same list in both modes
+        if cached is not None and cached[0] is test_triples and cached[1] == len(test_triples):
+            queries_all = cached[2]
+        else:
+            queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
+            self._ws['queries_np'] = (test_triples, len(test_triples), queries_all)
         rank, world = _dist()
         ent_begin, ent_end = shard_bounds(nentity, rank, world, align=128)
         desc = self._descriptor()
@@ -526,10 +531,11 @@ class KGEModel(nn.Module):
         # DistMult / ComplEx: the all-entity scores are a dense contraction -> tcgen05 path (exact SIMT re-score of
         # the ambiguous band keeps the counts identical); KGE_EVAL_SIMT=1 forces the exact tile kernel
         import os
-        gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not return_scores \
-            and not os.environ.get("KGE_EVAL_SIMT")
-        two_stage = self.model_name == 'RotatE' and not return_scores and not os.environ.get("KGE_EVAL_SIMT") \
-            and self.entity_dim % 8 == 0
+        exact = exact or return_scores or bool(os.environ.get("KGE_EVAL_SIMT"))
+        gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not exact
+        two_stage = self.model_name == 'RotatE' and not exact and self.entity_dim % 8 == 0
+        nchunks = (queries_all.shape[0] + query_chunk - 1) // query_chunk
+        amb_counts = torch.zeros((max(nchunks, 1), 2), dtype=torch.int32, device=dev) if (gemm or two_stage) else None
         if gemm:
             nE = self.entity_embedding.numel()
             ehi = self._buffer('gemm_ehi', nE, torch.float32, dev)
@@ -540,7 +546,7 @@ class KGEModel(nn.Module):
         counts_all = torch.zeros(queries_all.shape[0], dtype=torch.int32, device=dev)
         scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
         m = _lib.MODE_IDS[mode]
-        for lo in range(0, queries_all.shape[0], query_chunk):
+        for ci, lo in enumerate(range(0, queries_all.shape[0], query_chunk)):
             q_np = queries_all[lo:lo + query_chunk]
             Q = q_np.shape[0]
             offsets, ents = index.csr(q_np, mode)
@@ -564,45 +570,37 @@ class KGEModel(nn.Module):
                 qhi = self._buffer('gemm_qhi', Q * self.entity_dim, torch.float32, dev)
                 qlo = self._buffer('gemm_qlo', Q * self.entity_dim, torch.float32, dev)
                 qnorm = self._buffer('gemm_qnorm', Q, torch.float32, dev)
-                cap = Q * 1024
+                cap = int(os.environ.get('KGE_EVAL_AMB_CAP', Q * 1024))
                 amb = self._buffer('gemm_amb', cap * 2, torch.int32, dev)
-                amb_count = self._buffer('gemm_amb_count', 2, torch.int32, dev)
                 _lib.call("kge_eval_gemm_split", _ptr(qvec), Q, self.entity_dim, _ptr(qhi), _ptr(qlo), _ptr(qnorm), st)
                 _lib.call("kge_eval_gemm_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(qhi), _ptr(qlo),
                           _ptr(qnorm), _ptr(queries), Q, _ptr(pos), _ptr(bits), _ptr(ehi), _ptr(elo), _ptr(enorm),
-                          ent_begin, ent_end, _ptr(counts), _ptr(amb), cap, _ptr(amb_count), st)
-                stats = amb_count[:2].tolist()
-                self._ws['gemm_last_ambiguous'] = stats[0]
-                if stats[1] == 0:
-                    if events is not None:
-                        ev1.record()
-                        events.append((ev0, ev1))
-                    continue
-                counts.zero_()                               # ambiguous list overflowed: exact kernel for this chunk
+                          ent_begin, ent_end, _ptr(counts), _ptr(amb), cap, _ptr(amb_counts[ci]), st)
             elif two_stage:
-                cap = Q * 256
+                cap = int(os.environ.get('KGE_EVAL_AMB_CAP', Q * 256))
                 amb = self._buffer('gemm_amb', cap * 2, torch.int32, dev)
-                amb_count = self._buffer('gemm_amb_count', 2, torch.int32, dev)
                 _lib.call("kge_eval_count_ranks_two_stage", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q,
                           _ptr(phase), _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts), _ptr(amb), cap,
-                          _ptr(amb_count), st)
-                stats = amb_count[:2].tolist()
-                self._ws['two_stage_last_ambiguous'] = stats[0]
-                if stats[1] == 0:
-                    if events is not None:
-                        ev1.record()
-                        events.append((ev0, ev1))
-                    continue
-                counts.zero_()
-            _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
-                      _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
-                      _ptr(scores[lo:lo + Q]) if scores is not None else None, st)
+                          _ptr(amb_counts[ci]), st)
+            else:
+                _lib.call("kge_eval_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
+                          _ptr(pos), _ptr(bits), ent_begin, ent_end, _ptr(counts),
+                          _ptr(scores[lo:lo + Q]) if scores is not None else None, st)
             if events is not None:
                 ev1.record()
                 events.append((ev0, ev1))
         if world > 1:
             torch.distributed.all_reduce(counts_all)
-        ranks = (counts_all.to(torch.int64) + 1).cpu().numpy()
+            if amb_counts is not None:                       # an overflow on any rank re-runs the chunk everywhere
+                torch.distributed.all_reduce(amb_counts, op=torch.distributed.ReduceOp.MAX)
+        ranks = (counts_all.to(torch.int64) + 1).cpu().numpy()           # the call's one host sync
+        if amb_counts is not None:
+            stats = amb_counts.cpu().numpy()
+            self._ws['gemm_last_ambiguous' if gemm else 'two_stage_last_ambiguous'] = int(stats[:, 0].sum())
+            for ci in np.nonzero(stats[:, 1])[0]:            # ambiguous list overflowed: exact kernel for that chunk
+                lo = int(ci) * query_chunk
+                chunk = [tuple(int(v) for v in row) for row in queries_all[lo:lo + query_chunk]]
+                ranks[lo:lo + query_chunk] = self.filtered_ranks(chunk, all_true_triples, mode, query_chunk, exact=True)
         self._raise_if_bad_index()
         return (ranks, scores) if return_scores else ranks
 

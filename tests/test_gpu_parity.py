@@ -625,3 +625,23 @@ def test_sliced_entity_pass_matches_single_launch(monkeypatch):
         assert all(abs(a[k] - b[k]) <= 1e-6 * abs(a[k]) for k in a)
     assert relinf(out["sliced"][3], out["single"][3]) < 1e-6
     assert outlier_fraction(out["sliced"][1], out["single"][1]) < 1e-4 and relinf(out["sliced"][2], out["single"][2]) < 1e-5
+
+
+@pytest.mark.parametrize("model", ["RotatE", "ComplEx"])
+def test_two_stage_overflow_falls_back_to_exact(model, monkeypatch):
+    """A full ambiguous-pair list (capacity forced to 2) is detected at the call's single sync and the chunk is
+    re-ranked by the exact kernel: same ranks."""
+    de, dr = FLAGS[model]
+    nentity, nrel, d, gamma = 2500, 5, 32, 6.0
+    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=21)
+    rng = np.random.RandomState(22)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(200))) for _ in range(5000)})
+    test = all_true[:150]
+    m = make_model(model, nentity, nrel, d, gamma, st)
+    monkeypatch.setenv("KGE_EVAL_SIMT", "1")
+    exact = m.filtered_ranks(test, all_true, "tail-batch", query_chunk=64)
+    monkeypatch.delenv("KGE_EVAL_SIMT")
+    monkeypatch.setenv("KGE_EVAL_AMB_CAP", "2")
+    np.testing.assert_array_equal(m.filtered_ranks(test, all_true, "tail-batch", query_chunk=64), exact)
+    monkeypatch.delenv("KGE_EVAL_AMB_CAP")
+    np.testing.assert_array_equal(m.filtered_ranks(test, all_true, "tail-batch", query_chunk=64), exact)
