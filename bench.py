@@ -148,7 +148,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scores/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "model": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
+        "config": {"workload": wl, "score_function": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
                    "negative_sample_size": N, "batch_size": B, "gamma": gamma, "adversarial": True,
                    "sample_rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "scores/s", "cores": cores, "kind": "port",
@@ -295,9 +295,10 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "model": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
-                   "negative_sample_size": N, "batch_size_per_gpu": B, "global_batch": Bg, "gamma": gamma,
-                   "adversarial": True, "double_entity_embedding": de, "parallelism": f"dp{world}",
+        "config": {"workload": wl, "score_function": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
+                   "negative_sample_size": N, "batch_size_per_gpu": B, "positives_per_step": Bg, "gamma": gamma,
+                   "adversarial": True, "double_entity_embedding": de,
+                   "sharding": f"positive rows over {world} rank(s), tables replicated; eval: entity slices",
                    "l2_policy": "no flush: each step streams 0.6 GB of tables+moments+grads (> 126 MB L2)"},
         "clocks": clocks, "gpu_launches": 7 * args.steps,
         "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,

@@ -108,3 +108,45 @@ def test_bidirectional_iterator_contract_and_training():
                                  uni_weight=False, regularization=0.0)
     losses = [KGEModel.train_step(m, opt, it, args)["loss"] for _ in range(30)]
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+
+
+@pytest.mark.gpu
+def test_forty_steps_track_the_cpu_oracle_on_countries():
+    """40 consecutive train_steps on countries_S1 (device-sampled batches, alternating modes, one LR decay with the
+    Adam re-creation of run.py:315-322): every step's losses stay within 1e-4 of the C oracle fed the same batches,
+    and the final tables agree except for a vanishing fraction of sign-ambiguous Adam elements."""
+    import types
+
+    import torch
+    from conftest import outlier_fraction, relinf
+    from knowledgegraphembedding_b200 import KGEModel
+    from knowledgegraphembedding_b200.sampler import BidirectionalGpuIterator
+    from oracle import c_oracle as C
+    g, tri, nentity, nrel = countries()
+    d, gamma = 64, 2.0
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=4)
+    m = KGEModel("RotatE", nentity, nrel, d, gamma, double_entity_embedding=True)
+    with torch.no_grad():
+        m.entity_embedding.copy_(torch.from_numpy(st["entity_embedding"]))
+        m.relation_embedding.copy_(torch.from_numpy(st["relation_embedding"]))
+    m = m.cuda()
+    ts = C.TrainState("RotatE", st, gamma, d)
+    it = BidirectionalGpuIterator(tri, nentity, nrel, 32, 256, "cuda", seed=8)
+    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
+                                 uni_weight=False, regularization=0.0)
+    lr = 5e-4
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+    for step in range(40):
+        if step == 25:
+            lr /= 10
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+            ts.reset_optimizer()
+        batch = next(it)
+        log = KGEModel.train_step(m, opt, iter([batch]), args)
+        ref = C.train_step(ts, tuple(b.cpu().numpy() if hasattr(b, "cpu") else b for b in batch), lr=lr,
+                           adversarial=True, alpha=1.0)
+        for k in ref:
+            assert abs(log[k] - ref[k]) <= 1e-4 * abs(ref[k]), (step, k, log[k], ref[k])
+    E = m.entity_embedding.detach().cpu().numpy()
+    assert outlier_fraction(E, ts.state["entity_embedding"], 1e-4) < 2e-3
+    assert relinf(m.relation_embedding.detach().cpu().numpy(), ts.state["relation_embedding"]) < 1e-3
