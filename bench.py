@@ -248,7 +248,7 @@ def run_gpu(args):
 
     ms_e2e = timed(step_host, args.steps, args.warmup) / args.steps
     e2e_value = Bg * N / (ms_e2e * 1e-3)
-    h2d = Bg * 3 * 8 + Bg * N * 8 + Bg * 4
+    h2d = world * (B * 3 * 8 + B * N * 8 + Bg * 4)      # every rank copies its own rows (+ the whole weight vector)
     d2h = 8 * 4
 
     # ---- filtered evaluation throughput (entity-sharded over the ranks) ------------------------------------------

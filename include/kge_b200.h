@@ -193,6 +193,15 @@ int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const float *qvec,
 int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q,
                          int64_t nentity, uint32_t *filter_bits, void *stream);
 
+/* Same bitmap without a host round trip per query chunk: the index of all true triples lives on the device as a
+ * sorted-key CSR (built once per all_true_triples list: keys = r*nentity+t -> true heads for HEAD_BATCH,
+ * h*nrelation+r -> true tails for TAIL_BATCH; run i is index_entities[index_offsets[i] .. index_offsets[i+1])),
+ * and each query's key is looked up on the device.  Replaces TestDataset.__getitem__'s per-entity set probes
+ * (dataloader.py:134-154) for a whole chunk of queries in one launch.                                          */
+int kge_eval_filter_bits_lookup(const int64_t *index_keys, const int64_t *index_offsets, const int32_t *index_entities,
+                                int64_t nkeys, const int64_t *queries, int64_t Q, int mode, int64_t nentity,
+                                int64_t nrelation, uint32_t *filter_bits, void *stream);
+
 /* ---- negative sampling: TrainDataset.__getitem__ (dataloader.py:28-67) on the device ----
  * For row b (train triple triple_index[b]) draw N entity ids uniformly from the entities that are NOT in the
  * row's sorted true list true_entities[key_start[t] .. +key_len[t])  (the true heads of (r,t) for head-batch, the

@@ -343,6 +343,36 @@ __global__ void filter_bits_kernel(const int64_t *__restrict__ offsets, const in
   }
 }
 
+// Filter bitmap straight from the device-resident index of all true triples: one CTA per query looks its key
+// ((r, t) for head-batch, (h, r) for tail-batch) up in the sorted key table and sets the bits of that key's run.
+__global__ void filter_lookup_kernel(const int64_t *__restrict__ keys, const int64_t *__restrict__ key_offsets,
+                                     const int32_t *__restrict__ values, int64_t nkeys,
+                                     const int64_t *__restrict__ queries, int64_t Q, int head_batch, int64_t nentity,
+                                     int64_t nrelation, int words, uint32_t *__restrict__ bits) {
+  __shared__ int64_t run[2];
+  for (int64_t qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    if (threadIdx.x == 0) {
+      const int64_t h = queries[qi * 3], r = queries[qi * 3 + 1], t = queries[qi * 3 + 2];
+      const int64_t key = head_batch ? r * nentity + t : h * nrelation + r;
+      int64_t lo = 0, hi = nkeys;                                      // lower bound
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      const bool found = lo < nkeys && keys[lo] == key;
+      run[0] = found ? key_offsets[lo] : 0;
+      run[1] = found ? key_offsets[lo + 1] : 0;
+    }
+    __syncthreads();
+    const int64_t b = run[0], e = run[1];
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int32_t j = values[i];
+      if (j >= 0 && j < nentity) atomicOr(&bits[qi * words + (j >> 5)], 1u << (j & 31));
+    }
+    __syncthreads();
+  }
+}
+
 template <int OP>
 static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
   constexpr int H = op_is_complex(OP) ? 2 : 1;
@@ -546,6 +576,25 @@ extern "C" int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *c
   KGE_CUDA_OK(cudaMemsetAsync(filter_bits, 0, sizeof(uint32_t) * (size_t)Q * words, st));
   const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
   filter_bits_kernel<<<grid, 128, 0, st>>>(csr_offsets, csr_entities, Q, nentity, words, filter_bits);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_filter_bits_lookup(const int64_t *index_keys, const int64_t *index_offsets,
+                                           const int32_t *index_entities, int64_t nkeys, const int64_t *queries,
+                                           int64_t Q, int mode, int64_t nentity, int64_t nrelation,
+                                           uint32_t *filter_bits, void *stream) {
+  KGE_REQUIRE(filter_bits && queries && Q >= 0 && nentity > 0 && nrelation > 0 && nkeys >= 0, "bad arguments");
+  KGE_REQUIRE(nkeys == 0 || (index_keys && index_offsets && index_entities), "null filter index");
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "negative batch mode %d not supported", mode);
+  if (Q == 0) return KGE_OK;
+  const int words = (int)((nentity + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(filter_bits, 0, sizeof(uint32_t) * (size_t)Q * words, st));
+  if (nkeys == 0) return KGE_OK;
+  const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
+  filter_lookup_kernel<<<grid, 128, 0, st>>>(index_keys, index_offsets, index_entities, nkeys, queries, Q,
+                                             mode == KGE_HEAD_BATCH, nentity, nrelation, words, filter_bits);
   KGE_CUDA_OK(cudaGetLastError());
   return KGE_OK;
 }

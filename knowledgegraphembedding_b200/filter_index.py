@@ -38,6 +38,13 @@ class FilterIndex:
             return q[:, 0] * self.nrelation + q[:, 1]
         raise ValueError('negative batch mode %s not supported' % mode)       # dataloader.py:147
 
+    def table(self, mode):
+        """(sorted unique keys int64 [K], run offsets int64 [K+1], entities int32 [nnz]) of one mode: what the device
+        keeps resident for kge_eval_filter_bits_lookup."""
+        if mode not in self._tables:
+            raise ValueError('negative batch mode %s not supported' % mode)    # dataloader.py:147
+        return self._tables[mode]
+
     def csr(self, queries, mode):
         """(offsets int64 [Q+1], entities int32 [nnz]) : the true entities of every query's open slot."""
         ukeys, offsets, values = self._tables[mode] if mode in self._tables else (None, None, None)

@@ -6,8 +6,10 @@ arithmetic step runs in the hand-written sm_100a kernels of libkge_b200.so (incl
 used for device memory, streams, `nn.Module` bookkeeping and NCCL only.  There is no CPU / eager fallback:
 calling the scoring paths with parameters that are not on a B200 raises.
 """
+import collections
 import ctypes
 import logging
+import os
 
 import numpy as np
 import torch
@@ -44,6 +46,23 @@ def shard_bounds(total, rank, world, align=1):
     begin = rank * base + min(rank, rem)
     end = begin + base + (1 if rank < rem else 0)
     return min(begin * align, total), min(end * align, total)
+
+
+# A train batch cut down to this rank's positive rows (multi-GPU): only the shard crosses PCIe.  `weight` stays whole
+# (B floats) because the loss is normalised by the global sum of weights (model.py:285-286).
+_RowShard = collections.namedtuple('_RowShard', 'positive negative weight mode total row_begin')
+
+
+def _shard_rows(batch):
+    if isinstance(batch, _RowShard):
+        return batch
+    positive_sample, negative_sample, subsampling_weight, mode = batch
+    total = positive_sample.shape[0]
+    rank, world = _dist()
+    lo, hi = shard_bounds(total, rank, world)
+    if world > 1:
+        positive_sample, negative_sample = positive_sample[lo:hi], negative_sample[lo:hi]
+    return _RowShard(positive_sample, negative_sample, subsampling_weight, mode, total, lo)
 
 
 class _ScoreFunction(torch.autograd.Function):
@@ -320,14 +339,15 @@ class KGEModel(nn.Module):
     # so next() and the H2D copy run under step i's kernels.  One batch is held ahead per iterator; exhaustion is
     # re-raised at the call that would have hit it.  KGE_NO_PREFETCH=1 restores strict pull-at-call behaviour.
     def _stage_batch(self, batch, stream=None):
-        positive_sample, negative_sample, subsampling_weight, mode = batch
         dev = self.entity_embedding.device
         if stream is None:
             return batch
+        shard = _shard_rows(batch)
         with torch.cuda.stream(stream):
-            staged = (positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True),
-                      negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True),
-                      subsampling_weight.to(device=dev, dtype=torch.float32, non_blocking=True), mode)
+            staged = shard._replace(
+                positive=shard.positive.to(device=dev, dtype=torch.int64, non_blocking=True),
+                negative=shard.negative.to(device=dev, dtype=torch.int64, non_blocking=True),
+                weight=shard.weight.to(device=dev, dtype=torch.float32, non_blocking=True))
         return staged
 
     def _next_batch(self, iterator):
@@ -346,7 +366,6 @@ class KGEModel(nn.Module):
         return next(iterator)
 
     def _prefetch_batch(self, iterator):
-        import os
         if os.environ.get('KGE_NO_PREFETCH') or self.entity_embedding.device.type != 'cuda':
             return
         try:
@@ -369,12 +388,14 @@ class KGEModel(nn.Module):
         dev = model._device()
         st = _stream(dev)
 
-        positive_sample, negative_sample, subsampling_weight, mode = batch
-        if mode not in ('head-batch', 'tail-batch'):
-            raise ValueError('mode %s not supported' % mode)
+        if batch[3] not in ('head-batch', 'tail-batch'):
+            raise ValueError('mode %s not supported' % batch[3])
+        # multi-GPU: this rank's positive rows only (the H2D copy and the kernels see rows [row_begin, row_end) of B)
+        positive_sample, negative_sample, subsampling_weight, mode, B, row_begin = _shard_rows(batch)
         positive = positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         negative = negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-        B, N = negative.shape
+        rows, N = negative.shape
+        row_end = row_begin + rows
         uni = bool(getattr(args, 'uni_weight', False))
         weight = None if uni else subsampling_weight.to(device=dev, dtype=torch.float32,
                                                         non_blocking=True).contiguous()
@@ -388,20 +409,21 @@ class KGEModel(nn.Module):
         desc = model._descriptor()
         events = model._ws.get('kernel_events')       # bench.py: CUDA events around the dominant kernel
         rank, world = _dist()
-        row_begin, row_end = shard_bounds(B, rank, world)
 
         _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
         if weight is not None:
             _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
         gM = ws['gM'] if model.model_name == 'pRotatE' else None
-        common = (_ptr(positive), _ptr(negative), _ptr(weight), _ptr(ws['wsum']) if weight is not None else None,
-                  B, row_begin, row_end - row_begin, N)
+        # the row arrays passed down start at this rank's first row: [positive, negative] hold the shard only,
+        # weight / row losses are offset views of the whole-batch buffers
+        common = (_ptr(positive), _ptr(negative), _ptr(weight[row_begin:]) if weight is not None else None,
+                  _ptr(ws['wsum']) if weight is not None else None, B, 0, rows, N)
+        neg_row, pos_row = ws['neg_row'][row_begin:], ws['pos_row'][row_begin:]
         wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), row_end - row_begin, N)
         wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        import os
         params = model._trainable()
         grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
         fused_adam = KGEModel._fusable_adam(model, optimizer)
@@ -416,7 +438,7 @@ class KGEModel(nn.Module):
         if sliced:
             pending = ctypes.c_int32(0)
             _lib.call("kge_train_rows_begin", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
-                      _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
+                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
                       wbytes, _ptr(err), ctypes.byref(pending), st)
             nE = model.entity_embedding.numel()
             nE4 = (nE + 3) // 4 * 4
@@ -435,7 +457,7 @@ class KGEModel(nn.Module):
                 reductions.append((work, lo, hi - lo))
         else:
             _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
-                      _ptr(ws['neg_row']), _ptr(ws['pos_row']), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
+                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
                       wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
             if world > 1:
                 # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
@@ -502,8 +524,19 @@ class KGEModel(nn.Module):
     def _filter_index(self, all_true_triples, nentity, nrelation):
         key = (id(all_true_triples), len(all_true_triples), nentity, nrelation)
         if self._filter_cache is None or self._filter_cache[0] != key:
-            self._filter_cache = (key, FilterIndex(all_true_triples, nentity, nrelation))
+            self._filter_cache = (key, FilterIndex(all_true_triples, nentity, nrelation), {})
         return self._filter_cache[1]
+
+    def _filter_tables(self, index, mode, dev):
+        """The index of all true triples, resident on the device (uploaded once per list, mode and device)."""
+        held = self._filter_cache[2]
+        if (mode, dev) not in held:
+            keys, offsets, values = index.table(mode)
+            held[(mode, dev)] = (torch.from_numpy(np.ascontiguousarray(keys)).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(offsets)).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(values)).to(dev) if values.size else
+                                 torch.zeros(1, dtype=torch.int32, device=dev), int(keys.size))
+        return held[(mode, dev)]
 
     def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False, exact=False):
         """Filtered rank of every test triple in `mode` (model.py:382-418 without the sort): int64 [len].
@@ -514,11 +547,13 @@ class KGEModel(nn.Module):
         nentity, nrelation = self.entity_embedding.shape[0], self.relation_embedding.shape[0]
         index = self._filter_index(all_true_triples, nentity, nrelation)
         cached = self._ws.get('queries_np')                  # test_step ranks the same list in both modes
-        if cached is not None and cached[0] is test_triples and cached[1] == len(test_triples):
-            queries_all = cached[2]
+        if cached is not None and cached[0] is test_triples and cached[1] == len(test_triples) and cached[3].device == dev:
+            queries_all, queries_dev = cached[2], cached[3]
         else:
             queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
-            self._ws['queries_np'] = (test_triples, len(test_triples), queries_all)
+            queries_dev = torch.from_numpy(queries_all).to(dev, non_blocking=True)      # one H2D for the whole list
+            self._ws['queries_np'] = (test_triples, len(test_triples), queries_all, queries_dev)
+        f_keys, f_offsets, f_values, f_nkeys = self._filter_tables(index, mode, dev)
         rank, world = _dist()
         ent_begin, ent_end = shard_bounds(nentity, rank, world, align=128)
         desc = self._descriptor()
@@ -530,7 +565,6 @@ class KGEModel(nn.Module):
             _lib.call("kge_eval_phase_table", ctypes.byref(desc), _ptr(phase), st)
         # DistMult / ComplEx: the all-entity scores are a dense contraction -> tcgen05 path (exact SIMT re-score of
         # the ambiguous band keeps the counts identical); KGE_EVAL_SIMT=1 forces the exact tile kernel
-        import os
         exact = exact or return_scores or bool(os.environ.get("KGE_EVAL_SIMT"))
         gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not exact
         two_stage = self.model_name == 'RotatE' and not exact and self.entity_dim % 8 == 0
@@ -547,18 +581,15 @@ class KGEModel(nn.Module):
         scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
         m = _lib.MODE_IDS[mode]
         for ci, lo in enumerate(range(0, queries_all.shape[0], query_chunk)):
-            q_np = queries_all[lo:lo + query_chunk]
-            Q = q_np.shape[0]
-            offsets, ents = index.csr(q_np, mode)
-            queries = torch.from_numpy(q_np).to(dev, non_blocking=True)
-            d_off = torch.from_numpy(offsets).to(dev, non_blocking=True)
-            d_ent = torch.from_numpy(ents).to(dev, non_blocking=True) if ents.size else \
-                torch.zeros(1, dtype=torch.int32, device=dev)
+            queries = queries_dev[lo:lo + query_chunk]
+            Q = queries.shape[0]
             bits = self._buffer('filter_bits', Q * words, torch.int32, dev)
             qvec = self._buffer('qvec', Q * self.entity_dim, torch.float32, dev)
             pos = self._buffer('pos_score', Q, torch.float32, dev)
             counts = counts_all[lo:lo + Q]
-            _lib.call("kge_eval_filter_bits", _ptr(d_off), _ptr(d_ent), Q, nentity, _ptr(bits), st)
+            # filter bitmap of the chunk, looked up on the device in the resident index (dataloader.py:134-154)
+            _lib.call("kge_eval_filter_bits_lookup", _ptr(f_keys), _ptr(f_offsets), _ptr(f_values), f_nkeys,
+                      _ptr(queries), Q, m, nentity, nrelation, _ptr(bits), st)
             _lib.call("kge_eval_query_vectors", ctypes.byref(desc), m, _ptr(queries), Q, _ptr(qvec), _ptr(err), st)
             _lib.call("kge_eval_positive_scores", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), st)

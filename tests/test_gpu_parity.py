@@ -384,6 +384,40 @@ def test_entity_sharded_counts_sum_to_full():
         np.testing.assert_array_equal(total.cpu().numpy() + 1, full)
 
 
+def test_device_filter_lookup_equals_host_csr_bitmap():
+    """kge_eval_filter_bits_lookup (index resident on the device) sets exactly the bits of the host CSR path, which is
+    pinned to dataloader.py:134-154 by the CPU tests; includes queries whose key has no true triple and empty indexes."""
+    from knowledgegraphembedding_b200 import _lib, FilterIndex
+    from knowledgegraphembedding_b200.model import _ptr, _stream
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(5)
+    for nentity, nrel, ntrue, nq in ((5003, 17, 6000, 700), (33, 2, 40, 50), (100, 3, 0, 10)):
+        all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(min(nentity, 60))))
+                           for _ in range(ntrue)})
+        test = [(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(min(nentity, 70)))) for _ in range(nq)]
+        test += all_true[:nq]
+        index = FilterIndex(all_true, nentity, nrel)
+        q = torch.tensor(test, dtype=torch.int64, device=dev)
+        words = (nentity + 31) // 32
+        for mode in ("head-batch", "tail-batch"):
+            off, ent = index.csr(test, mode)
+            d_off = torch.from_numpy(off).to(dev)
+            d_ent = torch.from_numpy(ent).to(dev) if ent.size else torch.zeros(1, dtype=torch.int32, device=dev)
+            want = torch.full((len(test) * words,), -1, dtype=torch.int32, device=dev)
+            got = torch.full((len(test) * words,), -1, dtype=torch.int32, device=dev)
+            _lib.call("kge_eval_filter_bits", _ptr(d_off), _ptr(d_ent), len(test), nentity, _ptr(want), _stream(dev))
+            keys, offsets, values = index.table(mode)
+            d_keys = torch.from_numpy(np.ascontiguousarray(keys)).to(dev)
+            d_offsets = torch.from_numpy(np.ascontiguousarray(offsets)).to(dev)
+            d_values = torch.from_numpy(np.ascontiguousarray(values)).to(dev) if values.size else d_ent
+            _lib.call("kge_eval_filter_bits_lookup", _ptr(d_keys) if keys.size else None,
+                      _ptr(d_offsets) if keys.size else None, _ptr(d_values) if keys.size else None, int(keys.size),
+                      _ptr(q), len(test), _lib.MODE_IDS[mode], nentity, nrel, _ptr(got), _stream(dev))
+            assert torch.equal(got, want), (nentity, mode)
+            if ntrue:
+                assert int((want != 0).sum()) > 0
+
+
 # ------------------------------------------------------------------------------------------------ API behaviour
 def test_api_errors_and_state_dict():
     K = KGE()

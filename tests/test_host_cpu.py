@@ -109,6 +109,15 @@ cnt = torch.tensor([int(sum((row[j] > row[p]) or (row[j] == row[p] and j < p) fo
                     for row, p in zip(scores, cols)], dtype=torch.int32)
 dist.all_reduce(cnt)
 assert np.array_equal(cnt.numpy() + 1, ranks)
+# host-side row sharding of a train batch: the two ranks' shards tile the batch, weights stay whole
+from knowledgegraphembedding_b200.model import _shard_rows
+batch = (torch.from_numpy(pos), torch.from_numpy(neg), torch.from_numpy(w), "tail-batch")
+sh = _shard_rows(batch)
+assert sh.total == B and sh.row_begin == b and sh.positive.shape[0] == e - b and sh.weight.shape[0] == B
+assert _shard_rows(sh) is sh
+got = [None, None]
+dist.all_gather_object(got, (sh.row_begin, sh.positive.numpy(), sh.negative.numpy()))
+assert np.array_equal(np.concatenate([g[1] for g in got]), pos) and np.array_equal(np.concatenate([g[2] for g in got]), neg)
 dist.destroy_process_group()
 print("ok")
 """
