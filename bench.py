@@ -224,8 +224,12 @@ def run_gpu(args):
     for i in range(args.warmup):
         step_device(i)
     m._ws['kernel_events'] = events = []
+    m._ws['exchange_events'] = xevents = []
     ms_total = timed(step_device, args.steps, 0)
-    m._ws['kernel_events'] = None
+    m._ws['kernel_events'] = m._ws['exchange_events'] = None
+    exchange_ms = float(np.mean([a.elapsed_time(b) for a, b in xevents])) if xevents else None
+    exchange_path = "nvlink_peer_memory (kge_peer_reduce_adam)" if m._ws.get('peer') else \
+        ("nccl_allreduce + kge_adam_step" if world > 1 else "kge_adam_step")
     clocks = sampler.stop()
     row_ms = float(np.mean([a.elapsed_time(b) for a, b in events])) if events else None
     ms_per_step = ms_total / args.steps
@@ -304,6 +308,8 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "last_loss": last.get("loss")},
         "roofline": roofline, "cpu_baseline": cpu,
+        "exchange": {"path": exchange_path, "exchange_and_optimizer_ms": exchange_ms,
+                     "bytes_reduced_per_rank": 4 * (m.entity_embedding.numel() + m.relation_embedding.numel())},
         "eval": {"metric": "filtered_eval_queries_per_sec", "value": eval_qps, "queries": 2 * nq, "seconds": eval_s,
                  "what": "KGEModel.filtered_ranks end to end: host triples -> CSR filter -> H2D -> kernels -> host ranks",
                  "count_kernel_ms": eval_kernel_ms, "count_kernel_queries_per_sec": 2 * nq / (eval_kernel_ms * 1e-3),

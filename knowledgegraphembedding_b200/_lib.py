@@ -27,6 +27,14 @@ class KgeAdamTensor(Structure):
                 ("numel", c_int64), ("step", c_int32), ("l3", c_int32)]
 
 
+PEER_MAX_RANKS, PEER_HANDLE_BYTES = 16, 64
+
+
+class KgePeerGroup(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("grad", c_void_p * PEER_MAX_RANKS),
+                ("flags", c_void_p * PEER_MAX_RANKS)]
+
+
 # name -> (restype, argtypes): exactly the prototypes of include/kge_b200.h
 _M = POINTER(KgeModelStruct)
 PROTOTYPES = {
@@ -66,6 +74,14 @@ PROTOTYPES = {
     "kge_sample_negatives": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.c_uint64,
                                      ctypes.c_uint64, c_void_p, c_void_p]),
     "kge_eval_filter_bits": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "kge_peer_alloc": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
+    "kge_peer_free": (c_int, [c_void_p]),
+    "kge_peer_export": (c_int, [c_void_p, c_void_p]),
+    "kge_peer_open": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    "kge_peer_close": (c_int, [c_void_p]),
+    "kge_peer_reduce_adam": (c_int, [POINTER(KgePeerGroup), ctypes.c_uint32, POINTER(KgeAdamTensor), c_int, c_int64,
+                                     c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_double, c_double,
+                                     c_double, c_void_p, c_void_p]),
     "kge_eval_filter_bits_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                                             c_int64, c_void_p, c_void_p]),
 }

@@ -1,0 +1,276 @@
+// kge_peer.cu -- multi-GPU training exchange over NVLink peer memory: gradient reduce-scatter, Adam on the owned slice
+// and parameter broadcast in ONE kernel (no NCCL on the data path).
+//
+// The reference trains on one device (run.py:241-242); batch-sharded data parallelism is this repository's extension
+// (DESIGN.md section 6).  Every rank holds E, R and a gradient workspace [dE | dR | dM | row losses]; after the local
+// train kernels the workspaces have to be summed and the dense Adam step (model.py:303) applied to every replica.
+// Instead of all-reduce + replicated Adam, rank g owns the g-th contiguous slice of the parameter region:
+//     for every 16-byte group of its slice:  load the group from all G workspaces (G-1 NVLink reads, fixed rank order),
+//     sum, run torch.optim.Adam's update on the local p / exp_avg / exp_avg_sq, store p, and push the new parameter
+//     values into the other ranks' workspaces (G-1 NVLink writes).
+// A second, small kernel waits until every peer has finished pushing and copies the received slices into the local
+// tables.  Wire traffic per rank is (G-1)/G of the region in each direction, overlapped (reads and writes use opposite
+// NVLink directions); Adam's HBM traffic drops from 7 table passes to 7/G + 2(G-1)/G, and all replicas end bit-identical.
+// Moments are valid only on the owning rank (the host gathers them when optimizer.state_dict() is taken).
+//
+// Cross-GPU ordering uses two flag channels per rank in peer-visible memory: channel 0 "my gradients are final",
+// channel 1 "my pushes are done".  Flags carry the step epoch; waits are bounded (globaltimer) and report through
+// err_flag instead of hanging the GPU.
+#include <math.h>
+#include <string.h>
+
+#include "kge_common.cuh"
+
+namespace kge {
+
+constexpr int PEER_MAX = KGE_PEER_MAX_RANKS;
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct PeerTensor {
+  float *p, *m, *v;
+  int64_t off, n;                // position of the tensor's gradient inside the workspace (floats), element count
+  float step_size, bc2_sqrt;
+};
+struct PeerArgs {
+  float *grad[PEER_MAX];         // workspace base of every rank (peer-mapped); grad[rank] is local
+  uint32_t *flags[PEER_MAX];     // flag block of every rank: [2][PEER_MAX] uint32
+  int world, rank;
+  uint32_t epoch;
+  PeerTensor t[3];
+  int nt;
+  int64_t lo4, hi4, p4;          // owned slice and size of the parameter region, in float4 units
+  int64_t row_off, row_n;        // loss rows inside the workspace (floats); summed over ranks into rows_out
+  float *rows_out;
+  float w1, b2, w2, eps;
+  int32_t *err;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float *p) {          // system-scope load: never served from a stale L1
+  float4 r;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_peer4(float *p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// CTA 0 publishes `epoch` on `channel` to every rank; every CTA then waits until all ranks have published it here.
+__device__ __forceinline__ void peer_barrier(const PeerArgs &a, int channel) {
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + channel * PEER_MAX + a.rank, a.epoch);
+  }
+  if (threadIdx.x < a.world) {
+    const uint32_t *f = a.flags[a.rank] + channel * PEER_MAX + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
+      if (global_ns() - t0 > kPeerTimeoutNs) {             // a peer died or fell out of step: report, do not hang
+        if (a.err) atomicExch(a.err, 2);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void peer_adam(float &p, float g, float &m, float &v, const PeerArgs &a, const PeerTensor &t) {
+  m = m + (g - m) * a.w1;                                  // same operation order as adam_elem (kge_optim.cu)
+  v = v * a.b2;
+  v = v + a.w2 * g * g;
+  const float denom = sqrtf(v) / t.bc2_sqrt + a.eps;
+  p = p + t.step_size * (m / denom);
+}
+
+__device__ __forceinline__ int tensor_of(const PeerArgs &a, int64_t i) {      // tensor holding workspace float i, or -1
+  for (int k = 0; k < a.nt; ++k)
+    if (i >= a.t[k].off && i < a.t[k].off + a.t[k].n) return k;
+  return -1;
+}
+
+// W = compile-time bound on the number of ranks (2, 4, 8 or PEER_MAX): W float4 loads in flight per thread
+template <int W>
+__global__ void __launch_bounds__(256) peer_reduce_adam_kernel(const PeerArgs a) {
+  peer_barrier(a, 0);                                      // every rank's gradients are final
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i4 = a.lo4 + tid; i4 < a.hi4; i4 += nth) {
+    const int64_t i = i4 * 4;
+    float4 part[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+      if (r < a.world) part[r] = ld_peer4(a.grad[r] + i);
+    float4 g = part[0];
+#pragma unroll
+    for (int r = 1; r < W; ++r)
+      if (r < a.world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+    const int k = tensor_of(a, i);
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k >= 0) {
+      const PeerTensor &t = a.t[k];
+      const int64_t j = i - t.off;
+      if (j + 4 <= t.n && ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0)) {
+        float4 p = *reinterpret_cast<float4 *>(t.p + j), m = *reinterpret_cast<float4 *>(t.m + j),
+               v = *reinterpret_cast<float4 *>(t.v + j);
+        peer_adam(p.x, g.x, m.x, v.x, a, t);
+        peer_adam(p.y, g.y, m.y, v.y, a, t);
+        peer_adam(p.z, g.z, m.z, v.z, a, t);
+        peer_adam(p.w, g.w, m.w, v.w, a, t);
+        *reinterpret_cast<float4 *>(t.p + j) = p;
+        *reinterpret_cast<float4 *>(t.m + j) = m;
+        *reinterpret_cast<float4 *>(t.v + j) = v;
+        out = p;
+      } else {                                             // tensor tail or unaligned storage
+        float gs[4] = {g.x, g.y, g.z, g.w}, os[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < 4; ++e)
+          if (j + e < t.n) {
+            float p = t.p[j + e], m = t.m[j + e], v = t.v[j + e];
+            peer_adam(p, gs[e], m, v, a, t);
+            t.p[j + e] = p; t.m[j + e] = m; t.v[j + e] = v;
+            os[e] = p;
+          }
+        out = make_float4(os[0], os[1], os[2], os[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < a.world && r != a.rank) st_peer4(a.grad[r] + i, out);      // the new parameters travel in the slot
+    }
+  }
+  // per-row losses: each row is non-zero on exactly one rank; every rank sums all of them for its own log line
+  for (int64_t i = tid; i < a.row_n; i += nth) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) {
+      float x;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.grad[r] + a.row_off + i) : "memory");
+      s += x;
+    }
+    a.rows_out[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_finish_kernel(const PeerArgs a) {
+  peer_barrier(a, 1);                                      // every rank has pushed its slice (and read ours)
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t own = a.hi4 - a.lo4;
+  const float *local = a.grad[a.rank];
+  for (int64_t c = tid; c < a.p4 - own; c += nth) {        // every float4 group outside the owned slice
+    const int64_t i4 = c < a.lo4 ? c : c + own;
+    const int64_t i = i4 * 4;
+    const int k = tensor_of(a, i);
+    if (k < 0) continue;
+    const PeerTensor &t = a.t[k];
+    const int64_t j = i - t.off;
+    const float4 val = ld_peer4(local + i);
+    if (j + 4 <= t.n && (((uintptr_t)t.p & 15) == 0)) {
+      *reinterpret_cast<float4 *>(t.p + j) = val;
+    } else {
+      const float vs[4] = {val.x, val.y, val.z, val.w};
+      for (int e = 0; e < 4; ++e)
+        if (j + e < t.n) t.p[j + e] = vs[e];
+    }
+  }
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_peer_alloc(int device, int64_t bytes, void **ptr) {
+  KGE_REQUIRE(ptr && bytes > 0, "bad arguments");
+  KGE_CUDA_OK(cudaSetDevice(device));
+  KGE_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));             // a whole cudaMalloc block: exportable with cudaIpc
+  KGE_CUDA_OK(cudaMemset(*ptr, 0, (size_t)bytes));
+  return KGE_OK;
+}
+
+extern "C" int kge_peer_free(void *ptr) {
+  if (ptr) KGE_CUDA_OK(cudaFree(ptr));
+  return KGE_OK;
+}
+
+extern "C" int kge_peer_export(void *ptr, void *host_handle) {
+  KGE_REQUIRE(ptr && host_handle, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == KGE_PEER_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  KGE_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(host_handle, &h, sizeof(h));
+  return KGE_OK;
+}
+
+extern "C" int kge_peer_open(int device, const void *host_handle, void **peer_ptr) {
+  KGE_REQUIRE(host_handle && peer_ptr, "bad arguments");
+  KGE_CUDA_OK(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, host_handle, sizeof(h));
+  KGE_CUDA_OK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KGE_OK;
+}
+
+extern "C" int kge_peer_close(void *peer_ptr) {
+  if (peer_ptr) KGE_CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
+  return KGE_OK;
+}
+
+extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch, const kge_adam_tensor_t *ts,
+                                    int nt, int64_t param_floats, int64_t slice_begin4, int64_t slice_end4,
+                                    int64_t row_offset, int64_t row_floats, float *rows_out, double lr, double beta1,
+                                    double beta2, double eps, int32_t *err_flag, void *stream) {
+  KGE_REQUIRE(grp && ts && nt >= 1 && nt <= 3, "kge_peer_reduce_adam takes 1..3 tensors");
+  KGE_REQUIRE(grp->world >= 2 && grp->world <= PEER_MAX && grp->rank >= 0 && grp->rank < grp->world,
+              "peer group of %d ranks not supported (2..%d)", grp->world, PEER_MAX);
+  KGE_REQUIRE(param_floats > 0 && param_floats % 4 == 0, "parameter region must be a multiple of 4 floats");
+  KGE_REQUIRE(slice_begin4 >= 0 && slice_begin4 <= slice_end4 && slice_end4 * 4 <= param_floats, "bad slice");
+  KGE_REQUIRE(row_floats == 0 || (rows_out && row_offset >= param_floats), "bad loss-row region");
+  PeerArgs a{};
+  a.world = grp->world; a.rank = grp->rank; a.epoch = epoch;
+  for (int r = 0; r < grp->world; ++r) {
+    KGE_REQUIRE(grp->grad[r] && grp->flags[r], "peer %d is not mapped", r);
+    KGE_REQUIRE(((uintptr_t)grp->grad[r] & 15) == 0, "peer workspace %d is not 16-byte aligned", r);
+    a.grad[r] = (float *)grp->grad[r];
+    a.flags[r] = (uint32_t *)grp->flags[r];
+  }
+  const float *base = a.grad[a.rank];
+  a.nt = nt;
+  for (int i = 0; i < nt; ++i) {
+    KGE_REQUIRE(ts[i].param && ts[i].grad && ts[i].exp_avg && ts[i].exp_avg_sq && ts[i].numel > 0 && ts[i].step >= 1,
+                "bad Adam tensor %d", i);
+    const int64_t off = ts[i].grad - base;
+    KGE_REQUIRE(off >= 0 && off % 4 == 0 && off + ts[i].numel <= param_floats,
+                "gradient of tensor %d is not a 16-byte aligned view of the local workspace", i);
+    const double bc1 = 1.0 - pow(beta1, (double)ts[i].step);
+    const double bc2 = 1.0 - pow(beta2, (double)ts[i].step);
+    a.t[i] = PeerTensor{ts[i].param, ts[i].exp_avg, ts[i].exp_avg_sq, off, ts[i].numel, (float)(-(lr / bc1)),
+                        (float)sqrt(bc2)};
+  }
+  a.lo4 = slice_begin4; a.hi4 = slice_end4; a.p4 = param_floats / 4;
+  a.row_off = row_offset; a.row_n = row_floats; a.rows_out = rows_out;
+  a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
+  a.err = err_flag;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.world <= 2) peer_reduce_adam_kernel<2><<<148 * 8, 256, 0, st>>>(a);
+  else if (a.world <= 4) peer_reduce_adam_kernel<4><<<148 * 8, 256, 0, st>>>(a);
+  else if (a.world <= 8) peer_reduce_adam_kernel<8><<<148 * 8, 256, 0, st>>>(a);
+  else peer_reduce_adam_kernel<PEER_MAX><<<148 * 8, 256, 0, st>>>(a);
+  KGE_CUDA_OK(cudaGetLastError());
+  peer_finish_kernel<<<148 * 8, 256, 0, st>>>(a);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}

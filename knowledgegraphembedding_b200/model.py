@@ -271,17 +271,48 @@ class KGEModel(nn.Module):
             ps.append(self.modulus)
         return ps
 
+    def _peer_exchange(self, floats):
+        """The NVLink peer-memory exchange of this model's gradient workspace (peer.py), or None: single process,
+        KGE_NO_PEER=1, or peer memory could not be set up (then every rank falls back to the NCCL all-reduce)."""
+        rank, world = _dist()
+        if world == 1 or os.environ.get('KGE_NO_PEER'):
+            return None
+        peer = self._ws.get('peer')
+        if peer is False:
+            return None
+        dev = self.entity_embedding.device
+        if peer is not None and (peer.capacity < floats or peer.device != dev or peer.world != world):
+            torch.cuda.synchronize(dev)
+            peer.close()
+            peer = None
+            self._ws.pop('grad_views', None)
+        if peer is None:
+            from .peer import PeerExchange
+            try:
+                peer = PeerExchange(dev, floats + 8192)       # slack: a larger ragged batch does not re-map
+            except _lib.KgeError as exc:
+                logging.warning('NVLink peer exchange disabled, using NCCL all-reduce: %s' % exc)
+                self._ws['peer'] = False
+                return None
+            self._ws['peer'] = peer
+        return peer
+
     def _grad_workspace(self, B):
         """One flat fp32 buffer [dE | dR | dModulus(4) | pos_row[B] | neg_row[B]] so that the multi-GPU
-        exchange is a single all-reduce, plus the small scalar buffers."""
+        exchange covers it in one piece (peer-visible memory when the NVLink exchange is active), plus the small
+        scalar buffers."""
         dev = self.entity_embedding.device
-        cached = self._ws.get('grad_views')
-        if cached is not None and cached[0] == (B, dev):
-            return dict(cached[1])
         nE, nR = self.entity_embedding.numel(), self.relation_embedding.numel()
         nE4, nR4 = (nE + 3) // 4 * 4, (nR + 3) // 4 * 4
         total = nE4 + nR4 + 4 + 2 * B
-        flat = self._buffer('grad_flat', total, torch.float32, dev)[:total]
+        peer = self._peer_exchange(total)
+        cached = self._ws.get('grad_views')
+        if cached is not None and cached[0] == (B, dev, peer is not None):
+            return dict(cached[1])
+        if peer is not None:
+            flat = peer.workspace[:total]
+        else:
+            flat = self._buffer('grad_flat', total, torch.float32, dev)[:total]
         views = {
             'flat': flat,
             'gE': flat[:nE].view_as(self.entity_embedding),
@@ -289,11 +320,27 @@ class KGEModel(nn.Module):
             'gM': flat[nE4 + nR4:nE4 + nR4 + 1].view(1, 1),
             'pos_row': flat[nE4 + nR4 + 4:nE4 + nR4 + 4 + B],
             'neg_row': flat[nE4 + nR4 + 4 + B:total],
+            'param_floats': nE4 + nR4 + 4,
+            'rows_sum': self._buffer('rows_sum', 2 * B, torch.float32, dev)[:2 * B],
+            'peer': peer,
             'wsum': self._buffer('wsum', 1, torch.float32, dev),
             'reg': self._buffer('reg_partials', 148 * 8, torch.float64, dev),
         }
-        self._ws['grad_views'] = ((B, dev), views)           # slicing costs ~10 us per view: do it once per batch size
+        self._ws['grad_views'] = ((B, dev, peer is not None), views)   # slicing costs ~10 us per view: once per batch size
         return dict(views)
+
+    def _gather_moments(self, optimizer):
+        """Peer-exchange steps keep exp_avg / exp_avg_sq current only on the rank that owns each slice; make them whole
+        on every rank (collective: every rank calls it at the same point, e.g. run.py:106 optimizer.state_dict())."""
+        sliced = getattr(optimizer, '_kge_sliced_moments', None)
+        if not sliced:
+            return
+        from .peer import gather_sliced_moments
+        param_floats, offsets = sliced
+        params = self._trainable()
+        pairs = [(optimizer.state[p]['exp_avg'], optimizer.state[p]['exp_avg_sq']) for p in params if len(optimizer.state[p])]
+        gather_sliced_moments(pairs, offsets[:len(pairs)], param_floats)
+        optimizer._kge_sliced_moments = None
 
     @staticmethod
     def _fusable_adam(model, optimizer):
@@ -321,9 +368,13 @@ class KGEModel(nn.Module):
         out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
         model._prefetch_batch(train_iterator)     # next batch's next() + H2D overlap this step's kernels
         reg = float(getattr(args, 'regularization', 0.0))
-        out = out.tolist()                        # the step's single device->host sync (model.py:305-310 has 3-4)
-        if out[4] != 0.0:
+        host = out.cpu()                          # the step's single device->host sync (model.py:305-310 has 3-4)
+        code = int(host.view(torch.int32)[4])
+        out = host.tolist()
+        if code != 0:
             model._err_flag().zero_()
+            if code == 2:
+                raise _lib.KgeError('NVLink peer exchange timed out: a rank died or the ranks fell out of step')
             raise IndexError('index out of range in sample (entity/relation id outside the embedding table)')
         regularization_log = {'regularization': out[3]} if reg != 0.0 else {}
         log = {
@@ -459,12 +510,21 @@ class KGEModel(nn.Module):
             _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
                       _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
                       wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
-            if world > 1:
-                # batch-sharded data parallelism: one all-reduce of [dE|dR|dM|row losses] over NVLink
-                torch.distributed.all_reduce(ws['flat'])
         if events is not None:
             ev1.record()
             events.append((ev0, ev1))
+
+        peer = ws['peer'] if (fused_adam and reg == 0.0 and not sliced) else None
+        pos_rows, neg_rows = ws['pos_row'], ws['neg_row']
+        xevents = model._ws.get('exchange_events')    # bench.py: CUDA events around gradient exchange + optimizer
+        if xevents is not None:
+            xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xev0.record()
+        if world > 1 and not sliced and peer is None:
+            # batch-sharded data parallelism, NCCL path: one all-reduce of [dE|dR|dM|row losses]
+            if getattr(optimizer, '_kge_sliced_moments', None):
+                model._gather_moments(optimizer)
+            torch.distributed.all_reduce(ws['flat'])
 
         if fused_adam:
             group = optimizer.param_groups[0]
@@ -485,7 +545,18 @@ class KGEModel(nn.Module):
                 _lib.call("kge_adam_step", tensors, len(chunks), *hyper, reg,
                           _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
 
-            if sliced:
+            if peer is not None:
+                # NVLink peer-memory exchange (csrc/kge_peer.cu): reduce-scatter of the gradient workspaces, Adam on
+                # the slice this rank owns and broadcast of the new parameters, fused; no NCCL call in the step
+                if getattr(optimizer, '_kge_sliced_moments', None) is None:
+                    if not getattr(optimizer, '_kge_hooked', False):
+                        optimizer.register_state_dict_pre_hook(lambda opt: model._gather_moments(opt))
+                        optimizer._kge_hooked = True
+                flat_ptr = ws['flat'].data_ptr()
+                optimizer._kge_sliced_moments = (ws['param_floats'], [(e[1] - flat_ptr) // 4 for e in entries])
+                peer.reduce_adam(entries, hyper, ws['param_floats'], ws['param_floats'], 2 * B, ws['rows_sum'], err, st)
+                pos_rows, neg_rows = ws['rows_sum'][:B], ws['rows_sum'][B:]
+            elif sliced:
                 pE, gE_, mE, vE, _, stepE, _ = entries[0]
                 for work, lo, n in reductions:              # Adam on a slice as soon as its all-reduce has landed
                     if work is not None:
@@ -498,7 +569,7 @@ class KGEModel(nn.Module):
                 adam(entries)
             reg_partials = ws['reg'] if reg != 0.0 else None
             for p, g in zip(params, grads):
-                p.grad = g
+                p.grad = g if peer is None else None    # peer path: the workspace slots now carry parameter values
         else:
             # any other optimizer object: hand it our gradients and let it do its own update
             reg_partials = None
@@ -514,7 +585,10 @@ class KGEModel(nn.Module):
                 p.grad = g
             optimizer.step()
 
-        _lib.call("kge_loss_finalize", _ptr(ws['pos_row']), _ptr(ws['neg_row']), _ptr(weight),
+        if xevents is not None:
+            xev1.record()
+            xevents.append((xev0, xev1))
+        _lib.call("kge_loss_finalize", _ptr(pos_rows), _ptr(neg_rows), _ptr(weight),
                   _ptr(ws['wsum']) if weight is not None else None, B, reg,
                   _ptr(reg_partials) if reg_partials is not None else None,
                   reg_partials.numel() if reg_partials is not None else 0, _ptr(ws['out']), st)

@@ -1,0 +1,145 @@
+"""Worker of tests/test_multi_gpu.py (one process per GPU, launched with torch.distributed.run).
+
+Checks on N >= 2 B200s, against the numpy oracle of the reference's single-device train step on the WHOLE batch:
+  * batch-sharded training through the NVLink peer-memory exchange (kge_peer_reduce_adam): losses, tables and gathered
+    Adam moments within 1e-5, replicas bit-identical on every rank, optimizer.state_dict() whole on every rank;
+  * the same through the NCCL all-reduce path (KGE_NO_PEER behaviour), and that the two paths agree;
+  * switching an optimizer from the peer path to the NCCL path mid-run (moments gathered automatically);
+  * entity-sharded filtered ranking: ranks equal the oracle's.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import outlier_fraction, relinf          # noqa: E402
+from knowledgegraphembedding_b200 import KGEModel      # noqa: E402
+from oracle import kge_oracle as O                     # noqa: E402
+
+FLAGS = {"TransE": (False, False), "RotatE": (True, False), "pRotatE": (False, False), "ComplEx": (True, True)}
+TOL = 1e-5
+
+
+def build(model, nentity, nrel, d, gamma, st, dev):
+    de, dr = FLAGS[model]
+    m = KGEModel(model, nentity, nrel, d, gamma, double_entity_embedding=de, double_relation_embedding=dr)
+    with torch.no_grad():
+        m.entity_embedding.copy_(torch.from_numpy(st["entity_embedding"]))
+        m.relation_embedding.copy_(torch.from_numpy(st["relation_embedding"]))
+        if model == "pRotatE":
+            m.modulus.copy_(torch.from_numpy(st["modulus"]))
+    return m.to(dev)
+
+
+def batches(nentity, nrel, B, N, count, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(count):
+        pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
+        neg = rng.randint(nentity, size=(B, N))
+        w = np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)
+        out.append((pos.astype(np.int64), neg.astype(np.int64), w, "tail-batch" if i % 2 == 0 else "head-batch"))
+    return out
+
+
+def as_torch(b):
+    return (torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2]), b[3])
+
+
+def identical_on_all_ranks(t, what):
+    mine = t.detach().contiguous().view(torch.int32).to(torch.int64).sum().reshape(1)
+    got = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(got, mine)
+    assert all(int(g) == int(got[0]) for g in got), what + ": replicas differ"
+
+
+def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    st = O.init_tables(model, nentity, nrel, d, gamma, *FLAGS[model], seed=3)
+    pool = batches(nentity, nrel, B, N, steps, seed=7)
+    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
+                                 uni_weight=False, regularization=0.0)
+    ref = O.TrainState(model, st, gamma, d)
+    ref_logs = [O.train_step(ref, b, lr=lr, adversarial=True, alpha=1.0) for b in pool]
+
+    results = {}
+    for path in ("peer", "nccl", "switch"):
+        m = build(model, nentity, nrel, d, gamma, st, dev)
+        if path == "nccl":
+            m._ws['peer'] = False
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+        logs = []
+        for i, b in enumerate(pool):
+            if path == "switch" and i == steps // 2:
+                m._ws['peer'] = False            # from here on the NCCL path: the sliced moments must be gathered first
+                m._ws.pop('grad_views', None)
+            logs.append(KGEModel.train_step(m, opt, iter([as_torch(b)]), args))
+        if path == "peer":
+            assert m._ws.get('peer') not in (None, False), "peer exchange was not active"
+            assert getattr(opt, '_kge_sliced_moments', None) is not None
+        sd = opt.state_dict()                    # run.py:106 -- gathers the sliced moments on the peer path
+        assert getattr(opt, '_kge_sliced_moments', None) is None
+        for log, want in zip(logs, ref_logs):
+            for k, v in want.items():
+                assert abs(log[k] - v) <= 2e-5 * max(abs(v), 1e-3), (model, path, k, log[k], v)
+        names = ["entity_embedding", "relation_embedding"] + (["modulus"] if model == "pRotatE" else [])
+        for idx, name in enumerate(names):
+            got = getattr(m, name).detach().cpu().numpy()
+            want = ref.state[name]
+            assert outlier_fraction(got, want, TOL) <= 1e-3 and np.max(np.abs(got - want)) <= 2.5 * lr * steps, \
+                (model, path, name, relinf(got, want))
+            identical_on_all_ranks(getattr(m, name), f"{model}/{path}/{name}")
+            mom = sd['state'][idx]
+            for key, okey in (("exp_avg", "m"), ("exp_avg_sq", "v")):
+                g, w = mom[key].cpu().numpy(), ref.adam[name][okey]
+                assert relinf(g, w) <= 1e-4, (model, path, name, key, relinf(g, w))
+                identical_on_all_ranks(mom[key], f"{model}/{path}/{name}/{key}")
+        results[path] = {n: getattr(m, n).detach().clone() for n in names}
+    for n in results["peer"]:
+        a, b = results["peer"][n].cpu().numpy(), results["nccl"][n].cpu().numpy()
+        assert outlier_fraction(a, b, TOL) <= 1e-3, (model, n)
+    if rank == 0:
+        print(f"train ok: {model} nentity={nentity} d={d} B={B} N={N} world={world}", flush=True)
+
+
+def check_eval(dev):
+    model, nentity, nrel, d, gamma = "RotatE", 3001, 5, 32, 12.0
+    st = O.init_tables(model, nentity, nrel, d, gamma, True, False, seed=4)
+    m = build(model, nentity, nrel, d, gamma, st, dev)
+    rng = np.random.RandomState(0)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(40))) for _ in range(2000)})
+    test = all_true[:24]
+    want = O.filtered_ranks(model, st, test, all_true, nentity, gamma, d)
+    got = np.concatenate([m.filtered_ranks(test, all_true, mode, exact=True) for mode in ("head-batch", "tail-batch")])
+    fast = np.concatenate([m.filtered_ranks(test, all_true, mode) for mode in ("head-batch", "tail-batch")])
+    assert np.array_equal(got, fast)
+    assert np.mean(got == np.asarray(want)) >= 0.95 and np.max(np.abs(got - np.asarray(want))) <= 1, (got, want)
+    if dist.get_rank() == 0:
+        print("eval ok", flush=True)
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    check_case("RotatE", 2003, 7, 64, 12.0, 64, 32, 4, dev)            # single-read path sizes (pairs/entity small)
+    check_case("RotatE", 301, 5, 16, 6.0, 96, 64, 4, dev)              # many pairs per entity -> entity-major backward
+    check_case("pRotatE", 517, 3, 10, 6.0, 33, 8, 3, dev)              # ragged: odd rows per rank, modulus, tensor tails
+    check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev)
+    check_eval(dev)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()

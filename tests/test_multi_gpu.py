@@ -1,0 +1,23 @@
+"""Multi-GPU parity (one process per GPU over torch.distributed): the NVLink peer-memory training exchange, the NCCL
+path and entity-sharded evaluation against the oracle.  Needs >= 2 B200s (gpurun --gpus 2); skipped on one GPU."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_exchange_and_sharded_eval_against_oracle():
+    n = min(torch.cuda.device_count(), 8)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (res.stdout[-2000:], res.stderr[-4000:])
