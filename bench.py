@@ -228,8 +228,10 @@ def run_gpu(args):
     ms_total = timed(step_device, args.steps, 0)
     m._ws['kernel_events'] = m._ws['exchange_events'] = None
     exchange_ms = float(np.mean([a.elapsed_time(b) for a, b in xevents])) if xevents else None
-    exchange_path = "nvlink_peer_memory (kge_peer_reduce_adam)" if m._ws.get('peer') else \
-        ("nccl_allreduce + kge_adam_step" if world > 1 else "kge_adam_step")
+    px = m._ws.get('peer')
+    nreg = int(m._ws.get('exchange_regions', 1)) if px else 1
+    exchange_path = ("nvlink_peer_memory/%s%s (kge_peer_reduce_adam)" % (px.backend, "+nvswitch_multicast" if px.multicast else "")
+                     if px else ("nccl_allreduce + kge_adam_step" if world > 1 else "kge_adam_step"))
     clocks = sampler.stop()
     row_ms = float(np.mean([a.elapsed_time(b) for a, b in events])) if events else None
     ms_per_step = ms_total / args.steps
@@ -304,11 +306,14 @@ def run_gpu(args):
                    "adversarial": True, "double_entity_embedding": de,
                    "sharding": f"positive rows over {world} rank(s), tables replicated; eval: entity slices",
                    "l2_policy": "no flush: each step streams 0.6 GB of tables+moments+grads (> 126 MB L2)"},
-        "clocks": clocks, "gpu_launches": 7 * args.steps,
+        # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan, scatter, entity_kernel per region,
+        # loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish per region
+        "clocks": clocks, "gpu_launches": (5 + nreg + (2 * nreg if px else 1)) * args.steps,
         "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "last_loss": last.get("loss")},
         "roofline": roofline, "cpu_baseline": cpu,
-        "exchange": {"path": exchange_path, "exchange_and_optimizer_ms": exchange_ms,
+        "exchange": {"path": exchange_path, "exposed_exchange_and_optimizer_ms": exchange_ms,
+                     "regions_per_step": nreg,
                      "bytes_reduced_per_rank": 4 * (m.entity_embedding.numel() + m.relation_embedding.numel())},
         "eval": {"metric": "filtered_eval_queries_per_sec", "value": eval_qps, "queries": 2 * nq, "seconds": eval_s,
                  "what": "KGEModel.filtered_ranks end to end: host triples -> CSR filter -> H2D -> kernels -> host ranks",

@@ -214,15 +214,18 @@ int kge_sample_negatives(const int64_t *triple_index, const int32_t *key_start, 
 /* ---- multi-GPU training exchange over NVLink peer memory (no counterpart in the single-device reference: run.py:241-242;
  *      it replaces "all-reduce the gradients, then optimizer.step() on every replica", model.py:301-303) ----
  * Each rank allocates one peer-visible block (kge_peer_alloc), exports it (kge_peer_export -> 64 opaque bytes the host
- * side exchanges by any means) and maps the other ranks' blocks (kge_peer_open).  The block holds the rank's gradient
+ * side exchanges by any means) and maps the other ranks' blocks (kge_peer_open) -- or obtains the mappings, and an
+ * NVSwitch multicast mapping on top, from any symmetric-memory allocator.  The block holds the rank's gradient
  * workspace [dE | dR | dM | row losses] and a flag block of 2*KGE_PEER_MAX_RANKS uint32.
  * kge_peer_reduce_adam, called by every rank with the same epoch (1, 2, 3, ... per call) after its local train kernels:
  *   - waits until every rank has arrived (flags, bounded wait: err_flag := 2 on a 20 s timeout),
- *   - for the float4 groups [slice_begin4, slice_end4) of the parameter region it owns: sums the G workspaces in rank
- *     order, applies the Adam update (same arithmetic as kge_adam_step) to the local param / exp_avg / exp_avg_sq and
+ *   - one call exchanges the region [region_begin4, region_end4) of the parameter part of the workspace (float4 units; a
+ *     step may be cut into several regions so that the exchange of a finished gradient slice overlaps the computation
+ *     of the next one); for the groups [slice_begin4, slice_end4) of the region it owns the rank sums the G workspaces
+ *     (in rank order, or inside the NVSwitch with multimem.ld_reduce when a multicast mapping is given), applies the Adam update (same arithmetic as kge_adam_step) to the local param / exp_avg / exp_avg_sq and
  *     pushes the new parameter values to every other rank,
  *   - sums the row-loss region of all ranks into rows_out (local, row_floats floats),
- *   - waits until every rank has pushed, then copies the received slices into the local parameter tensors.
+ *   - waits until every rank has pushed, then copies the rest of the region (received slices) into the local parameters.
  * host_tensors[i].grad must be the tensor's gradient view inside the local workspace (16-byte aligned offset).
  * After the call all ranks hold bit-identical parameters; exp_avg / exp_avg_sq are current only on the owning rank. */
 #define KGE_PEER_MAX_RANKS 16
@@ -231,6 +234,8 @@ typedef struct kge_peer_group {
   int32_t world, rank;
   void *grad[KGE_PEER_MAX_RANKS];      /* gradient workspace of every rank as mapped here; [rank] is the local one */
   void *flags[KGE_PEER_MAX_RANKS];     /* flag block of every rank as mapped here (zero-initialised)               */
+  void *multicast;                     /* NVSwitch multicast mapping of the gradient workspaces (one address = all G
+                                          replicas; multimem.ld_reduce / multimem.st), or NULL: unicast NVLink accesses */
 } kge_peer_group_t;
 
 int kge_peer_alloc(int device, int64_t bytes, void **ptr);
@@ -239,9 +244,10 @@ int kge_peer_export(void *ptr, void *host_handle);
 int kge_peer_open(int device, const void *host_handle, void **peer_ptr);
 int kge_peer_close(void *peer_ptr);
 int kge_peer_reduce_adam(const kge_peer_group_t *host_group, uint32_t epoch, const kge_adam_tensor_t *host_tensors,
-                         int n_tensors, int64_t param_floats, int64_t slice_begin4, int64_t slice_end4,
-                         int64_t row_offset, int64_t row_floats, float *rows_out, double lr, double beta1,
-                         double beta2, double eps, int32_t *err_flag, void *stream);
+                         int n_tensors, int64_t param_floats, int64_t region_begin4, int64_t region_end4,
+                         int64_t slice_begin4, int64_t slice_end4, int64_t row_offset, int64_t row_floats,
+                         float *rows_out, double lr, double beta1, double beta2, double eps, int32_t *err_flag,
+                         void *stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ PEER_MAX_RANKS, PEER_HANDLE_BYTES = 16, 64
 
 class KgePeerGroup(Structure):
     _fields_ = [("world", c_int32), ("rank", c_int32), ("grad", c_void_p * PEER_MAX_RANKS),
-                ("flags", c_void_p * PEER_MAX_RANKS)]
+                ("flags", c_void_p * PEER_MAX_RANKS), ("multicast", c_void_p)]
 
 
 # name -> (restype, argtypes): exactly the prototypes of include/kge_b200.h
@@ -80,8 +80,8 @@ PROTOTYPES = {
     "kge_peer_open": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
     "kge_peer_close": (c_int, [c_void_p]),
     "kge_peer_reduce_adam": (c_int, [POINTER(KgePeerGroup), ctypes.c_uint32, POINTER(KgeAdamTensor), c_int, c_int64,
-                                     c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_double, c_double,
-                                     c_double, c_void_p, c_void_p]),
+                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_double,
+                                     c_double, c_double, c_void_p, c_void_p]),
     "kge_eval_filter_bits_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                                             c_int64, c_void_p, c_void_p]),
 }

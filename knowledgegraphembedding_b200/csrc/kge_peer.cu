@@ -17,6 +17,7 @@
 // channel 1 "my pushes are done".  Flags carry the step epoch; waits are bounded (globaltimer) and report through
 // err_flag instead of hanging the GPU.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kge_common.cuh"
@@ -33,12 +34,14 @@ struct PeerTensor {
 };
 struct PeerArgs {
   float *grad[PEER_MAX];         // workspace base of every rank (peer-mapped); grad[rank] is local
+  float *mc;                     // multicast mapping of the workspaces (NVSwitch multimem), or null
+  int64_t rlo4, rhi4;            // region of the workspace this call exchanges (float4 units); [lo4, hi4) lies inside
   uint32_t *flags[PEER_MAX];     // flag block of every rank: [2][PEER_MAX] uint32
   int world, rank;
   uint32_t epoch;
   PeerTensor t[3];
   int nt;
-  int64_t lo4, hi4, p4;          // owned slice and size of the parameter region, in float4 units
+  int64_t lo4, hi4;              // slice of the region this rank owns, in float4 units
   int64_t row_off, row_n;        // loss rows inside the workspace (floats); summed over ranks into rows_out
   float *rows_out;
   float w1, b2, w2, eps;
@@ -63,6 +66,26 @@ __device__ __forceinline__ float4 ld_peer4(const float *p) {          // system-
 }
 __device__ __forceinline__ void st_peer4(float *p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// NVSwitch in-fabric reduction / broadcast (NVLS): one load returns the sum of the G replicas of an address, one store
+// writes all G replicas.  Halves the NVLink bytes of the exchange compared with G-1 unicast reads + G-1 unicast writes.
+__device__ __forceinline__ float4 multimem_sum4(const float *mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float multimem_sum1(const float *mc) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_store4(float *mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -106,73 +129,114 @@ __device__ __forceinline__ int tensor_of(const PeerArgs &a, int64_t i) {      //
 }
 
 // W = compile-time bound on the number of ranks (2, 4, 8 or PEER_MAX): W float4 loads in flight per thread
-template <int W>
-__global__ void __launch_bounds__(256) peer_reduce_adam_kernel(const PeerArgs a) {
+// MC: the reduction and the broadcast go through the multicast mapping (a.mc) instead of W unicast accesses
+// Adam on one 16-byte group of the owned slice; returns the new parameter values (zeros outside any tensor)
+__device__ __forceinline__ float4 peer_update_group(const PeerArgs &a, int k, int64_t i, float4 g) {
+  const PeerTensor &t = a.t[k];
+  const int64_t j = i - t.off;
+  if (j + 4 <= t.n && ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0)) {
+    float4 p = *reinterpret_cast<float4 *>(t.p + j), m = *reinterpret_cast<float4 *>(t.m + j),
+           v = *reinterpret_cast<float4 *>(t.v + j);
+    peer_adam(p.x, g.x, m.x, v.x, a, t);
+    peer_adam(p.y, g.y, m.y, v.y, a, t);
+    peer_adam(p.z, g.z, m.z, v.z, a, t);
+    peer_adam(p.w, g.w, m.w, v.w, a, t);
+    *reinterpret_cast<float4 *>(t.p + j) = p;
+    *reinterpret_cast<float4 *>(t.m + j) = m;
+    *reinterpret_cast<float4 *>(t.v + j) = v;
+    return p;
+  }
+  float gs[4] = {g.x, g.y, g.z, g.w}, os[4] = {0.f, 0.f, 0.f, 0.f};      // tensor tail or unaligned storage
+  for (int e = 0; e < 4; ++e)
+    if (j + e < t.n) {
+      float p = t.p[j + e], m = t.m[j + e], v = t.v[j + e];
+      peer_adam(p, gs[e], m, v, a, t);
+      t.p[j + e] = p; t.m[j + e] = m; t.v[j + e] = v;
+      os[e] = p;
+    }
+  return make_float4(os[0], os[1], os[2], os[3]);
+}
+
+// W = compile-time bound on the number of ranks (2, 4, 8 or PEER_MAX): W unicast float4 loads in flight per thread.
+// MCR / MCS: the reduction / the broadcast go through the multicast mapping (a.mc); with MCR 4 groups are in flight
+// per thread.  CTAs are small (128 threads) so that one fits next to the persistent entity kernel of the next slice.
+constexpr int PEER_THREADS = 128;
+template <int W, bool MCR, bool MCS>
+__global__ void __launch_bounds__(PEER_THREADS) peer_reduce_adam_kernel(const PeerArgs a) {
   peer_barrier(a, 0);                                      // every rank's gradients are final
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i4 = a.lo4 + tid; i4 < a.hi4; i4 += nth) {
-    const int64_t i = i4 * 4;
-    float4 part[W];
+  if constexpr (MCR) {
+    constexpr int U = 4;
+    for (int64_t i4 = a.lo4 + tid; i4 < a.hi4; i4 += U * nth) {
+      float4 g[U];
+      int k[U];
 #pragma unroll
-    for (int r = 0; r < W; ++r)
-      if (r < a.world) part[r] = ld_peer4(a.grad[r] + i);
-    float4 g = part[0];
-#pragma unroll
-    for (int r = 1; r < W; ++r)
-      if (r < a.world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-    const int k = tensor_of(a, i);
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k >= 0) {
-      const PeerTensor &t = a.t[k];
-      const int64_t j = i - t.off;
-      if (j + 4 <= t.n && ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0)) {
-        float4 p = *reinterpret_cast<float4 *>(t.p + j), m = *reinterpret_cast<float4 *>(t.m + j),
-               v = *reinterpret_cast<float4 *>(t.v + j);
-        peer_adam(p.x, g.x, m.x, v.x, a, t);
-        peer_adam(p.y, g.y, m.y, v.y, a, t);
-        peer_adam(p.z, g.z, m.z, v.z, a, t);
-        peer_adam(p.w, g.w, m.w, v.w, a, t);
-        *reinterpret_cast<float4 *>(t.p + j) = p;
-        *reinterpret_cast<float4 *>(t.m + j) = m;
-        *reinterpret_cast<float4 *>(t.v + j) = v;
-        out = p;
-      } else {                                             // tensor tail or unaligned storage
-        float gs[4] = {g.x, g.y, g.z, g.w}, os[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int e = 0; e < 4; ++e)
-          if (j + e < t.n) {
-            float p = t.p[j + e], m = t.m[j + e], v = t.v[j + e];
-            peer_adam(p, gs[e], m, v, a, t);
-            t.p[j + e] = p; t.m[j + e] = m; t.v[j + e] = v;
-            os[e] = p;
-          }
-        out = make_float4(os[0], os[1], os[2], os[3]);
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = (i4 + u * nth) * 4;
+        k[u] = (i4 + u * nth < a.hi4) ? tensor_of(a, i) : -1;
+        if (k[u] >= 0) g[u] = multimem_sum4(a.mc + i);     // one load = the sum over all ranks, reduced in the switch
       }
 #pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = (i4 + u * nth) * 4;
+        if (k[u] < 0) continue;
+        const float4 out = peer_update_group(a, k[u], i, g[u]);
+        if constexpr (MCS) {
+          multimem_store4(a.mc + i, out);                  // every replica's slot (ours too) takes the new parameters
+        } else {
+          for (int r = 0; r < a.world; ++r)
+            if (r != a.rank) st_peer4(a.grad[r] + i, out);
+        }
+      }
+    }
+  } else {
+    for (int64_t i4 = a.lo4 + tid; i4 < a.hi4; i4 += nth) {
+      const int64_t i = i4 * 4;
+      float4 part[W];
+#pragma unroll
       for (int r = 0; r < W; ++r)
-        if (r < a.world && r != a.rank) st_peer4(a.grad[r] + i, out);      // the new parameters travel in the slot
+        if (r < a.world) part[r] = ld_peer4(a.grad[r] + i);
+      float4 g = part[0];
+#pragma unroll
+      for (int r = 1; r < W; ++r)
+        if (r < a.world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+      const int k = tensor_of(a, i);
+      if (k < 0) continue;
+      const float4 out = peer_update_group(a, k, i, g);
+      if constexpr (MCS) {
+        multimem_store4(a.mc + i, out);
+      } else {
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+          if (r < a.world && r != a.rank) st_peer4(a.grad[r] + i, out);    // the new parameters travel in the slot
+      }
     }
   }
   // per-row losses: each row is non-zero on exactly one rank; every rank sums all of them for its own log line
   for (int64_t i = tid; i < a.row_n; i += nth) {
     float s = 0.f;
-    for (int r = 0; r < a.world; ++r) {
-      float x;
-      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.grad[r] + a.row_off + i) : "memory");
-      s += x;
+    if constexpr (MCR) {
+      s = multimem_sum1(a.mc + a.row_off + i);
+    } else {
+      for (int r = 0; r < a.world; ++r) {
+        float x;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.grad[r] + a.row_off + i) : "memory");
+        s += x;
+      }
     }
     a.rows_out[i] = s;
   }
 }
 
-__global__ void __launch_bounds__(256) peer_finish_kernel(const PeerArgs a) {
+__global__ void __launch_bounds__(PEER_THREADS) peer_finish_kernel(const PeerArgs a) {
   peer_barrier(a, 1);                                      // every rank has pushed its slice (and read ours)
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t own = a.hi4 - a.lo4;
   const float *local = a.grad[a.rank];
-  for (int64_t c = tid; c < a.p4 - own; c += nth) {        // every float4 group outside the owned slice
-    const int64_t i4 = c < a.lo4 ? c : c + own;
+  for (int64_t c = tid; c < (a.rhi4 - a.rlo4) - own; c += nth) {    // every float4 group of the region we do not own
+    const int64_t i4 = a.rlo4 + c < a.lo4 ? a.rlo4 + c : a.rlo4 + c + own;
     const int64_t i = i4 * 4;
     const int k = tensor_of(a, i);
     if (k < 0) continue;
@@ -230,14 +294,17 @@ extern "C" int kge_peer_close(void *peer_ptr) {
 }
 
 extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch, const kge_adam_tensor_t *ts,
-                                    int nt, int64_t param_floats, int64_t slice_begin4, int64_t slice_end4,
-                                    int64_t row_offset, int64_t row_floats, float *rows_out, double lr, double beta1,
-                                    double beta2, double eps, int32_t *err_flag, void *stream) {
+                                    int nt, int64_t param_floats, int64_t region_begin4, int64_t region_end4,
+                                    int64_t slice_begin4, int64_t slice_end4, int64_t row_offset, int64_t row_floats,
+                                    float *rows_out, double lr, double beta1, double beta2, double eps,
+                                    int32_t *err_flag, void *stream) {
   KGE_REQUIRE(grp && ts && nt >= 1 && nt <= 3, "kge_peer_reduce_adam takes 1..3 tensors");
   KGE_REQUIRE(grp->world >= 2 && grp->world <= PEER_MAX && grp->rank >= 0 && grp->rank < grp->world,
               "peer group of %d ranks not supported (2..%d)", grp->world, PEER_MAX);
   KGE_REQUIRE(param_floats > 0 && param_floats % 4 == 0, "parameter region must be a multiple of 4 floats");
-  KGE_REQUIRE(slice_begin4 >= 0 && slice_begin4 <= slice_end4 && slice_end4 * 4 <= param_floats, "bad slice");
+  KGE_REQUIRE(region_begin4 >= 0 && region_begin4 <= slice_begin4 && slice_begin4 <= slice_end4 &&
+                  slice_end4 <= region_end4 && region_end4 * 4 <= param_floats,
+              "bad region / slice");
   KGE_REQUIRE(row_floats == 0 || (rows_out && row_offset >= param_floats), "bad loss-row region");
   PeerArgs a{};
   a.world = grp->world; a.rank = grp->rank; a.epoch = epoch;
@@ -260,17 +327,34 @@ extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch,
     a.t[i] = PeerTensor{ts[i].param, ts[i].exp_avg, ts[i].exp_avg_sq, off, ts[i].numel, (float)(-(lr / bc1)),
                         (float)sqrt(bc2)};
   }
-  a.lo4 = slice_begin4; a.hi4 = slice_end4; a.p4 = param_floats / 4;
+  a.rlo4 = region_begin4; a.rhi4 = region_end4; a.lo4 = slice_begin4; a.hi4 = slice_end4;
   a.row_off = row_offset; a.row_n = row_floats; a.rows_out = rows_out;
   a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
   a.err = err_flag;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.world <= 2) peer_reduce_adam_kernel<2><<<148 * 8, 256, 0, st>>>(a);
-  else if (a.world <= 4) peer_reduce_adam_kernel<4><<<148 * 8, 256, 0, st>>>(a);
-  else if (a.world <= 8) peer_reduce_adam_kernel<8><<<148 * 8, 256, 0, st>>>(a);
-  else peer_reduce_adam_kernel<PEER_MAX><<<148 * 8, 256, 0, st>>>(a);
+  const int grid = 148 * 12;
+  // multicast use: bit 0 = reduce through the switch (multimem.ld_reduce), bit 1 = broadcast through it (multimem.st)
+  int mc_mode = 0;
+  if (grp->multicast) {
+    KGE_REQUIRE(((uintptr_t)grp->multicast & 15) == 0, "multicast mapping is not 16-byte aligned");
+    a.mc = (float *)grp->multicast;
+    const char *e = getenv("KGE_PEER_MC_MODE");
+    mc_mode = e ? (atoi(e) & 3) : 3;
+  }
+#define KGE_PEER_LAUNCH(W)                                                                               \
+  do {                                                                                                   \
+    if (mc_mode == 2) peer_reduce_adam_kernel<W, false, true><<<grid, PEER_THREADS, 0, st>>>(a);        \
+    else peer_reduce_adam_kernel<W, false, false><<<grid, PEER_THREADS, 0, st>>>(a);                    \
+  } while (0)
+  if (mc_mode == 3) peer_reduce_adam_kernel<1, true, true><<<grid, PEER_THREADS, 0, st>>>(a);
+  else if (mc_mode == 1) peer_reduce_adam_kernel<1, true, false><<<grid, PEER_THREADS, 0, st>>>(a);
+  else if (a.world <= 2) KGE_PEER_LAUNCH(2);
+  else if (a.world <= 4) KGE_PEER_LAUNCH(4);
+  else if (a.world <= 8) KGE_PEER_LAUNCH(8);
+  else KGE_PEER_LAUNCH(PEER_MAX);
+#undef KGE_PEER_LAUNCH
   KGE_CUDA_OK(cudaGetLastError());
-  peer_finish_kernel<<<148 * 8, 256, 0, st>>>(a);
+  peer_finish_kernel<<<grid, PEER_THREADS, 0, st>>>(a);
   KGE_CUDA_OK(cudaGetLastError());
   return KGE_OK;
 }

@@ -336,10 +336,10 @@ class KGEModel(nn.Module):
         if not sliced:
             return
         from .peer import gather_sliced_moments
-        param_floats, offsets = sliced
+        regions, offsets = sliced
         params = self._trainable()
         pairs = [(optimizer.state[p]['exp_avg'], optimizer.state[p]['exp_avg_sq']) for p in params if len(optimizer.state[p])]
-        gather_sliced_moments(pairs, offsets[:len(pairs)], param_floats)
+        gather_sliced_moments(pairs, list(offsets)[:len(pairs)], list(regions))
         optimizer._kge_sliced_moments = None
 
     @staticmethod
@@ -432,6 +432,19 @@ class KGEModel(nn.Module):
             batch = self._stage_batch(batch, stream)
         self._ws['prefetched'] = (iterator, batch, None, stream)
 
+    def _exchange_slices(self, B, world, N):
+        """How many regions the multi-GPU exchange of one step is cut into (KGE_PEER_SLICES, default 1 = no slicing).
+        With n > 1 the exchange of a finished entity range runs on a second stream under the entity-major backward of
+        the next range.  Measured on B200 (FB15k shapes): the exposed exchange shrinks (0.41 -> 0.27 ms at 8 GPUs, n=3)
+        but the backward slows by as much (0.73 -> 0.88 ms: both kernels fight for L2 and issue slots), 1.22 vs 1.19 ms
+        per step -- so it stays opt-in.  The answer must be the same on every rank, so it is derived from the global
+        batch only: slicing needs the entity-major backward (csrc/kge_train.cu takes it when a rank's rows x N >=
+        6 x nentity) on the rank with the fewest rows."""
+        n = int(os.environ.get('KGE_PEER_SLICES', '1'))
+        if n <= 1 or self.entity_dim % 4 or (B // world) * N < 6 * self.nentity or self.nentity < 4 * n:
+            return 1
+        return min(n, 8)
+
     def train_step_async(self, optimizer, batch, args):
         """Everything train_step does on the device, without the final read-back: returns the device buffer
         [positive_sample_loss, negative_sample_loss, loss, regularization, err_flag(int32 bits), ...]."""
@@ -446,86 +459,29 @@ class KGEModel(nn.Module):
         positive = positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         negative = negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         rows, N = negative.shape
-        row_end = row_begin + rows
         uni = bool(getattr(args, 'uni_weight', False))
         weight = None if uni else subsampling_weight.to(device=dev, dtype=torch.float32,
                                                         non_blocking=True).contiguous()
         reg = float(getattr(args, 'regularization', 0.0))
         adversarial = bool(args.negative_adversarial_sampling)
         alpha = float(args.adversarial_temperature) if adversarial else 1.0
+        loss_kind = _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM
+        mode_id = _lib.MODE_IDS[mode]
 
         ws = model._grad_workspace(B)
         err = model._err_flag()
         ws['out'] = model._ws['loss_out']
         desc = model._descriptor()
         events = model._ws.get('kernel_events')       # bench.py: CUDA events around the dominant kernel
+        xevents = model._ws.get('exchange_events')    # bench.py: CUDA events around the exposed exchange + optimizer
         rank, world = _dist()
-
-        _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
-        if weight is not None:
-            _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
-        gM = ws['gM'] if model.model_name == 'pRotatE' else None
-        # the row arrays passed down start at this rank's first row: [positive, negative] hold the shard only,
-        # weight / row losses are offset views of the whole-batch buffers
-        common = (_ptr(positive), _ptr(negative), _ptr(weight[row_begin:]) if weight is not None else None,
-                  _ptr(ws['wsum']) if weight is not None else None, B, 0, rows, N)
-        neg_row, pos_row = ws['neg_row'][row_begin:], ws['pos_row'][row_begin:]
-        wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), row_end - row_begin, N)
-        wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
-        if events is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
         params = model._trainable()
         grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
+        gM = ws['gM'] if model.model_name == 'pRotatE' else None
+
+        # ---- optimizer bookkeeping (host only): torch.optim.Adam with run.py's defaults is fused, anything else steps itself
         fused_adam = KGEModel._fusable_adam(model, optimizer)
-        loss_kind = _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM
-        # optional (KGE_SLICED_TRAIN=1): slice the entity-major pass so that the all-reduce of finished gradient slices
-        # (NCCL, its own stream) overlaps the computation of the next slice, and Adam runs slice by slice behind the
-        # all-reduces.  Measured on B200: 1.21 -> 1.15 ms per step at 2 GPUs, but 1.28 -> 1.47 ms at 8 GPUs (five
-        # latency-bound collectives instead of one), so the single all-reduce below stays the default.
-        sliced = bool(os.environ.get('KGE_SLICED_TRAIN')) and fused_adam and reg == 0.0
-        reductions = []                                      # (async work or None, first element, numel) of dE slices
-        tail_work = None
-        if sliced:
-            pending = ctypes.c_int32(0)
-            _lib.call("kge_train_rows_begin", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
-                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
-                      wbytes, _ptr(err), ctypes.byref(pending), st)
-            nE = model.entity_embedding.numel()
-            nE4 = (nE + 3) // 4 * 4
-            if world > 1:                                    # dR | dM | row losses are final already
-                tail_work = torch.distributed.all_reduce(ws['flat'][nE4:], async_op=True)
-            nslices = 4 if pending.value else 1
-            for k in range(nslices):
-                eb, ee = shard_bounds(model.nentity if pending.value else 1, k, nslices)
-                if pending.value:
-                    _lib.call("kge_train_entity_pass", ctypes.byref(desc), _lib.MODE_IDS[mode], _ptr(wsp),
-                              row_end - row_begin, N, eb, ee, k, _ptr(ws['gE']), _ptr(gM), st)
-                    lo, hi = eb * model.entity_dim, ee * model.entity_dim
-                else:
-                    lo, hi = 0, nE
-                work = torch.distributed.all_reduce(ws['flat'][lo:hi], async_op=True) if world > 1 else None
-                reductions.append((work, lo, hi - lo))
-        else:
-            _lib.call("kge_train_rows", ctypes.byref(desc), _lib.MODE_IDS[mode], loss_kind, alpha, *common,
-                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
-                      wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
-        if events is not None:
-            ev1.record()
-            events.append((ev0, ev1))
-
-        peer = ws['peer'] if (fused_adam and reg == 0.0 and not sliced) else None
-        pos_rows, neg_rows = ws['pos_row'], ws['neg_row']
-        xevents = model._ws.get('exchange_events')    # bench.py: CUDA events around gradient exchange + optimizer
-        if xevents is not None:
-            xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            xev0.record()
-        if world > 1 and not sliced and peer is None:
-            # batch-sharded data parallelism, NCCL path: one all-reduce of [dE|dR|dM|row losses]
-            if getattr(optimizer, '_kge_sliced_moments', None):
-                model._gather_moments(optimizer)
-            torch.distributed.all_reduce(ws['flat'])
-
+        entries = hyper = None
         if fused_adam:
             group = optimizer.param_groups[0]
             hyper = (float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']))
@@ -540,33 +496,94 @@ class KGEModel(nn.Module):
                 entries.append((p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
                                 p.numel(), int(state['step'].item()), 1 if (reg != 0.0 and i < 2) else 0))
 
-            def adam(chunks):
-                tensors = (_lib.KgeAdamTensor * len(chunks))(*[_lib.KgeAdamTensor(*c) for c in chunks])
-                _lib.call("kge_adam_step", tensors, len(chunks), *hyper, reg,
-                          _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
+        # ---- multi-GPU plan: NVLink peer-memory exchange (csrc/kge_peer.cu) when it is set up and Adam is fused,
+        # otherwise one NCCL all-reduce of the workspace followed by the replicated optimizer
+        peer = ws['peer'] if (world > 1 and fused_adam and reg == 0.0) else None
+        regions = entity_slices = None
+        if peer is not None:
+            from .peer import exchange_regions
+            regions, entity_slices = exchange_regions(ws['param_floats'], model.nentity, model.entity_dim,
+                                                      model._exchange_slices(B, world, N))
+            layout = (tuple(regions), tuple((e[1] - ws['flat'].data_ptr()) // 4 for e in entries))
+            held = getattr(optimizer, '_kge_sliced_moments', None)
+            if held is not None and held != layout:
+                model._gather_moments(optimizer)             # ownership of the moments moves: make them whole first
+            if not getattr(optimizer, '_kge_hooked', False):
+                optimizer.register_state_dict_pre_hook(lambda opt: model._gather_moments(opt))
+                optimizer._kge_hooked = True
+            optimizer._kge_sliced_moments = layout
+            model._ws['exchange_regions'] = len(regions)
+        elif world > 1 and getattr(optimizer, '_kge_sliced_moments', None):
+            model._gather_moments(optimizer)
 
+        # ---- local kernels ---------------------------------------------------------------------------------------
+        _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
+        if weight is not None:
+            _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
+        # the row arrays passed down start at this rank's first row: [positive, negative] hold the shard only,
+        # weight / row losses are offset views of the whole-batch buffers
+        common = (_ptr(positive), _ptr(negative), _ptr(weight[row_begin:]) if weight is not None else None,
+                  _ptr(ws['wsum']) if weight is not None else None, B, 0, rows, N)
+        neg_row, pos_row = ws['neg_row'][row_begin:], ws['pos_row'][row_begin:]
+        wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), rows, N)
+        wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        pos_rows, neg_rows = ws['pos_row'], ws['neg_row']
+        if peer is None or len(regions) == 1:
+            _lib.call("kge_train_rows", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
+                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
+                      wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
+            if events is not None:
+                ev1.record()
+                events.append((ev0, ev1))
+            if xevents is not None:
+                xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                xev0.record()
             if peer is not None:
-                # NVLink peer-memory exchange (csrc/kge_peer.cu): reduce-scatter of the gradient workspaces, Adam on
-                # the slice this rank owns and broadcast of the new parameters, fused; no NCCL call in the step
-                if getattr(optimizer, '_kge_sliced_moments', None) is None:
-                    if not getattr(optimizer, '_kge_hooked', False):
-                        optimizer.register_state_dict_pre_hook(lambda opt: model._gather_moments(opt))
-                        optimizer._kge_hooked = True
-                flat_ptr = ws['flat'].data_ptr()
-                optimizer._kge_sliced_moments = (ws['param_floats'], [(e[1] - flat_ptr) // 4 for e in entries])
-                peer.reduce_adam(entries, hyper, ws['param_floats'], ws['param_floats'], 2 * B, ws['rows_sum'], err, st)
-                pos_rows, neg_rows = ws['rows_sum'][:B], ws['rows_sum'][B:]
-            elif sliced:
-                pE, gE_, mE, vE, _, stepE, _ = entries[0]
-                for work, lo, n in reductions:              # Adam on a slice as soon as its all-reduce has landed
-                    if work is not None:
-                        work.wait()
-                    adam([(pE + 4 * lo, gE_ + 4 * lo, mE + 4 * lo, vE + 4 * lo, n, stepE, 0)])
-                if tail_work is not None:
-                    tail_work.wait()
-                adam(entries[1:])
-            else:
-                adam(entries)
+                peer.reduce_adam(entries, hyper, ws['param_floats'], regions[0], ws['param_floats'], 2 * B,
+                                 ws['rows_sum'], err, st)
+            elif world > 1:
+                torch.distributed.all_reduce(ws['flat'])     # [dE|dR|dM|row losses] in one piece
+        else:
+            # sliced: row pass + counting sort, then per entity range the entity-major backward on this stream and, as
+            # soon as a range is final, its exchange (reduce-scatter + Adam + broadcast) on a second stream -- the
+            # NVLink traffic of slice k runs under the computation of slice k+1
+            pending = ctypes.c_int32(0)
+            _lib.call("kge_train_rows_begin", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
+                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
+                      wbytes, _ptr(err), ctypes.byref(pending), st)
+            main = torch.cuda.current_stream(dev)
+            side = model._ws.get('exchange_stream')
+            if side is None:
+                side = model._ws['exchange_stream'] = torch.cuda.Stream(dev)
+            side_ptr = ctypes.c_void_p(side.cuda_stream)
+            last = len(regions) - 1
+            for k, (region, (eb, ee)) in enumerate(zip(regions, entity_slices)):
+                if pending.value:
+                    _lib.call("kge_train_entity_pass", ctypes.byref(desc), mode_id, _ptr(wsp), rows, N, eb, ee, k,
+                              _ptr(ws['gE']), _ptr(gM), st)
+                if k == last:
+                    if events is not None:
+                        ev1.record()
+                        events.append((ev0, ev1))
+                    if xevents is not None:
+                        xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        xev0.record()
+                side.wait_stream(main)
+                peer.reduce_adam(entries, hyper, ws['param_floats'], region, ws['param_floats'],
+                                 2 * B if k == last else 0, ws['rows_sum'], err, side_ptr)
+            main.wait_stream(side)
+        if peer is not None:
+            pos_rows, neg_rows = ws['rows_sum'][:B], ws['rows_sum'][B:]
+
+        # ---- optimizer ---------------------------------------------------------------------------------------------
+        if fused_adam:
+            if peer is None:
+                tensors = (_lib.KgeAdamTensor * len(entries))(*[_lib.KgeAdamTensor(*c) for c in entries])
+                _lib.call("kge_adam_step", tensors, len(entries), *hyper, reg,
+                          _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
             reg_partials = ws['reg'] if reg != 0.0 else None
             for p, g in zip(params, grads):
                 p.grad = g if peer is None else None    # peer path: the workspace slots now carry parameter values

@@ -83,6 +83,8 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3):
             logs.append(KGEModel.train_step(m, opt, iter([as_torch(b)]), args))
         if path == "peer":
             assert m._ws.get('peer') not in (None, False), "peer exchange was not active"
+            if rank == 0:
+                print("peer backend:", m._ws['peer'].backend, "multicast" if m._ws['peer'].multicast else "unicast", flush=True)
             assert getattr(opt, '_kge_sliced_moments', None) is not None
         sd = opt.state_dict()                    # run.py:106 -- gathers the sliced moments on the peer path
         assert getattr(opt, '_kge_sliced_moments', None) is None
@@ -131,7 +133,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     check_case("RotatE", 2003, 7, 64, 12.0, 64, 32, 4, dev)            # single-read path sizes (pairs/entity small)
-    check_case("RotatE", 301, 5, 16, 6.0, 96, 64, 4, dev)              # many pairs per entity -> entity-major backward
+    check_case("RotatE", 301, 5, 16, 6.0, 512, 64, 4, dev)             # many pairs per entity -> entity-major backward,
+    #                                                                    exchange cut into regions overlapping it
     check_case("pRotatE", 517, 3, 10, 6.0, 33, 8, 3, dev)              # ragged: odd rows per rank, modulus, tensor tails
     check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev)
     check_eval(dev)

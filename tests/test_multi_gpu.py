@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_peer_exchange_and_sharded_eval_against_oracle():
+@pytest.mark.parametrize("backend", ["auto", "ipc"])     # auto = symmetric memory (+ NVSwitch multicast) when available
+def test_peer_exchange_and_sharded_eval_against_oracle(backend):
     n = min(torch.cuda.device_count(), 8)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KGE_PEER_BACKEND=backend))
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (res.stdout[-2000:], res.stderr[-4000:])
