@@ -84,9 +84,9 @@ class ClockSampler:
 
 
 def ncu_traffic(wl):
-    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1g.raw.csv:
+    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1j.raw.csv:
     dram__bytes_read.sum + dram__bytes_write.sum of row_kernel_split + entity_kernel); only for the captured workload."""
-    path = os.path.join(ROOT, "profiles", "prof_train_r1g.raw.csv")
+    path = os.path.join(ROOT, "profiles", "prof_train_r1j.raw.csv")
     if wl != "rotate_fb15k" or not os.path.exists(path):
         return None
     import csv
@@ -94,6 +94,8 @@ def ncu_traffic(wl):
     hdr, units = rows[0], rows[1]
     total = 0.0
     for r in rows[2:]:
+        if "row_kernel_split" not in r[0] and "entity_kernel" not in r[0]:
+            continue
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
@@ -356,7 +358,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rotate_fb15k", choices=list(WORKLOADS))
     ap.add_argument("--cpu-rows", type=int, default=0, help="positive rows per CPU step (0 = the full batch)")
-    ap.add_argument("--eval-queries", type=int, default=2048)
+    ap.add_argument("--eval-queries", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,13 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _on_device(t, dev, dtype):
+    """t as a contiguous `dtype` tensor on `dev` (no torch dispatch at all when it already is: the staged batches are)."""
+    if t.device == dev and t.dtype == dtype and t.is_contiguous():
+        return t
+    return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
+
 def _dist():
     """(rank, world_size) of the data-parallel group, (0, 1) when torch.distributed is not initialised."""
     import torch.distributed as dist
@@ -154,6 +161,15 @@ class KGEModel(nn.Module):
             self._ws['scalars_key'] = key
             self._ws['scalars'] = (self.gamma.item(), self.embedding_range.item())
         return self._ws['scalars']
+
+    def _own_descriptor(self):
+        """_descriptor() of the model's own tables, rebuilt only when a table moved (train_step's launch path)."""
+        E, R = self.entity_embedding, self.relation_embedding
+        key = (E.data_ptr(), R.data_ptr(), self.gamma._version, self.embedding_range._version)
+        held = self._ws.get('own_desc')
+        if held is None or held[0] != key:
+            held = self._ws['own_desc'] = (key, self._descriptor())
+        return held[1]
 
     def _descriptor(self, entity=None, relation=None, modulus=None, name=None):
         entity = self.entity_embedding if entity is None else entity
@@ -363,8 +379,13 @@ class KGEModel(nn.Module):
         self-adversarial / uniform loss -> positive scores -> weighted loss (+ L3) -> backward -> Adam.
         Returns the same log dict of python floats.
         '''
-        model.train()
-        optimizer.zero_grad()
+        if not model.training:
+            model.train()
+        if KGEModel._fusable_adam(model, optimizer):
+            for p in model._trainable():          # optimizer.zero_grad(set_to_none=True) for exactly these parameters
+                p.grad = None
+        else:
+            optimizer.zero_grad()
         out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
         model._prefetch_batch(train_iterator)     # next batch's next() + H2D overlap this step's kernels
         reg = float(getattr(args, 'regularization', 0.0))
@@ -456,12 +477,11 @@ class KGEModel(nn.Module):
             raise ValueError('mode %s not supported' % batch[3])
         # multi-GPU: this rank's positive rows only (the H2D copy and the kernels see rows [row_begin, row_end) of B)
         positive_sample, negative_sample, subsampling_weight, mode, B, row_begin = _shard_rows(batch)
-        positive = positive_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-        negative = negative_sample.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        positive = _on_device(positive_sample, dev, torch.int64)
+        negative = _on_device(negative_sample, dev, torch.int64)
         rows, N = negative.shape
         uni = bool(getattr(args, 'uni_weight', False))
-        weight = None if uni else subsampling_weight.to(device=dev, dtype=torch.float32,
-                                                        non_blocking=True).contiguous()
+        weight = None if uni else _on_device(subsampling_weight, dev, torch.float32)
         reg = float(getattr(args, 'regularization', 0.0))
         adversarial = bool(args.negative_adversarial_sampling)
         alpha = float(args.adversarial_temperature) if adversarial else 1.0
@@ -471,7 +491,7 @@ class KGEModel(nn.Module):
         ws = model._grad_workspace(B)
         err = model._err_flag()
         ws['out'] = model._ws['loss_out']
-        desc = model._descriptor()
+        desc = model._own_descriptor()
         events = model._ws.get('kernel_events')       # bench.py: CUDA events around the dominant kernel
         xevents = model._ws.get('exchange_events')    # bench.py: CUDA events around the exposed exchange + optimizer
         rank, world = _dist()
@@ -479,22 +499,24 @@ class KGEModel(nn.Module):
         grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
         gM = ws['gM'] if model.model_name == 'pRotatE' else None
 
-        # ---- optimizer bookkeeping (host only): torch.optim.Adam with run.py's defaults is fused, anything else steps itself
         fused_adam = KGEModel._fusable_adam(model, optimizer)
-        entries = hyper = None
-        if fused_adam:
+
+        def adam_entries():
+            """torch.optim.Adam bookkeeping (host only; state created lazily exactly like torch/optim/adam.py
+            _init_group).  Called after the local kernels are in flight so that it does not delay them."""
             group = optimizer.param_groups[0]
             hyper = (float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']))
             entries = []
             for i, (p, g) in enumerate(zip(params, grads)):
                 state = optimizer.state[p]
-                if len(state) == 0:             # same lazy state as torch/optim/adam.py _init_group
+                if len(state) == 0:
                     state['step'] = torch.tensor(0.0, dtype=torch.float32)
                     state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state['step'] += 1
                 entries.append((p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
                                 p.numel(), int(state['step'].item()), 1 if (reg != 0.0 and i < 2) else 0))
+            return entries, hyper
 
         # ---- multi-GPU plan: NVLink peer-memory exchange (csrc/kge_peer.cu) when it is set up and Adam is fused,
         # otherwise one NCCL all-reduce of the workspace followed by the replicated optimizer
@@ -504,7 +526,7 @@ class KGEModel(nn.Module):
             from .peer import exchange_regions
             regions, entity_slices = exchange_regions(ws['param_floats'], model.nentity, model.entity_dim,
                                                       model._exchange_slices(B, world, N))
-            layout = (tuple(regions), tuple((e[1] - ws['flat'].data_ptr()) // 4 for e in entries))
+            layout = (tuple(regions), tuple((g.data_ptr() - ws['flat'].data_ptr()) // 4 for g in grads))
             held = getattr(optimizer, '_kge_sliced_moments', None)
             if held is not None and held != layout:
                 model._gather_moments(optimizer)             # ownership of the moments moves: make them whole first
@@ -525,7 +547,11 @@ class KGEModel(nn.Module):
         common = (_ptr(positive), _ptr(negative), _ptr(weight[row_begin:]) if weight is not None else None,
                   _ptr(ws['wsum']) if weight is not None else None, B, 0, rows, N)
         neg_row, pos_row = ws['neg_row'][row_begin:], ws['pos_row'][row_begin:]
-        wbytes = _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), rows, N)
+        wkey = (rows, N, desc.entity_dim, desc.nentity)
+        held = model._ws.get('train_ws_bytes')
+        if held is None or held[0] != wkey:
+            held = model._ws['train_ws_bytes'] = (wkey, _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), rows, N))
+        wbytes = held[1]
         wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -541,6 +567,8 @@ class KGEModel(nn.Module):
             if xevents is not None:
                 xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 xev0.record()
+            if fused_adam:
+                entries, hyper = adam_entries()
             if peer is not None:
                 peer.reduce_adam(entries, hyper, ws['param_floats'], regions[0], ws['param_floats'], 2 * B,
                                  ws['rows_sum'], err, st)
@@ -554,6 +582,7 @@ class KGEModel(nn.Module):
             _lib.call("kge_train_rows_begin", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
                       _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
                       wbytes, _ptr(err), ctypes.byref(pending), st)
+            entries, hyper = adam_entries()
             main = torch.cuda.current_stream(dev)
             side = model._ws.get('exchange_stream')
             if side is None:
@@ -660,7 +689,11 @@ class KGEModel(nn.Module):
         gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not exact
         two_stage = self.model_name == 'RotatE' and not exact and self.entity_dim % 8 == 0
         nchunks = (queries_all.shape[0] + query_chunk - 1) // query_chunk
-        amb_counts = torch.zeros((max(nchunks, 1), 2), dtype=torch.int32, device=dev) if (gemm or two_stage) else None
+        # one int32 buffer [rank counts | per-chunk (ambiguous pairs, overflow flag)]: a single all-reduce and a single
+        # read-back per call
+        nq_all = queries_all.shape[0]
+        tally = torch.zeros(nq_all + 2 * max(nchunks, 1), dtype=torch.int32, device=dev)
+        amb_counts = tally[nq_all:].view(-1, 2) if (gemm or two_stage) else None
         if gemm:
             nE = self.entity_embedding.numel()
             ehi = self._buffer('gemm_ehi', nE, torch.float32, dev)
@@ -668,7 +701,7 @@ class KGEModel(nn.Module):
             enorm = self._buffer('gemm_enorm', nentity, torch.float32, dev)
             _lib.call("kge_eval_gemm_split", _ptr(self.entity_embedding), nentity, self.entity_dim, _ptr(ehi), _ptr(elo),
                       _ptr(enorm), st)
-        counts_all = torch.zeros(queries_all.shape[0], dtype=torch.int32, device=dev)
+        counts_all = tally[:nq_all]
         scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
         m = _lib.MODE_IDS[mode]
         for ci, lo in enumerate(range(0, queries_all.shape[0], query_chunk)):
@@ -712,12 +745,12 @@ class KGEModel(nn.Module):
                 ev1.record()
                 events.append((ev0, ev1))
         if world > 1:
-            torch.distributed.all_reduce(counts_all)
-            if amb_counts is not None:                       # an overflow on any rank re-runs the chunk everywhere
-                torch.distributed.all_reduce(amb_counts, op=torch.distributed.ReduceOp.MAX)
-        ranks = (counts_all.to(torch.int64) + 1).cpu().numpy()           # the call's one host sync
+            torch.distributed.all_reduce(tally)              # integer sums over the entity shards: bit-exact; an
+            #                                                  overflow flag on any rank re-runs the chunk everywhere
+        host = tally.cpu().numpy()                           # the call's one host sync
+        ranks = host[:nq_all].astype(np.int64) + 1
         if amb_counts is not None:
-            stats = amb_counts.cpu().numpy()
+            stats = host[nq_all:].reshape(-1, 2)
             self._ws['gemm_last_ambiguous' if gemm else 'two_stage_last_ambiguous'] = int(stats[:, 0].sum())
             for ci in np.nonzero(stats[:, 1])[0]:            # ambiguous list overflowed: exact kernel for that chunk
                 lo = int(ci) * query_chunk
