@@ -555,7 +555,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
   return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 64) +
-         2 * align256(rows * N * 4);
+         align256(((nentity + 1023) / 1024) * 4) + 2 * align256(rows * N * 4);
 }
 
 static SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity) {
@@ -567,6 +567,7 @@ static SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t 
   ws.cursor = ws.cnt + (nentity + 1);
   ws.queue = ws.cursor + nentity;                          // 16 queue counters (one per entity slice)
   wp += align256((size_t)(nentity + 1) * 4 + (size_t)nentity * 4 + 64);
+  ws.tile_tot = (int *)wp; wp += align256((size_t)((nentity + 1023) / 1024) * 4);
   ws.perm = (int *)wp;     wp += align256((size_t)rows * N * 4);
   ws.gsorted = (float *)wp;
   return ws;
@@ -648,8 +649,13 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         KGE_CUDA_OK(cudaGetLastError());
         if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
       }
-      scan_offsets_kernel<<<1, 1024, 0, st>>>(ws.cnt, ws.cursor, a.nentity);
-      KGE_CUDA_OK(cudaGetLastError());
+      {
+        const int tiles = (int)((a.nentity + 1023) / 1024);
+        scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+        KGE_CUDA_OK(cudaGetLastError());
+        scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+        KGE_CUDA_OK(cudaGetLastError());
+      }
       {
         const int64_t pairs = (int64_t)a.row_count * a.N;
         int g2 = (int)((pairs + 255) / 256);

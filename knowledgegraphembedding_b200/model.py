@@ -558,9 +558,10 @@ class KGEModel(nn.Module):
             ev0.record()
         pos_rows, neg_rows = ws['pos_row'], ws['neg_row']
         if peer is None or len(regions) == 1:
-            _lib.call("kge_train_rows", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
-                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
-                      wbytes, _ptr(err), st)          # negatives and the positive triple of every row, one call
+            if rows:                                  # (a rank can be left without rows by a short last batch)
+                _lib.call("kge_train_rows", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
+                          _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
+                          wbytes, _ptr(err), st)      # negatives and the positive triple of every row, one call
             if events is not None:
                 ev1.record()
                 events.append((ev0, ev1))
@@ -579,9 +580,10 @@ class KGEModel(nn.Module):
             # soon as a range is final, its exchange (reduce-scatter + Adam + broadcast) on a second stream -- the
             # NVLink traffic of slice k runs under the computation of slice k+1
             pending = ctypes.c_int32(0)
-            _lib.call("kge_train_rows_begin", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
-                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
-                      wbytes, _ptr(err), ctypes.byref(pending), st)
+            if rows:
+                _lib.call("kge_train_rows_begin", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
+                          _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
+                          wbytes, _ptr(err), ctypes.byref(pending), st)
             entries, hyper = adam_entries()
             main = torch.cuda.current_stream(dev)
             side = model._ws.get('exchange_stream')
@@ -787,27 +789,27 @@ class KGEModel(nn.Module):
         steps_per_mode = (len(test_triples) + batch - 1) // batch
         total_steps = 2 * steps_per_mode
         log_every = max(1, int(getattr(args, 'test_log_steps', 1000)))
-        logs = []
+        all_ranks = []
         step = 0
         with torch.no_grad():
             for mode in ('head-batch', 'tail-batch'):
-                ranks = model.filtered_ranks(test_triples, all_true_triples, mode)
+                all_ranks.append(model.filtered_ranks(test_triples, all_true_triples, mode))
                 for _ in range(steps_per_mode):          # same progress lines as model.py:420-423
                     if step % log_every == 0:
                         logging.info('Evaluating the model... (%d/%d)' % (step, total_steps))
                     step += 1
-                for ranking in ranks.tolist():
-                    logs.append({
-                        'MRR': 1.0 / ranking,
-                        'MR': float(ranking),
-                        'HITS@1': 1.0 if ranking <= 1 else 0.0,
-                        'HITS@3': 1.0 if ranking <= 3 else 0.0,
-                        'HITS@10': 1.0 if ranking <= 10 else 0.0,
-                    })
-        metrics = {}
-        for metric in logs[0].keys():
-            metrics[metric] = sum([log[metric] for log in logs]) / len(logs)
-        return metrics
+        # model.py:412-427: per-query MRR / MR / HITS@k appended head-batch first, then python's `sum(list) / len(logs)`.
+        # The same float64 values go through the same builtin sum() in the same order (bit-identical metrics, also
+        # under CPython >= 3.12's compensated float sum) without building 2*|test| dicts.
+        ranking = np.concatenate(all_ranks).astype(np.float64)
+        per_query = {
+            'MRR': 1.0 / ranking,
+            'MR': ranking,
+            'HITS@1': (ranking <= 1).astype(np.float64),
+            'HITS@3': (ranking <= 3).astype(np.float64),
+            'HITS@10': (ranking <= 10).astype(np.float64),
+        }
+        return {name: sum(values.tolist()) / len(ranking) for name, values in per_query.items()}
 
 
 class _NamedView:

@@ -60,14 +60,14 @@ def identical_on_all_ranks(t, what):
     assert all(int(g) == int(got[0]) for g in got), what + ": replicas differ"
 
 
-def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3):
+def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, adversarial=True, uni_weight=False):
     rank, world = dist.get_rank(), dist.get_world_size()
     st = O.init_tables(model, nentity, nrel, d, gamma, *FLAGS[model], seed=3)
     pool = batches(nentity, nrel, B, N, steps, seed=7)
-    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
-                                 uni_weight=False, regularization=0.0)
+    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=adversarial, adversarial_temperature=0.5,
+                                 uni_weight=uni_weight, regularization=0.0)
     ref = O.TrainState(model, st, gamma, d)
-    ref_logs = [O.train_step(ref, b, lr=lr, adversarial=True, alpha=1.0) for b in pool]
+    ref_logs = [O.train_step(ref, b, lr=lr, adversarial=adversarial, alpha=0.5, uni_weight=uni_weight) for b in pool]
 
     results = {}
     for path in ("peer", "nccl", "switch"):
@@ -136,7 +136,8 @@ def main():
     check_case("RotatE", 301, 5, 16, 6.0, 512, 64, 4, dev)             # many pairs per entity -> entity-major backward,
     #                                                                    exchange cut into regions overlapping it
     check_case("pRotatE", 517, 3, 10, 6.0, 33, 8, 3, dev)              # ragged: odd rows per rank, modulus, tensor tails
-    check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev)
+    check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev, adversarial=False, uni_weight=True)   # model.py:274-275,281-283
+    check_case("TransE", 200, 3, 8, 6.0, 1, 4, 2, dev)                 # fewer rows than ranks: some ranks hold no row
     check_eval(dev)
     dist.barrier()
     dist.destroy_process_group()
