@@ -187,6 +187,7 @@ class PeerExchange:
                   ctypes.c_void_p(err.data_ptr()), stream)
 
     def close(self):
+        """Unmap the peers' blocks and release the local one (the caller makes sure no exchange is in flight)."""
         self._symm = None
         lib = _lib.load()
         for p in self._mapped:
@@ -195,6 +196,12 @@ class PeerExchange:
         if self._local:
             lib.kge_peer_free(self._local)
             self._local = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                   # noqa: BLE001 -- interpreter shutdown: the driver reclaims the mappings
+            pass
 
 
 def gather_sliced_moments(tensors, offsets, regions, group=None):

@@ -118,6 +118,25 @@ assert _shard_rows(sh) is sh
 got = [None, None]
 dist.all_gather_object(got, (sh.row_begin, sh.positive.numpy(), sh.negative.numpy()))
 assert np.array_equal(np.concatenate([g[1] for g in got]), pos) and np.array_equal(np.concatenate([g[2] for g in got]), neg)
+# peer-exchange bookkeeping: moments that are current only on the owning rank become whole on every rank
+from knowledgegraphembedding_b200.peer import exchange_regions, gather_sliced_moments, region_slices
+nE, nR = 52 * 12, 5 * 8                                    # [dE | dR(pad to 4) | dM(4)] like KGEModel._grad_workspace
+param_floats = nE + nR + 4
+regions, _ = exchange_regions(param_floats, 52, 12, 3)
+offsets = [0, nE, nE + nR]
+truth = [torch.arange(n, dtype=torch.float32) + 1000 * k for k, n in enumerate((nE, nR, 1))]
+pairs = []
+for t, off in zip(truth, offsets):
+    m, v = torch.full_like(t, -1.0), torch.full_like(t, -2.0)
+    for region in regions:
+        lo4, hi4 = region_slices(region, world)[rank]
+        a, b_ = max(4 * lo4, off) - off, min(4 * hi4, off + t.numel()) - off
+        if a < b_:
+            m[a:b_] = t[a:b_]; v[a:b_] = 2 * t[a:b_]
+    pairs.append((m, v))
+gather_sliced_moments(pairs, offsets, regions)
+for (m, v), t in zip(pairs, truth):
+    assert torch.equal(m, t) and torch.equal(v, 2 * t)
 dist.destroy_process_group()
 print("ok")
 """
@@ -133,3 +152,44 @@ def test_world_size_2_gloo_data_path(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0 and out.strip().endswith("ok"), err[-2000:]
+
+
+def test_peer_exchange_region_arithmetic():
+    from knowledgegraphembedding_b200.peer import exchange_regions, region_slices
+    for nentity, De, nrel_floats, nslices in ((14951, 2000, 1345 * 1000, 1), (14951, 2000, 1345 * 1000, 3),
+                                              (301, 32, 5 * 16, 4), (7, 8, 12, 3), (10, 6, 8, 2)):
+        nE4 = (nentity * De + 3) // 4 * 4
+        param_floats = nE4 + (nrel_floats + 3) // 4 * 4 + 4
+        regions, entities = exchange_regions(param_floats, nentity, De, nslices)
+        assert regions[0][0] == 0 and regions[-1][1] == param_floats // 4
+        assert all(a[1] == b[0] for a, b in zip(regions, regions[1:]))          # regions tile the parameter part
+        assert entities[0][0] == 0 and entities[-1][1] == nentity
+        assert all(a[1] == b[0] for a, b in zip(entities, entities[1:]))
+        if De % 4:
+            assert len(regions) == 1                                           # rows are not float4 multiples: no slicing
+        for (lo4, hi4), (eb, ee) in list(zip(regions, entities))[:-1]:
+            assert hi4 * 4 == ee * De                                          # a region ends with its entity range
+        for world in (2, 3, 8):
+            for region in regions:
+                sl = region_slices(region, world)
+                assert sl[0][0] == region[0] and sl[-1][1] == region[1]
+                assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+                sizes = [b - a for a, b in sl]
+                assert max(sizes) - min(sizes) <= 1
+
+
+def test_peer_abi_argument_errors_without_a_gpu():
+    import ctypes
+    from knowledgegraphembedding_b200 import _lib
+    lib = _lib.load()
+    grp = _lib.KgePeerGroup(world=1, rank=0)
+    t = (_lib.KgeAdamTensor * 1)(_lib.KgeAdamTensor(16, 16, 16, 16, 4, 1, 0))
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    assert rc == _lib.ERR_INVALID and b"peer group of 1 ranks not supported" in lib.kge_last_error()
+    grp = _lib.KgePeerGroup(world=2, rank=0)
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 6, 0, 1, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    assert rc == _lib.ERR_INVALID and b"multiple of 4" in lib.kge_last_error()
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 1, 3, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    assert rc == _lib.ERR_INVALID and b"bad region / slice" in lib.kge_last_error()
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    assert rc == _lib.ERR_INVALID and b"peer 0 is not mapped" in lib.kge_last_error()
