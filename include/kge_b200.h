@@ -218,7 +218,7 @@ int kge_sample_negatives(const int64_t *triple_index, const int32_t *key_start, 
  * NVSwitch multicast mapping on top, from any symmetric-memory allocator.  The block holds the rank's gradient
  * workspace [dE | dR | dM | row losses] and a flag block of 2*KGE_PEER_MAX_RANKS uint32.
  * kge_peer_reduce_adam, called by every rank with the same epoch (1, 2, 3, ... per call) after its local train kernels:
- *   - waits until every rank has arrived (flags, bounded wait: err_flag := 2 on a 20 s timeout),
+ *   - waits until every rank has arrived (flags, bounded wait: err_flag := 2 after 60 s, or KGE_PEER_TIMEOUT_S),
  *   - one call exchanges the region [region_begin4, region_end4) of the parameter part of the workspace (float4 units; a
  *     step may be cut into several regions so that the exchange of a finished gradient slice overlaps the computation
  *     of the next one); for the groups [slice_begin4, slice_end4) of the region it owns the rank sums the G workspaces

@@ -25,7 +25,7 @@
 namespace kge {
 
 constexpr int PEER_MAX = KGE_PEER_MAX_RANKS;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kPeerTimeoutNsDefault = 60ull * 1000ull * 1000ull * 1000ull;   // KGE_PEER_TIMEOUT_S
 
 struct PeerTensor {
   float *p, *m, *v;
@@ -46,6 +46,7 @@ struct PeerArgs {
   float *rows_out;
   float w1, b2, w2, eps;
   int32_t *err;
+  unsigned long long timeout_ns; // bound on a barrier wait
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -104,7 +105,7 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs &a, int channel) {
     const uint32_t *f = a.flags[a.rank] + channel * PEER_MAX + threadIdx.x;
     const unsigned long long t0 = global_ns();
     while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
-      if (global_ns() - t0 > kPeerTimeoutNs) {             // a peer died or fell out of step: report, do not hang
+      if (global_ns() - t0 > a.timeout_ns) {             // a peer died or fell out of step: report, do not hang
         if (a.err) atomicExch(a.err, 2);
         break;
       }
@@ -331,6 +332,11 @@ extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch,
   a.row_off = row_offset; a.row_n = row_floats; a.rows_out = rows_out;
   a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
   a.err = err_flag;
+  {
+    const char *t = getenv("KGE_PEER_TIMEOUT_S");          // a rank that is later than this aborts the step (err_flag 2)
+    const double secs = t ? atof(t) : 0.0;
+    a.timeout_ns = secs > 0.0 ? (unsigned long long)(secs * 1e9) : kPeerTimeoutNsDefault;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = 148 * 12;
   // multicast use: bit 0 = reduce through the switch (multimem.ld_reduce), bit 1 = broadcast through it (multimem.st)

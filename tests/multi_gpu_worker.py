@@ -5,7 +5,8 @@ Checks on N >= 2 B200s, against the numpy oracle of the reference's single-devic
     Adam moments within 1e-5, replicas bit-identical on every rank, optimizer.state_dict() whole on every rank;
   * the same through the NCCL all-reduce path (KGE_NO_PEER behaviour), and that the two paths agree;
   * switching an optimizer from the peer path to the NCCL path mid-run (moments gathered automatically);
-  * entity-sharded filtered ranking: ranks equal the oracle's.
+  * entity-sharded filtered ranking: ranks equal the oracle's;
+  * at BASELINE.json's full RotatE FB15k shapes: peer path == NCCL path (tables, losses, gathered moments).
 """
 import os
 import sys
@@ -111,6 +112,42 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
         print(f"train ok: {model} nentity={nentity} d={d} B={B} N={N} world={world}", flush=True)
 
 
+def check_full_size(dev):
+    """BASELINE.json configs[2] shapes (RotatE FB15k: 14,951 x 2000 table, 1024 rows per rank, 256 negatives): the
+    peer-memory exchange and the NCCL all-reduce + replicated Adam give the same tables and losses (1e-5, infinity-norm
+    relative; Adam's sign-like first steps bounded by lr per step), replicas stay bit-identical."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    model, nentity, nrel, d, gamma, N, lr, steps = "RotatE", 14951, 1345, 1000, 24.0, 256, 1e-4, 3
+    B = 1024 * world
+    st = O.init_tables(model, nentity, nrel, d, gamma, True, False, seed=0)
+    pool = batches(nentity, nrel, B, N, steps, seed=11)
+    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
+                                 uni_weight=False, regularization=0.0)
+    out = {}
+    for path in ("peer", "nccl"):
+        m = build(model, nentity, nrel, d, gamma, st, dev)
+        if path == "nccl":
+            m._ws['peer'] = False
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+        logs = [KGEModel.train_step(m, opt, iter([as_torch(b)]), args) for b in pool]
+        sd = opt.state_dict()
+        for name in ("entity_embedding", "relation_embedding"):
+            identical_on_all_ranks(getattr(m, name), f"full/{path}/{name}")
+        out[path] = (logs, m.entity_embedding.detach().cpu().numpy(), m.relation_embedding.detach().cpu().numpy(),
+                     sd['state'][0]['exp_avg'].cpu().numpy(), sd['state'][0]['exp_avg_sq'].cpu().numpy())
+        del m, opt
+        torch.cuda.empty_cache()
+    for a, b in zip(out["peer"][0], out["nccl"][0]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]), (k, a[k], b[k])
+    for i, what in ((1, "E"), (2, "R")):
+        got, want = out["peer"][i], out["nccl"][i]
+        assert outlier_fraction(got, want, TOL) <= 1e-4 and np.max(np.abs(got - want)) <= 2.5 * lr * steps, what
+    assert relinf(out["peer"][3], out["nccl"][3]) <= 1e-4 and relinf(out["peer"][4], out["nccl"][4]) <= 1e-4
+    if rank == 0:
+        print(f"full-size ok: world={world}", flush=True)
+
+
 def check_eval(dev):
     model, nentity, nrel, d, gamma = "RotatE", 3001, 5, 32, 12.0
     st = O.init_tables(model, nentity, nrel, d, gamma, True, False, seed=4)
@@ -139,6 +176,7 @@ def main():
     check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev, adversarial=False, uni_weight=True)   # model.py:274-275,281-283
     check_case("TransE", 200, 3, 8, 6.0, 1, 4, 2, dev)                 # fewer rows than ranks: some ranks hold no row
     check_eval(dev)
+    check_full_size(dev)
     dist.barrier()
     dist.destroy_process_group()
     if int(os.environ.get("RANK", "0")) == 0:
