@@ -13,9 +13,10 @@ namespace kge {
 // F = fixed entity row (head for tail-batch/single, tail for head-batch), Rr = relation row.
 // Written with un-contractable primitives so that the train path, the eval path and the CPU oracle
 // agree bit-for-bit on q.
+// qd = position of the imaginary half inside q (d for a compact vector, a padded stride in the train kernel's smem)
 template <int MODEL, bool HEAD>
 __device__ __forceinline__ void build_q(const float *__restrict__ F, const float *__restrict__ Rr, int k, int d,
-                                        float scale, float *__restrict__ q) {
+                                        float scale, float *__restrict__ q, int qd) {
   if constexpr (MODEL == KGE_TRANSE) {
     float f = F[k], r = Rr[k];
     q[k] = HEAD ? fsub(r, f) : fadd(f, r);                 // model.py:168 (r - t) / :170 (h + r)
@@ -26,10 +27,10 @@ __device__ __forceinline__ void build_q(const float *__restrict__ F, const float
     float fr = F[k], fi = F[d + k], rr = Rr[k], ri = Rr[d + k];
     if (HEAD) {                                            // model.py:190-191
       q[k] = fadd(fmul(rr, fr), fmul(ri, fi));
-      q[d + k] = fsub(fmul(rr, fi), fmul(ri, fr));
+      q[qd + k] = fsub(fmul(rr, fi), fmul(ri, fr));
     } else {                                               // model.py:194-195
       q[k] = fsub(fmul(fr, rr), fmul(fi, ri));
-      q[d + k] = fadd(fmul(fr, ri), fmul(fi, rr));
+      q[qd + k] = fadd(fmul(fr, ri), fmul(fi, rr));
     }
   } else if constexpr (MODEL == KGE_ROTATE) {
     float fr = F[k], fi = F[d + k];
@@ -37,15 +38,20 @@ __device__ __forceinline__ void build_q(const float *__restrict__ F, const float
     sincos_rep(fdiv(Rr[k], scale), &s, &c);                // model.py:209-212
     if (HEAD) {                                            // model.py:215-216
       q[k] = fadd(fmul(c, fr), fmul(s, fi));
-      q[d + k] = fsub(fmul(c, fi), fmul(s, fr));
+      q[qd + k] = fsub(fmul(c, fi), fmul(s, fr));
     } else {                                               // model.py:220-221
       q[k] = fsub(fmul(fr, c), fmul(fi, s));
-      q[d + k] = fadd(fmul(fr, s), fmul(fi, c));
+      q[qd + k] = fadd(fmul(fr, s), fmul(fi, c));
     }
   } else {                                                 // pRotatE, model.py:236-243
     float pf = fdiv(F[k], scale), pr = fdiv(Rr[k], scale);
     q[k] = HEAD ? fsub(pr, pf) : fadd(pf, pr);
   }
+}
+template <int MODEL, bool HEAD>
+__device__ __forceinline__ void build_q(const float *__restrict__ F, const float *__restrict__ Rr, int k, int d,
+                                        float scale, float *__restrict__ q) {
+  build_q<MODEL, HEAD>(F, Rr, k, d, scale, q, d);
 }
 
 // ---- forward element op (train path: compiler may contract, approximate sqrt allowed) ------------------

@@ -625,50 +625,71 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
                        // several pairs (17 at FB15k shapes: 0.73 vs 0.96 ms) and loses when pairs are sparse
                        // (3.3 at YAGO3-10 shapes: 1.59 vs 0.99 ms)
                        ((int64_t)a.row_count * a.N >= 6 * a.nentity || getenv("KGE_FORCE_SPLIT"));
-    const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + ((a.do_loss || split) ? 2 * (size_t)a.N : 0) + 32);
+    // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
+    if (split) {
+      constexpr int Hs = CPLX ? 2 : 1;
+      const int chunks = (nunits + 31) / 32;                 // 128-float chunks per half row
+      const int nch = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16);
+      const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
+      const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
+      const size_t per_warp = 2 * hs * sizeof(float) + 16;
+      int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
+      if (Ws > 16) Ws = 16;
+      if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
+      if (Ws >= 4 && fixed_s + Ws * per_warp <= 227 * 1024) {
+        const size_t total = fixed_s + Ws * per_warp;
+        SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
+        KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
+#define KGE_SPLIT_LAUNCH(NCH)                                                                          \
+  do {                                                                                                 \
+    auto k = row_kernel_split<MODEL, HEAD, NCH>;                                                       \
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
+    k<<<grid, Ws * 32, total, st>>>(a, ws);                                                            \
+  } while (0)
+        if (nch == 4) KGE_SPLIT_LAUNCH(4);
+        else if (nch == 8) KGE_SPLIT_LAUNCH(8);
+        else {
+          if constexpr (CPLX) { set_error("row too wide"); return KGE_ERR_INVALID; }      // unreachable: nunits <= 256
+          else KGE_SPLIT_LAUNCH(16);
+        }
+#undef KGE_SPLIT_LAUNCH
+        KGE_CUDA_OK(cudaGetLastError());
+        if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
+        {
+          const int tiles = (int)((a.nentity + 1023) / 1024);
+          scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+          KGE_CUDA_OK(cudaGetLastError());
+          scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+          KGE_CUDA_OK(cudaGetLastError());
+        }
+        {
+          const int64_t pairs = (int64_t)a.row_count * a.N;
+          int g2 = (int)((pairs + 255) / 256);
+          if (g2 > 148 * 16) g2 = 148 * 16;
+          scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
+                                                   ws.G, ws.cursor, ws.perm, ws.gsorted);
+          KGE_CUDA_OK(cudaGetLastError());
+        }
+        if (a.defer_entity) {
+          if (a.entity_deferred) *a.entity_deferred = 1;
+          return KGE_OK;
+        }
+        return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
+      }
+    }
+    // ---- two-sweep TMA kernel ------------------------------------------------------------------------------
+    const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
     const size_t fixed = base + 16;
     int W = (int)((227 * 1024 - fixed) / (2 * rowbytes + 16));
     if (W > 16) W = 16;
     if (a.N < 4 * W) W = a.N >= 16 ? (a.N + 3) / 4 : 4;                // short candidate lists: fewer, busier warps
     if (W >= 4 && fixed + W * (2 * rowbytes + 16) <= 227 * 1024) {
       const size_t total = fixed + W * (2 * rowbytes + 16);
-      if (!split) {
-        auto k = row_kernel_tma<MODEL, HEAD>;
-        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-        k<<<grid, W * 32, total, st>>>(a);
-        KGE_CUDA_OK(cudaGetLastError());
-        return KGE_OK;
-      }
-      // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
-      SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
-      KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
-      {
-        auto k = row_kernel_split<MODEL, HEAD>;
-        KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-        k<<<grid, W * 32, total, st>>>(a, ws);
-        KGE_CUDA_OK(cudaGetLastError());
-        if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
-      }
-      {
-        const int tiles = (int)((a.nentity + 1023) / 1024);
-        scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
-        KGE_CUDA_OK(cudaGetLastError());
-        scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
-        KGE_CUDA_OK(cudaGetLastError());
-      }
-      {
-        const int64_t pairs = (int64_t)a.row_count * a.N;
-        int g2 = (int)((pairs + 255) / 256);
-        if (g2 > 148 * 16) g2 = 148 * 16;
-        scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
-                                                 ws.G, ws.cursor, ws.perm, ws.gsorted);
-        KGE_CUDA_OK(cudaGetLastError());
-      }
-      if (a.defer_entity) {
-        if (a.entity_deferred) *a.entity_deferred = 1;
-        return KGE_OK;
-      }
-      return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
+      auto k = row_kernel_tma<MODEL, HEAD>;
+      KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+      k<<<grid, W * 32, total, st>>>(a);
+      KGE_CUDA_OK(cudaGetLastError());
+      return KGE_OK;
     }
   }
   if (vec4) {

@@ -33,35 +33,40 @@ struct SplitWs {             // carved from the caller's workspace
   float *gsorted;            // [rows * N]  dL/ds of every pair in the same order
 };
 
-template <int MODEL, bool HEAD>
+// NCH = 128-float chunks per half row (4, 8 or 16): the halves of a row sit at a fixed padded stride DP = 128 * NCH
+// floats in every shared-memory slot and in q, the pad is zero (and stays zero: every element op maps (q, x) = (0, 0) to
+// value 0 and u 0), so the per-lane loops over the row have compile-time trip counts and immediate address offsets --
+// no bounds guards, no divergence bookkeeping (the guarded version spent 11 % of its instructions on them).
+template <int MODEL, bool HEAD, int NCH>
 __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, const SplitWs ws) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
   constexpr int V = 4;
-  constexpr int CH = CPLX ? 8 : 16;
+  constexpr int DP = 128 * NCH;                 // padded half length (floats)
+  constexpr int HS = H * DP;                    // slot size (floats)
   extern __shared__ __align__(128) float smem[];
-  const int Dq = a.De;
-  const int Dq4 = (Dq + 3) & ~3;
+  const int Dq4 = (a.De + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  // layout: [slots: nwarps x 2 x De | q | dq | sc[N] | gg[N] | scratch(32) | mbarriers], all derived from `smem`
-  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;
-  float *q = smem + (size_t)(2 * nwarps) * a.De;
-  float *dq = q + Dq4;
+  // layout: [slots: nwarps x 2 x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers], all derived from `smem`
+  float *slot0 = smem + (size_t)(2 * warp) * HS, *slot1 = slot0 + HS;
+  float *q = smem + (size_t)(2 * nwarps) * HS;
+  float *dq = q + HS;                           // compact [d | d]
   float *sc = dq + Dq4;                         // [N]
   float *gg = sc + a.N;                         // [N]
   float *scratch = gg + a.N;                    // [32]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32 + (a.N & 1) * 0);
-  const uint32_t rowbytes = (uint32_t)a.De * 4u;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
+  const uint32_t halfbytes = (uint32_t)a.d * 4u;
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
   uint32_t par0 = 0, par1 = 0;
 
-  const int nunits = a.d / V;
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const bool adversarial = a.do_loss && a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL;
 
+  for (int i = tid; i < (2 * nwarps + 1) * HS; i += blockDim.x) smem[i] = 0.f;       // slots and q: zero pads
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
   for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
@@ -76,64 +81,74 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
     const float *Rr = a.R + rid * a.Dr;
     const int64_t *cand = a.cand + b * a.cand_stride;
 
-    auto issue = [&](int s, int n) {
-      int64_t id = cand[n];
+    // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
+    // by shuffle: no dependent global load sits in front of a bulk copy
+    int64_t ids = 0;
+    int ids_base = -32;
+    auto issue = [&](int s, int j) {                       // j-th candidate of this warp
+      if (j >= ids_base + 32) {
+        ids_base = j;
+        const int n = warp + (j + lane) * nwarps;
+        ids = n < a.N ? cand[n] : 0;
+      }
+      int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
       if (lane == 0) {
         atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
         uint64_t *bar = s ? bar1 : bar0;
-        mbar_expect_tx(bar, rowbytes);
-        bulk_g2s(s ? slot1 : slot0, a.E + id * a.De, rowbytes, bar);
+        float *dst = s ? slot1 : slot0;
+        const float *src = a.E + id * a.De;
+        mbar_expect_tx(bar, halfbytes * H);
+        bulk_g2s(dst, src, halfbytes, bar);
+        if constexpr (CPLX) bulk_g2s(dst + DP, src + a.d, halfbytes, bar);
       }
     };
-    if (warp < a.N) issue(0, warp);
-    if (warp + nwarps < a.N) issue(1, warp + nwarps);
+    if (warp < a.N) issue(0, 0);
+    if (warp + nwarps < a.N) issue(1, 1);
 
     // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
     float *qout = ws.Qtab + (size_t)rl * a.De;
     for (int k = tid; k < a.d; k += blockDim.x) {
-      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q);
+      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q, DP);
       qout[k] = q[k];
       dq[k] = 0.f;
-      if (CPLX) { qout[a.d + k] = q[a.d + k]; dq[a.d + k] = 0.f; }
+      if (CPLX) { qout[a.d + k] = q[DP + k]; dq[a.d + k] = 0.f; }
     }
     __syncthreads();
 
     // ---- phase 1: per candidate, score (sweep 1) and deferred-normalised dL/dq (sweep 2) ------------------
-    float acc[CH][H][V];
+    float acc[NCH][H][V];
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
+    for (int i = 0; i < NCH; ++i)
 #pragma unroll
       for (int h = 0; h < H; ++h)
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
     float Mw = -INFINITY;                                  // running max of alpha * s over this warp's rows
+    const float *ql = q + lane * V;
     {
       int it = 0;
       for (int n = warp; n < a.N; n += nwarps, ++it) {
         const int s = it & 1;
         if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-        float *x = s ? slot1 : slot0;
+        float *xl = (s ? slot1 : slot0) + lane * V;
         // sweep 1: element values -> score; u = d(value)/dq is parked in the slot (in place of x)
         float part = 0.f;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int u = lane + 32 * i;
-          if (u < nunits) {
-            float x0[V], x1[V], q0[V], q1[V], u0[V], u1[V];
-            load_shared<V>(x0, x + u * V);
-            load_shared<V>(q0, q + u * V);
-            if constexpr (CPLX) {
-              load_shared<V>(x1, x + a.d + u * V);
-              load_shared<V>(q1, q + a.d + u * V);
-            }
+        for (int i = 0; i < NCH; ++i) {
+          float x0[V], x1[V], q0[V], q1[V], u0[V], u1[V];
+          load_shared<V>(x0, xl + i * 128);
+          load_shared<V>(q0, ql + i * 128);
+          if constexpr (CPLX) {
+            load_shared<V>(x1, xl + DP + i * 128);
+            load_shared<V>(q1, ql + DP + i * 128);
+          }
 #pragma unroll
-            for (int j = 0; j < V; ++j)
-              part += op_unit<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, u0[j], u1[j]);
-            if constexpr (!op_unit_is_x(OP)) {
-              *reinterpret_cast<float4 *>(x + u * V) = make_float4(u0[0], u0[1], u0[2], u0[3]);
-              if constexpr (CPLX) *reinterpret_cast<float4 *>(x + a.d + u * V) = make_float4(u1[0], u1[1], u1[2], u1[3]);
-            }
+          for (int j = 0; j < V; ++j)
+            part += op_unit<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, u0[j], u1[j]);
+          if constexpr (!op_unit_is_x(OP)) {
+            *reinterpret_cast<float4 *>(xl + i * 128) = make_float4(u0[0], u0[1], u0[2], u0[3]);
+            if constexpr (CPLX) *reinterpret_cast<float4 *>(xl + DP + i * 128) = make_float4(u1[0], u1[1], u1[2], u1[3]);
           }
         }
         float coef;
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
             if (z > Mw) {
               const float r = expf(Mw - z);                // 0 on the first row (Mw = -inf)
 #pragma unroll
-              for (int i = 0; i < CH; ++i)
+              for (int i = 0; i < NCH; ++i)
 #pragma unroll
                 for (int h = 0; h < H; ++h)
 #pragma unroll
@@ -165,23 +180,20 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
         }
         // sweep 2: acc += coef * u  (each lane re-reads exactly the slot words it wrote)
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int u = lane + 32 * i;
-          if (u < nunits) {
-            float u0[V], u1[V];
-            load_shared<V>(u0, x + u * V);
-            if constexpr (CPLX) load_shared<V>(u1, x + a.d + u * V);
+        for (int i = 0; i < NCH; ++i) {
+          float u0[V], u1[V];
+          load_shared<V>(u0, xl + i * 128);
+          if constexpr (CPLX) load_shared<V>(u1, xl + DP + i * 128);
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-              acc[i][0][j] = fmaf(coef, u0[j], acc[i][0][j]);
-              if constexpr (CPLX) acc[i][1][j] = fmaf(coef, u1[j], acc[i][1][j]);
-            }
+          for (int j = 0; j < V; ++j) {
+            acc[i][0][j] = fmaf(coef, u0[j], acc[i][0][j]);
+            if constexpr (CPLX) acc[i][1][j] = fmaf(coef, u1[j], acc[i][1][j]);
           }
         }
         // the slot was rewritten with generic stores: order them before the bulk engine's next write to it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (n + 2 * nwarps < a.N) issue(s, n + 2 * nwarps);
+        if (n + 2 * nwarps < a.N) issue(s, it + 2);
       }
     }
 
@@ -234,21 +246,22 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
 
     // ---- phase 4: fold the per-warp partial dL/dq.  Each warp parks its (scaled) accumulators in its own idle
     // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
+    {
+      float *pl = slot0 + lane * V;
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int u = lane + 32 * i;
-      if (u < nunits) {
-        *reinterpret_cast<float4 *>(slot0 + u * V) =
+      for (int i = 0; i < NCH; ++i) {
+        *reinterpret_cast<float4 *>(pl + i * 128) =
             make_float4(acc[i][0][0] * factor, acc[i][0][1] * factor, acc[i][0][2] * factor, acc[i][0][3] * factor);
         if constexpr (CPLX)
-          *reinterpret_cast<float4 *>(slot0 + a.d + u * V) =
+          *reinterpret_cast<float4 *>(pl + DP + i * 128) =
               make_float4(acc[i][1][0] * factor, acc[i][1][1] * factor, acc[i][1][2] * factor, acc[i][1][3] * factor);
       }
     }
     __syncthreads();
     for (int k = tid; k < a.De; k += blockDim.x) {
+      const int kk = (CPLX && k >= a.d) ? DP + (k - a.d) : k;           // compact index -> padded slot offset
       float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(2 * w) * a.De + k];
+      for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(2 * w) * HS + kk];
       dq[k] = t;
     }
     __syncthreads();
@@ -272,11 +285,11 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
       if ((uint64_t)ph >= (uint64_t)a.nentity) ph = 0;
       if ((uint64_t)pt >= (uint64_t)a.nentity) pt = 0;
       const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
-      for (int k = tid; k < a.d; k += blockDim.x) build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q);
+      for (int k = tid; k < a.d; k += blockDim.x) build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q, DP);
       __syncthreads();
       float part = 0.f;
       for (int k = tid; k < a.d; k += blockDim.x)
-        part += op_forward<OPS>(q[k], CPLX ? q[a.d + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale);
+        part += op_forward<OPS>(q[k], CPLX ? q[DP + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale);
       part = block_reduce(part, scratch, false);
       const float sp = finish_score<MODEL>(part, a.gamma, modulus);
       const float up = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
       float *gT = a.gE + pt * a.De;
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dq0 = 0.f, dq1 = 0.f, dx0 = 0.f, dx1 = 0.f;
-        op_backward<OPS>(q[k], CPLX ? q[a.d + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale, gop, dq0, dq1, dx0, dx1);
+        op_backward<OPS>(q[k], CPLX ? q[DP + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale, gop, dq0, dq1, dx0, dx1);
         dq[k] = dq0;
         red_add1(gT + k, dx0);
         if constexpr (CPLX) { dq[a.d + k] = dq1; red_add1(gT + a.d + k, dx1); }
@@ -305,7 +318,10 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
         if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staging stores vs the next row's bulk copies
+    __syncthreads();
+    // phase 4 parked folded accumulators in every warp's slot0 (pads included: zeros); the bulk engine overwrites
+    // [0, d) of each half, the pad keeps its zeros.  Order the generic stores before the next row's bulk copies.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
   }
 }
