@@ -640,11 +640,16 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         const size_t total = fixed_s + Ws * per_warp;
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
         KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
+        // persistent CTAs (one per SM: the slots take the whole shared memory), rows are dealt round-robin
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int sgrid = grid < sms ? grid : sms;
 #define KGE_SPLIT_LAUNCH(NCH)                                                                          \
   do {                                                                                                 \
     auto k = row_kernel_split<MODEL, HEAD, NCH>;                                                       \
     KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
-    k<<<grid, Ws * 32, total, st>>>(a, ws);                                                            \
+    k<<<sgrid, Ws * 32, total, st>>>(a, ws);                                                           \
   } while (0)
         if (nch == 4) KGE_SPLIT_LAUNCH(4);
         else if (nch == 8) KGE_SPLIT_LAUNCH(8);

@@ -63,12 +63,25 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const bool adversarial = a.do_loss && a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL;
 
-  for (int i = tid; i < (2 * nwarps + 1) * HS; i += blockDim.x) smem[i] = 0.f;       // slots and q: zero pads
+  {                                                        // zero the pads of every slot and of q (once per CTA)
+    const int padn = DP - a.d, nslots = 2 * nwarps + 1;
+    for (int i = tid; i < nslots * H * padn; i += blockDim.x) {
+      const int sl = i / (H * padn), r = i % (H * padn);
+      smem[(size_t)sl * HS + (r / padn) * DP + a.d + (r % padn)] = 0.f;
+    }
+  }
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
+  // The CTA is persistent (one per SM) and walks its rows; the first two candidates of the NEXT row are issued while the
+  // block-wide phases of the current row run (slot 1 right after the candidate loop, slot 0 as soon as the fold has
+  // consumed the parked accumulators), so every row but the first starts with its bulk copies already in flight.
+  int fs = 0;                                              // slot holding candidate 0 of the current row
+  bool primed = false;                                     // candidates 0 and 1 of the current row are already issued
+  int64_t ids = 0;                                         // candidate ids of this warp (see issue())
+  int ids_base = -32;
   for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
     const int64_t b = a.row_begin + rl;
     int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
@@ -80,12 +93,11 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
     const float *F = a.E + fid * a.De;
     const float *Rr = a.R + rid * a.Dr;
     const int64_t *cand = a.cand + b * a.cand_stride;
+    const bool has_next = rl + (int)gridDim.x < a.row_count;
 
     // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
     // by shuffle: no dependent global load sits in front of a bulk copy
-    int64_t ids = 0;
-    int ids_base = -32;
-    auto issue = [&](int s, int j) {                       // j-th candidate of this warp
+    auto issue = [&](int s, int j) {                       // j-th candidate of this warp (of the row `cand` points to)
       if (j >= ids_base + 32) {
         ids_base = j;
         const int n = warp + (j + lane) * nwarps;
@@ -103,8 +115,11 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
         if constexpr (CPLX) bulk_g2s(dst + DP, src + a.d, halfbytes, bar);
       }
     };
-    if (warp < a.N) issue(0, 0);
-    if (warp + nwarps < a.N) issue(1, 1);
+    if (!primed) {
+      ids_base = -32;
+      if (warp < a.N) issue(fs, 0);
+      if (warp + nwarps < a.N) issue(fs ^ 1, 1);
+    }
 
     // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
     float *qout = ws.Qtab + (size_t)rl * a.De;
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
     {
       int it = 0;
       for (int n = warp; n < a.N; n += nwarps, ++it) {
-        const int s = it & 1;
+        const int s = (it + fs) & 1;
         if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
         float *xl = (s ? slot1 : slot0) + lane * V;
         // sweep 1: element values -> score; u = d(value)/dq is parked in the slot (in place of x)
@@ -195,6 +210,11 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
         __syncwarp();
         if (n + 2 * nwarps < a.N) issue(s, it + 2);
       }
+    }
+    if (has_next) {                                        // next row, candidate 0 -> slot 1 (slot 0 parks the fold)
+      cand = a.cand + (b + gridDim.x) * a.cand_stride;
+      ids_base = -32;
+      if (warp < a.N) issue(1, 0);
     }
 
     // ---- phase 2: loss of this row (model.py:270-288), dL/ds to the workspace ---------------------------------
@@ -264,7 +284,9 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
       for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(2 * w) * HS + kk];
       dq[k] = t;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // parked / folded slot words vs the next bulk copy
     __syncthreads();
+    if (has_next && warp + nwarps < a.N) issue(0, 1);      // next row, candidate 1 -> slot 0
     // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
     float *gF = a.gE + fid * a.De;
     float *gRr = a.gR + rid * a.Dr;
@@ -318,11 +340,9 @@ __global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, cons
         if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
       }
     }
-    __syncthreads();
-    // phase 4 parked folded accumulators in every warp's slot0 (pads included: zeros); the bulk engine overwrites
-    // [0, d) of each half, the pad keeps its zeros.  Order the generic stores before the next row's bulk copies.
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                                        // q / dq / sc are rewritten by the next row
+    fs = 1;
+    primed = has_next;
   }
 }
 
