@@ -634,8 +634,10 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
       const size_t per_warp = 2 * hs * sizeof(float) + 16;
       int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
-      if (Ws > 16) Ws = 16;
+      const int wcap = split_max_threads(CPLX, nch) / 32;
+      if (Ws > wcap) Ws = wcap;
       if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
+      if (Ws > wcap) Ws = wcap;
       if (Ws >= 4 && fixed_s + Ws * per_warp <= 227 * 1024) {
         const size_t total = fixed_s + Ws * per_warp;
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);

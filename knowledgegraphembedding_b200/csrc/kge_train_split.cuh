@@ -37,8 +37,14 @@ struct SplitWs {             // carved from the caller's workspace
 // floats in every shared-memory slot and in q, the pad is zero (and stays zero: every element op maps (q, x) = (0, 0) to
 // value 0 and u 0), so the per-lane loops over the row have compile-time trip counts and immediate address offsets --
 // no bounds guards, no divergence bookkeeping (the guarded version spent 11 % of its instructions on them).
+// 8 KB slots (complex NCH = 8, real NCH = 16) leave room for 13 warps.  Registers stay capped at 128 per thread: one
+// SM sub-partition holds 4 of the 13 warps (4 x 32 x 128 = its 16 K registers).  Measured alternative: 12 warps with
+// 168 registers (no cap) is 1 % slower (0.705 vs 0.699 ms per cfg-3 launch) -- the extra warp is worth more than the ILP.
+__host__ __device__ constexpr int split_max_threads(bool cplx, int nch) { return (cplx ? 2 : 1) * nch >= 16 ? 416 : 512; }
+
 template <int MODEL, bool HEAD, int NCH>
-__global__ void __launch_bounds__(512, 1) row_kernel_split(const RowArgs a, const SplitWs ws) {
+__global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, HEAD)), NCH), 1)
+    row_kernel_split(const RowArgs a, const SplitWs ws) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
