@@ -591,7 +591,8 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   if (reserve_sms > 0 && sms > 2 * reserve_sms) sms -= reserve_sms;   // leave SMs for the concurrent NCCL kernel
   const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
   e.upp = two ? (nunits + 1) / 2 : nunits;
-  const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * e.upp * 16;
+  // slots have the kernel's compile-time half stride: CH chunks of 32 float4 units, CH = (complex ? 8 : 16) / parts
+  const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * ((CPLX ? 8 : 16) / (two ? 2 : 1)) * 32 * 16;
   int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
   const int wmax = two ? 20 : 12;
   if (We > wmax) We = wmax;

@@ -451,7 +451,10 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
   constexpr int CH = (CPLX ? 8 : 16) / S;
   extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int slot_floats = H * a.upp * V;
+  // a slot holds the H halves of a q segment at the compile-time stride HSTR; lanes past the segment (the pad) read
+  // whatever an earlier, longer segment left there -- their x registers are 0 and their accumulators are never stored
+  constexpr int HSTR = CH * 32 * V;
+  constexpr int slot_floats = H * HSTR;
   float *slot0 = smem + (size_t)(2 * warp) * slot_floats, *slot1 = slot0 + slot_floats;     // [slots | mbarriers]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * nwarps) * slot_floats);
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
@@ -461,8 +464,10 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const int64_t ntasks = a.ent_count * S;
 
+  for (int i = tid; i < 2 * nwarps * slot_floats; i += blockDim.x) smem[i] = 0.f;     // finite pads from the start
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
   float gmod = 0.f;
@@ -499,7 +504,7 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
         const float *src = a.Qtab + (size_t)row * a.De + ubeg * V;
         mbar_expect_tx(bar, segbytes * H);
         bulk_g2s(dst, src, segbytes, bar);
-        if constexpr (CPLX) bulk_g2s(dst + a.upp * V, src + a.d, segbytes, bar);
+        if constexpr (CPLX) bulk_g2s(dst + HSTR, src + a.d, segbytes, bar);
       }
     };
     issue(0, beg);
@@ -518,27 +523,28 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
       }
     }
 
+    const int nact = (ucnt + 31) >> 5;                    // chunks holding at least one unit: the same for every lane
     int it = 0;
     for (int i = beg; i < end; ++i, ++it) {
       const int s = it & 1;
       if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-      const float *q = s ? slot1 : slot0;
+      const float *ql = (s ? slot1 : slot0) + lane * V;
       const float g = s ? g1 : g0;
       const float go = dsum_of<MODEL>(g, modulus);
       float vsum = 0.f;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int u = lane + 32 * c;
-        if (u < ucnt) {
+        if (c < nact) {                                     // warp-uniform; no per-lane bounds guard (see HSTR)
           float q0[V], q1[V];
-          load_shared<V>(q0, q + u * V);
-          if constexpr (CPLX) load_shared<V>(q1, q + a.upp * V + u * V);
+          load_shared<V>(q0, ql + c * 128);
+          if constexpr (CPLX) load_shared<V>(q1, ql + HSTR + c * 128);
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             float dq0, dq1, ex0 = 0.f, ex1 = 0.f;
             float xb = 0.f;
             if constexpr (CPLX) xb = x1[c][j];
-            vsum += op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[c][j], xb, a.scale, go, dq0, dq1, ex0, ex1);
+            const float val = op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[c][j], xb, a.scale, go, dq0, dq1, ex0, ex1);
+            if constexpr (MODEL == KGE_PROTATE) vsum += (lane + 32 * c < ucnt) ? val : 0.f;   // pads must not count
             acc[c][0][j] += ex0;
             if constexpr (CPLX) acc[c][1][j] += ex1;
           }
