@@ -84,9 +84,9 @@ class ClockSampler:
 
 
 def ncu_traffic(wl):
-    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1k.raw.csv:
+    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1l.raw.csv:
     dram__bytes_read.sum + dram__bytes_write.sum of row_kernel_split + entity_kernel); only for the captured workload."""
-    path = os.path.join(ROOT, "profiles", "prof_train_r1k.raw.csv")
+    path = os.path.join(ROOT, "profiles", "prof_train_r1l.raw.csv")
     if wl != "rotate_fb15k" or not os.path.exists(path):
         return None
     import csv
