@@ -798,18 +798,23 @@ class KGEModel(nn.Module):
                     if step % log_every == 0:
                         logging.info('Evaluating the model... (%d/%d)' % (step, total_steps))
                     step += 1
-        # model.py:412-427: per-query MRR / MR / HITS@k appended head-batch first, then python's `sum(list) / len(logs)`.
-        # The same float64 values go through the same builtin sum() in the same order (bit-identical metrics, also
-        # under CPython >= 3.12's compensated float sum) without building 2*|test| dicts.
-        ranking = np.concatenate(all_ranks).astype(np.float64)
-        per_query = {
-            'MRR': 1.0 / ranking,
-            'MR': ranking,
-            'HITS@1': (ranking <= 1).astype(np.float64),
-            'HITS@3': (ranking <= 3).astype(np.float64),
-            'HITS@10': (ranking <= 10).astype(np.float64),
-        }
-        return {name: sum(values.tolist()) / len(ranking) for name, values in per_query.items()}
+        return metrics_from_ranks(np.concatenate(all_ranks))
+
+
+def metrics_from_ranks(ranks):
+    """model.py:412-427: per-query MRR / MR / HITS@1,3,10 (head-batch queries first, then tail-batch) averaged with
+    python's `sum(list) / len(logs)`.  The same float64 values go through the same builtin sum() in the same order, so
+    the metrics are bit-identical to the reference's loop over per-query dicts (also under CPython >= 3.12's compensated
+    float sum) without building 2*|test| dicts."""
+    ranking = np.asarray(ranks).astype(np.float64)
+    per_query = {
+        'MRR': 1.0 / ranking,
+        'MR': ranking,
+        'HITS@1': (ranking <= 1).astype(np.float64),
+        'HITS@3': (ranking <= 3).astype(np.float64),
+        'HITS@10': (ranking <= 10).astype(np.float64),
+    }
+    return {name: sum(values.tolist()) / len(ranking) for name, values in per_query.items()}
 
 
 class _NamedView:

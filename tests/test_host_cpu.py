@@ -193,3 +193,21 @@ def test_peer_abi_argument_errors_without_a_gpu():
     assert rc == _lib.ERR_INVALID and b"bad region / slice" in lib.kge_last_error()
     rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
     assert rc == _lib.ERR_INVALID and b"peer 0 is not mapped" in lib.kge_last_error()
+
+
+def test_metrics_from_ranks_bit_identical_to_the_reference_loop():
+    """model.py:412-427 builds one dict per query and averages with sum()/len(); ours must give the same bits."""
+    from knowledgegraphembedding_b200.model import metrics_from_ranks
+    rng = np.random.RandomState(3)
+    for n in (1, 7, 2 * 3134, 100001):
+        ranks = rng.randint(1, 15000, size=n)
+        ranks[rng.rand(n) < 0.2] = rng.randint(1, 12, size=int((rng.rand(n) < 0.2).sum()) or 1)[0]
+        logs = []
+        for ranking in ranks.tolist():                       # verbatim shape of the reference's loop body
+            logs.append({'MRR': 1.0 / ranking, 'MR': float(ranking), 'HITS@1': 1.0 if ranking <= 1 else 0.0,
+                         'HITS@3': 1.0 if ranking <= 3 else 0.0, 'HITS@10': 1.0 if ranking <= 10 else 0.0})
+        want = {m: sum([log[m] for log in logs]) / len(logs) for m in logs[0].keys()}
+        got = metrics_from_ranks(ranks)
+        assert list(got.keys()) == list(want.keys())
+        for m in want:
+            assert got[m] == want[m], (n, m, got[m], want[m])
