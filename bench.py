@@ -308,9 +308,10 @@ def run_gpu(args):
                    "adversarial": True, "double_entity_embedding": de,
                    "sharding": f"positive rows over {world} rank(s), tables replicated; eval: entity slices",
                    "l2_policy": "no flush: each step streams 0.6 GB of tables+moments+grads (> 126 MB L2)"},
-        # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan, scatter, entity_kernel per region,
-        # loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish per region
-        "clocks": clocks, "gpu_launches": (5 + nreg + (2 * nreg if px else 1)) * args.steps,
+        # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan_tiles, scan_apply, scatter_pairs,
+        # entity_kernel per region, loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish
+        # per region
+        "clocks": clocks, "gpu_launches": (6 + nreg + (2 * nreg if px else 1)) * args.steps,
         "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "last_loss": last.get("loss")},
         "roofline": roofline, "cpu_baseline": cpu,
