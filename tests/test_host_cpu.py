@@ -137,6 +137,57 @@ for t, off in zip(truth, offsets):
 gather_sliced_moments(pairs, offsets, regions)
 for (m, v), t in zip(pairs, truth):
     assert torch.equal(m, t) and torch.equal(v, 2 * t)
+# the peer-exchange scheme itself (csrc/kge_peer.cu), restated over gloo: every rank owns one slice per region of the
+# parameter part, sums the ranks' partial gradients of that slice in rank order, runs Adam there with its own moments,
+# and the new parameters are broadcast; after two steps every replica equals the oracle's full-batch train steps.
+def peer_step(params, moments, partial, step, lr, regions):
+    flat_g = torch.from_numpy(np.concatenate([partial[k].ravel() for k in ("entity_embedding", "relation_embedding")]))
+    gathered = [torch.zeros_like(flat_g) for _ in range(world)]
+    dist.all_gather(gathered, flat_g)                       # stand-in for the NVLink loads of the peers' workspaces
+    flat_p = np.concatenate([params[k].ravel() for k in ("entity_embedding", "relation_embedding")])
+    new_p = torch.from_numpy(flat_p.copy())
+    for region in regions:
+        lo4, hi4 = region_slices(region, world)[rank]
+        a, b_ = 4 * lo4, min(4 * hi4, flat_p.size)
+        if a < b_:
+            g = gathered[0].numpy()[a:b_].copy()
+            for r in range(1, world):
+                g = g + gathered[r].numpy()[a:b_]
+            O.adam_update(flat_p[a:b_], g, moments[0][a:b_], moments[1][a:b_], step, lr)
+            new_p[a:b_] = torch.from_numpy(flat_p[a:b_])
+        for r in range(world):                              # the owner's slice reaches every replica
+            l4, h4 = region_slices(region, world)[r]
+            x, y = 4 * l4, min(4 * h4, flat_p.size)
+            if x < y:
+                dist.broadcast(new_p[x:y], src=r)
+    nE_ = params["entity_embedding"].size
+    params["entity_embedding"][...] = new_p.numpy()[:nE_].reshape(params["entity_embedding"].shape)
+    params["relation_embedding"][...] = new_p.numpy()[nE_:].reshape(params["relation_embedding"].shape)
+
+nentity, nrel, d, gamma, B, N, lr = 60, 4, 8, 6.0, 10, 6, 1e-2
+st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=0)
+ref = O.TrainState("RotatE", st, gamma, d)
+mine = {k: v.copy() for k, v in st.items()}
+total = mine["entity_embedding"].size + mine["relation_embedding"].size          # both multiples of 4 here
+regions, _ = exchange_regions(total, nentity, 2 * d, 3)
+moments = (np.zeros(total, np.float32), np.zeros(total, np.float32))
+for step in (1, 2):
+    rng2 = np.random.RandomState(100 + step)
+    pos = np.stack([rng2.randint(nentity, size=B), rng2.randint(nrel, size=B), rng2.randint(nentity, size=B)], 1)
+    neg = rng2.randint(nentity, size=(B, N)); w = (rng2.rand(B) + 0.1).astype(np.float32)
+    O.train_step(ref, (pos, neg, w, "tail-batch"), lr=lr, adversarial=True, alpha=1.0)
+    neg_s = O.forward("RotatE", mine, (pos, neg), "tail-batch", gamma, d); pos_s = O.forward("RotatE", mine, pos, "single", gamma, d)
+    _, _, _, dneg, dpos = O.loss_and_dscore(neg_s, pos_s, w, True, 1.0, False)
+    b, e = shard_bounds(B, rank, world)
+    g1 = O.score_backward("RotatE", mine, (pos[b:e], neg[b:e]), "tail-batch", dneg[b:e], gamma, d)
+    g2 = O.score_backward("RotatE", mine, pos[b:e], "single", dpos[b:e], gamma, d)
+    partial = {k: (g1[k] + g2[k]).astype(np.float32) for k in g1}
+    peer_step(mine, moments, partial, step, lr, regions)
+for k in ("entity_embedding", "relation_embedding"):
+    assert np.max(np.abs(mine[k] - ref.state[k])) <= 1e-5 * np.max(np.abs(ref.state[k])) + 2 * lr * 1e-3, k
+    mineT = torch.from_numpy(mine[k].copy()); other = mineT.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mineT, other), "replicas differ"                      # bit-identical on every rank
 dist.destroy_process_group()
 print("ok")
 """
