@@ -284,6 +284,16 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # what bounds the distance-model ranking kernel: one square root per (query, entity, complex dimension) on the MUFU
+    # pipe, 16 results per clock and SM (DESIGN.md section 3.3 / SURVEY 8d); peak at the SM clock sampled under load
+    eval_roofline = None
+    if model in ("RotatE",) and eval_kernel_ms > 0:
+        sm_mhz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        sqrt_per_s = 2 * nq * nentity * d / (eval_kernel_ms * 1e-3) / world      # per GPU: its entity slice
+        peak_sqrt = 148 * 16 * sm_mhz * 1e6
+        eval_roofline = {"bound": "mufu (1 sqrt per query x entity x complex dim, 16/clk/SM)",
+                         "achieved": sqrt_per_s / 1e9, "peak": peak_sqrt / 1e9, "unit": "Gsqrt/s per GPU",
+                         "frac": sqrt_per_s / peak_sqrt}
     peak, peak_src = peaks()
     De, Dr = m.entity_dim, m.relation_dim
     a_bytes = train_bytes(B, N, De, Dr)
@@ -322,7 +332,7 @@ def run_gpu(args):
                  "what": "KGEModel.filtered_ranks end to end: host triples -> CSR filter -> H2D -> kernels -> host ranks",
                  "count_kernel_ms": eval_kernel_ms, "count_kernel_queries_per_sec": 2 * nq / (eval_kernel_ms * 1e-3),
                  "one_table_pass_per_query_equiv_gbs": 2 * nq * nentity * De * 4 / (eval_kernel_ms * 1e-3) / 1e9 / world,
-                 "sharding": f"entities/{world}", "filter_triples": len(all_true)},
+                 "sharding": f"entities/{world}", "filter_triples": len(all_true), "roofline": eval_roofline},
     }
     emit(line)
     if world > 1:
