@@ -3,10 +3,18 @@
 -g 24 -adv -de) train-step throughput in negative-sample scores/s, plus filtered-eval queries/s.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun by the driver)
-    python bench.py --impl reference ...                     (CPU oracle port of the reference path, host cores)
+    python bench.py --impl reference ...                     (the reference's CPU path on the host cores)
 
 One JSON line on stdout (rank 0).  A "step" is one full KGEModel.train_step: gather+score+loss+backward, dense
 Adam, loss read-back excluded for `value` (inputs resident in HBM) and included for `e2e` (host batches).
+
+Reference arm: the UNMODIFIED reference (baseline/_ref/codes, copied from /root/reference by __graft_entry__.build();
+git-ignored, travels with gpurun) through its own KGEModel.train_step on torch-CPU with every host thread, on a bounded
+sample of rows per step (the reference needs ~50 s for one full 1024-row step); when baseline/_ref is absent the C/OpenMP
+restatement oracle/kge_oracle.c is timed instead (kind "port").  The GPU arm also reports, as extras, the port's full-batch
+rate, the reference's own torch-CUDA eager path on the same B200 ("reference_cuda": the practical bar), an oracle parity
+check of the timed path, and the other BASELINE configs (TransE FB15k-237, ComplEx wn18rr incl. the tcgen05 eval, RotatE
+YAGO3-10).
 """
 import argparse
 import json
@@ -21,16 +29,28 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_CODES = os.path.join(ROOT, "baseline", "_ref", "codes")
 
 WORKLOADS = {
-    # name: (model, nentity, nrelation, d, gamma, B, N, lr, de, dr)
-    "rotate_fb15k": ("RotatE", 14951, 1345, 1000, 24.0, 1024, 256, 1e-4, True, False),
-    "transe_fb15k237": ("TransE", 14541, 237, 1000, 9.0, 1024, 256, 5e-5, False, False),
-    "rotate_yago310": ("RotatE", 123182, 37, 500, 24.0, 1024, 400, 2e-4, True, False),
-    "complex_wn18rr": ("ComplEx", 40943, 11, 500, 200.0, 512, 1024, 2e-3, True, True),
-    "distmult_fb15k": ("DistMult", 14951, 1345, 2000, 500.0, 1024, 256, 1e-3, False, False),
+    # name: (model, nentity, nrelation, d, gamma, B, N, lr, de, dr, regularization, filter triples)   [best_config.sh]
+    "rotate_fb15k": ("RotatE", 14951, 1345, 1000, 24.0, 1024, 256, 1e-4, True, False, 0.0, 483142),
+    "transe_fb15k237": ("TransE", 14541, 237, 1000, 9.0, 1024, 256, 5e-5, False, False, 0.0, 272115),
+    "rotate_yago310": ("RotatE", 123182, 37, 500, 24.0, 1024, 400, 2e-4, True, False, 0.0, 1079040),
+    "complex_wn18rr": ("ComplEx", 40943, 11, 500, 200.0, 512, 1024, 2e-3, True, True, 5e-6, 86835),
+    "distmult_fb15k": ("DistMult", 14951, 1345, 2000, 500.0, 1024, 256, 1e-3, False, False, 2e-6, 483142),
 }
 METRIC = "rotate_negative_sample_scores_per_sec_train_step"
+
+
+def make_config(wl, world):
+    """The `config` object of BOTH arms (same keys and values: the driver compares them)."""
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    return {"workload": wl, "score_function": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
+            "negative_sample_size": N, "batch_size_per_gpu": B, "positives_per_step": B * world, "gamma": gamma,
+            "adversarial": True, "double_entity_embedding": de, "double_relation_embedding": dr,
+            "regularization": reg, "learning_rate": lr,
+            "sharding": f"positive rows over {world} rank(s), tables replicated; eval: entity slices",
+            "l2_policy": "no flush: each step streams >= 0.5 GB of tables+moments (> 126 MB L2)"}
 
 
 def make_batches(nentity, nrel, B, N, count, seed):
@@ -45,8 +65,13 @@ def make_batches(nentity, nrel, B, N, count, seed):
 
 
 def train_bytes(B, N, De, Dr):
-    """Algorithmic bytes of the negative-pass row kernel (DESIGN.md section 5 / SURVEY 8d)."""
+    """Algorithmic bytes of score + loss + backward (DESIGN.md section 5 / SURVEY 8d `A_train`)."""
     return B * N * De * 4 * 2 + B * N * 8 + 2 * B * (De + Dr) * 4 + B * 28
+
+
+def adam_bytes(numel):
+    """SURVEY 8d `A_adam`: read p, g, m, v; write p, m, v."""
+    return 7 * numel * 4
 
 
 class ClockSampler:
@@ -84,259 +109,513 @@ class ClockSampler:
 
 
 def ncu_traffic(wl):
-    """DRAM bytes per train-path launch from the committed `ncu --set full` capture (profiles/prof_train_r1l.raw.csv:
-    dram__bytes_read.sum + dram__bytes_write.sum of row_kernel_split + entity_kernel); only for the captured workload."""
-    path = os.path.join(ROOT, "profiles", "prof_train_r1l.raw.csv")
-    if wl != "rotate_fb15k" or not os.path.exists(path):
-        return None
+    """DRAM bytes per train-path launch, NOT measured in this run: read from the committed `ncu --set full` capture of
+    the same command (dram__bytes_read.sum + dram__bytes_write.sum of the row kernel + entity kernel)."""
+    if wl != "rotate_fb15k":
+        return None, None
     import csv
-    rows = list(csv.reader(open(path)))
-    hdr, units = rows[0], rows[1]
-    total = 0.0
-    for r in rows[2:]:
-        if "row_kernel_split" not in r[0] and "entity_kernel" not in r[0]:
-            continue
-        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(name)
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-            total += float(r[i]) * scale
-    return total
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "prof_train_r*.raw.csv")), reverse=True):
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        total = 0.0
+        for r in rows[2:]:
+            if "row_kernel_split" not in r[0] and "entity_kernel" not in r[0]:
+                continue
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+                total += float(r[i]) * scale
+        if total:
+            return total, "not measured in this run: " + os.path.relpath(path, ROOT) + " (ncu --set full of this command)"
+    return None, None
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            p = json.load(f)
+            return p, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1418.0}, "fallback (B200_PROFILING.md)"
 
 
-# ---------------------------------------------------------------------------------------------- CPU oracle arm
-def cpu_train_sample(wl, rows, steps, warmup):
-    """The reference's train_step restated by the oracle on the host cores, on the first `rows` positive rows of
-    each batch at full width (N negatives, full tables incl. the dense Adam)."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------- reference helpers
+def load_reference():
+    """The unmodified reference modules from baseline/_ref/codes (None when the copy is absent)."""
+    if not os.path.exists(os.path.join(REF_CODES, "model.py")):
+        return None
+    import importlib.util
+    mods = {}
+    for name in ("dataloader", "model"):
+        spec = importlib.util.spec_from_file_location("kge_reference_" + name, os.path.join(REF_CODES, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        if name == "model":                       # model.py does `from dataloader import TestDataset`
+            sys.modules.setdefault("dataloader", mods["dataloader"])
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    return mods
+
+
+def reference_model(mods, wl, tables, device):
+    import torch
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    m = mods["model"].KGEModel(model_name=model, nentity=nentity, nrelation=nrel, hidden_dim=d, gamma=gamma,
+                               double_entity_embedding=de, double_relation_embedding=dr)
+    with torch.no_grad():
+        m.entity_embedding.copy_(torch.from_numpy(tables["entity_embedding"]))
+        m.relation_embedding.copy_(torch.from_numpy(tables["relation_embedding"]))
+    return m.to(device)
+
+
+def reference_args(wl, cuda):
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    return types.SimpleNamespace(cuda=cuda, negative_adversarial_sampling=True, adversarial_temperature=1.0,
+                                 uni_weight=False, regularization=reg, countries=False, regions=None,
+                                 test_batch_size=16, cpu_num=2, test_log_steps=100000, nentity=nentity, nrelation=nrel)
+
+
+def time_reference_train(mods, wl, rows, steps, warmup, cuda):
+    """The unmodified reference KGEModel.train_step (model.py:251-312) on `rows` positive rows x N negatives per step,
+    full tables, stock torch.optim.Adam; returns (scores/s, seconds per step)."""
+    import torch
+    from oracle import kge_oracle as O
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    tables = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
+    dev = torch.device("cuda") if cuda else torch.device("cpu")
+    m = reference_model(mods, wl, tables, dev)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+    args = reference_args(wl, cuda)
+    batches = [(torch.from_numpy(p), torch.from_numpy(n), torch.from_numpy(w), md)
+               for p, n, w, md in make_batches(nentity, nrel, rows, N, steps + warmup, seed=1)]
+    if cuda:
+        batches = [(p.pin_memory(), n.pin_memory(), w.pin_memory(), md) for p, n, w, md in batches]
+    it = iter(batches)
+    for _ in range(warmup):
+        mods["model"].KGEModel.train_step(m, opt, it, args)
+    if cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mods["model"].KGEModel.train_step(m, opt, it, args)        # (its .item() calls synchronise)
+    if cuda:
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return rows * N / dt, dt
+
+
+def time_reference_eval(mods, wl, all_true, test, cuda):
+    """The unmodified reference KGEModel.test_step (model.py:314-429: TestDataset + DataLoader + forward + argsort) on a
+    few test triples; returns (queries/s, seconds, metrics)."""
+    import torch
+    from oracle import kge_oracle as O
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    tables = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
+    m = reference_model(mods, wl, tables, torch.device("cuda") if cuda else torch.device("cpu"))
+    args = reference_args(wl, cuda)
+    t0 = time.perf_counter()
+    metrics = mods["model"].KGEModel.test_step(m, test, all_true, args)
+    if cuda:
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return 2 * len(test) / dt, dt, metrics
+
+
+def cpu_port_train(wl, rows, steps, warmup, threads):
+    """The reference's train_step restated by the C/OpenMP oracle on the host cores, on the first `rows` positive rows
+    of each batch at full width (N negatives, full tables incl. the dense Adam)."""
     from oracle import c_oracle as C
     from oracle import kge_oracle as O
-    model, nentity, nrel, d, gamma, B, N, lr, de, dr = WORKLOADS[wl]
-    rows = rows or B
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    C.set_num_threads(threads)
     st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
     batches = make_batches(nentity, nrel, rows, N, steps + warmup, seed=1)
-    if hasattr(C, "train_step"):
-        state = C.TrainState(model, st, gamma, d)
-        step_fn = lambda b: C.train_step(state, b, lr=lr, adversarial=True, alpha=1.0)     # noqa: E731
-        cores, kind = C.num_threads(), "port (oracle/kge_oracle.c, OpenMP)"
-    else:
-        state = O.TrainState(model, st, gamma, d)
-        step_fn = lambda b: O.train_step(state, b, lr=lr, adversarial=True, alpha=1.0)     # noqa: E731
-        cores, kind = 1, "port (oracle/kge_oracle.py, numpy)"
+    state = C.TrainState(model, st, gamma, d)
     for b in batches[:warmup]:
-        step_fn(b)
+        C.train_step(state, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
     t0 = time.perf_counter()
     for b in batches[warmup:]:
-        step_fn(b)
+        C.train_step(state, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return rows * N / dt, dt, cores, kind
+    return rows * N / dt, dt, C.num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
     wl = args.workload
-    model, nentity, nrel, d, gamma, B, N, lr, de, dr = WORKLOADS[wl]
-    rows = args.cpu_rows or B
-    value, dt, cores, kind = cpu_train_sample(wl, rows, args.steps, args.warmup)
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    cores = host_cores()
+    mods = None if args.reference_kind == "port" else load_reference()
+    if mods is not None:
+        import torch
+        torch.set_num_threads(cores)              # torchrun exports OMP_NUM_THREADS=1: use every host core explicitly
+        rows = args.cpu_rows or 16
+        value, dt = time_reference_train(mods, wl, rows, args.steps, args.warmup, cuda=False)
+        kind = "reference"
+        sample = (f"unmodified reference (baseline/_ref/codes/model.py KGEModel.train_step, torch {torch.__version__} CPU, "
+                  f"{torch.get_num_threads()} threads): {rows} of the {B * world} positive rows of a step x {N} negatives "
+                  f"at full width per step, full {nentity} x {d * (2 if de else 1)} tables, stock torch.optim.Adam included")
+        pv, pdt, pthreads = cpu_port_train(wl, B, 2, 1, cores)
+        extra = {"cpu_port": {"value": pv, "unit": "scores/s", "cores": pthreads, "kind": "port",
+                              "sample": f"oracle/kge_oracle.c (C/OpenMP restatement), full {B}-row batch, 2 steps after 1"}}
+    else:
+        rows = args.cpu_rows or B
+        value, dt, cores = cpu_port_train(wl, rows, args.steps, args.warmup, cores)
+        kind = "port"
+        sample = (f"oracle/kge_oracle.c (C/OpenMP restatement of model.py:251-312; baseline/_ref absent): {rows} of "
+                  f"{B * world} positive rows x {N} negatives per step at full width, full-table dense Adam included")
+        extra = {}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scores/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "score_function": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
-                   "negative_sample_size": N, "batch_size": B, "gamma": gamma, "adversarial": True,
-                   "sample_rows_per_step": rows},
-        "cpu_baseline": {"value": value, "unit": "scores/s", "cores": cores, "kind": "port",
-                         "sample": f"{rows} of {B} positive rows x {N} negatives per step at full width, "
-                                   f"full-table dense Adam included; {kind}"},
+        "config": make_config(wl, world),
+        "cpu_baseline": {"value": value, "unit": "scores/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        **extra,
     }
     emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    from knowledgegraphembedding_b200 import KGEModel
-    from oracle import kge_oracle as O          # only for the portable synthetic table initialiser + cpu_baseline
+def synthetic_triples(nentity, nrel, count, seed):
+    rng = np.random.RandomState(seed)
+    h, r, t = rng.randint(nentity, size=count), rng.randint(nrel, size=count), rng.randint(nentity, size=count)
+    keys = np.unique((h.astype(np.int64) * nrel + r) * nentity + t)
+    h, rem = np.divmod(keys, nrel * nentity)
+    r, t = np.divmod(rem, nentity)
+    return list(zip(h.tolist(), r.tolist(), t.tolist())), rng
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = args.workload
-    model, nentity, nrel, d, gamma, B, N, lr, de, dr = WORKLOADS[wl]
-    Bg = B * world                                   # weak scaling: every rank keeps B rows of the global batch
 
-    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
-    m = KGEModel(model, nentity, nrel, d, gamma, double_entity_embedding=de, double_relation_embedding=dr)
-    with torch.no_grad():
-        m.entity_embedding.copy_(torch.from_numpy(st["entity_embedding"]))
-        m.relation_embedding.copy_(torch.from_numpy(st["relation_embedding"]))
-    m = m.to(dev)
-    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
-    targs = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
-                                  uni_weight=False, regularization=0.0)
-    pool = make_batches(nentity, nrel, Bg, N, 8, seed=1)            # same batches on every rank
-    dev_pool = [(torch.from_numpy(p).to(dev), torch.from_numpy(n).to(dev), torch.from_numpy(w).to(dev), md)
-                for p, n, w, md in pool]
-    pin_pool = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(w).pin_memory(), md)
-                for p, n, w, md in pool]
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        torch = self.torch
         for i in range(warmup):
             fn(i)
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # max over ranks
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)               # max over ranks
         return float(ms.item())
 
-    # ---- value: inputs resident in HBM, no host read-back inside the timed region --------------------------------
-    m.train()
+    def build_model(self, wl):
+        torch = self.torch
+        from knowledgegraphembedding_b200 import KGEModel
+        from oracle import kge_oracle as O          # only the portable synthetic table initialiser
+        model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+        st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
+        m = KGEModel(model, nentity, nrel, d, gamma, double_entity_embedding=de, double_relation_embedding=dr)
+        with torch.no_grad():
+            m.entity_embedding.copy_(torch.from_numpy(st["entity_embedding"]))
+            m.relation_embedding.copy_(torch.from_numpy(st["relation_embedding"]))
+        m = m.to(self.dev)
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+        targs = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
+                                      uni_weight=False, regularization=reg)
+        return m, opt, targs, st
 
-    def step_device(i):
-        m.train_step_async(opt, dev_pool[i % len(dev_pool)], targs)
+    def train(self, wl, steps, warmup, e2e=True):
+        """value (device-resident inputs), kernel timing, e2e (public KGEModel.train_step on pinned host batches)."""
+        torch = self.torch
+        from knowledgegraphembedding_b200 import KGEModel
+        model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+        world, dev = self.world, self.dev
+        Bg = B * world                                   # weak scaling: every rank keeps B rows of the global batch
+        m, opt, targs, _ = self.build_model(wl)
+        pool = make_batches(nentity, nrel, Bg, N, min(steps + warmup, 32), seed=1)            # same batches on every rank
+        dev_pool = [(torch.from_numpy(p).to(dev), torch.from_numpy(n).to(dev), torch.from_numpy(w).to(dev), md)
+                    for p, n, w, md in pool]
+        m.train()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    m._ws['kernel_events'] = None
-    for i in range(args.warmup):
-        step_device(i)
-    m._ws['kernel_events'] = events = []
-    m._ws['exchange_events'] = xevents = []
-    ms_total = timed(step_device, args.steps, 0)
-    m._ws['kernel_events'] = m._ws['exchange_events'] = None
-    exchange_ms = float(np.mean([a.elapsed_time(b) for a, b in xevents])) if xevents else None
-    px = m._ws.get('peer')
-    nreg = int(m._ws.get('exchange_regions', 1)) if px else 1
-    exchange_path = ("nvlink_peer_memory/%s%s (kge_peer_reduce_adam)" % (px.backend, "+nvswitch_multicast" if px.multicast else "")
-                     if px else ("nccl_allreduce + kge_adam_step" if world > 1 else "kge_adam_step"))
-    clocks = sampler.stop()
-    row_ms = float(np.mean([a.elapsed_time(b) for a, b in events])) if events else None
-    ms_per_step = ms_total / args.steps
-    value = Bg * N / (ms_per_step * 1e-3)
+        def step_device(i):
+            m.train_step_async(opt, dev_pool[i % len(dev_pool)], targs)
 
-    # ---- e2e: the public call (KGEModel.train_step) on pinned host batches, loss read back every step ----------
-    it_state = {"i": 0}
+        m._ws['kernel_events'] = None
+        for i in range(warmup):
+            step_device(i)
+        m._ws['kernel_events'] = events = []
+        m._ws['exchange_events'] = xevents = []
+        ms_total = self.timed(step_device, steps, 0)
+        m._ws['kernel_events'] = m._ws['exchange_events'] = None
+        out = {"ms_per_step": ms_total / steps, "value": Bg * N / (ms_total / steps * 1e-3),
+               "row_ms": float(np.mean([a.elapsed_time(b) for a, b in events])) if events else None,
+               "exchange_ms": float(np.mean([a.elapsed_time(b) for a, b in xevents])) if xevents else None,
+               "fused_entity_adam": m.entity_embedding.grad is None, "model": m, "opt": opt, "targs": targs}
+        px = m._ws.get('peer')
+        out["peer"] = px
+        out["nreg"] = int(m._ws.get('exchange_regions', 1)) if px else 1
+        if e2e:
+            pin_pool = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory(),
+                         torch.from_numpy(w).pin_memory(), md) for p, n, w, md in pool]
+            it_state = {"i": 0}
 
-    class HostIterator:
-        def __next__(self):
-            b = pin_pool[it_state["i"] % len(pin_pool)]
-            it_state["i"] += 1
-            return b
+            class HostIterator:
+                def __next__(self):
+                    b = pin_pool[it_state["i"] % len(pin_pool)]
+                    it_state["i"] += 1
+                    return b
 
-    host_it = HostIterator()
-    last = {}
+            host_it, last = HostIterator(), {}
 
-    def step_host(i):
-        last.update(KGEModel.train_step(m, opt, host_it, targs))
+            def step_host(i):
+                last.update(KGEModel.train_step(m, opt, host_it, targs))
 
-    ms_e2e = timed(step_host, args.steps, args.warmup) / args.steps
-    e2e_value = Bg * N / (ms_e2e * 1e-3)
-    h2d = world * (B * 3 * 8 + B * N * 8 + Bg * 4)      # every rank copies its own rows (+ the whole weight vector)
-    d2h = 8 * 4
+            out["ms_e2e"] = self.timed(step_host, steps, warmup) / steps
+            out["e2e_value"] = Bg * N / (out["ms_e2e"] * 1e-3)
+            out["last_loss"] = last.get("loss")
+            # every rank copies its own rows (+ the whole weight vector); one 32-byte loss read-back
+            out["h2d"] = world * (B * 3 * 8 + B * N * 8 + Bg * 4)
+            out["d2h"] = 8 * 4
+        return out
 
-    # ---- filtered evaluation throughput (entity-sharded over the ranks) ------------------------------------------
-    rng = np.random.RandomState(2)
-    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(nentity)))
-                       for _ in range(483142 if wl == "rotate_fb15k" else 200000)})
-    nq = args.eval_queries
-    test = [all_true[i] for i in rng.choice(len(all_true), nq, replace=False)]
-    for mode in ("head-batch", "tail-batch"):                      # warm-up: filter index, workspaces, clocks
-        m.filtered_ranks(test, all_true, mode)
-    reps = 3
-    m._ws['eval_events'] = eval_events = []
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    def parity(self, wl, steps=2):
+        """The timed path against the C oracle on the same seeded full batches (losses 1e-5, tables outlier bound);
+        raises if it fails: a fast kernel whose results differ from the reference's is not done."""
+        torch = self.torch
+        from knowledgegraphembedding_b200 import KGEModel
+        from oracle import c_oracle as C
+        model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+        m, opt, targs, st = self.build_model(wl)
+        ts = C.TrainState(model, st, gamma, d)
+        worst = 0.0
+        for b in make_batches(nentity, nrel, B, N, steps, seed=11):
+            log = KGEModel.train_step(m, opt, iter([tuple(torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+                                                          for x in b)]), targs)
+            ref = C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
+            worst = max(worst, max(abs(log[k] - ref[k]) / abs(ref[k]) for k in ref))
+        E = m.entity_embedding.detach().cpu().numpy()
+        bad = float(np.mean(np.abs(E - ts.state["entity_embedding"]) > 1e-5 * np.abs(ts.state["entity_embedding"]).max()))
+        ok = worst <= 1e-5 and bad < 1e-4
+        res = {"against": "oracle/kge_oracle.c full-batch train_step (pinned to the reference's goldens)", "steps": steps,
+               "max_rel_loss_err": worst, "entity_table_outlier_fraction": bad, "tolerance": 1e-5, "ok": bool(ok)}
+        if not ok:
+            raise SystemExit("bench.py parity check failed: " + json.dumps(res))
+        return res
+
+    def eval(self, wl, m, nq, reps=3):
+        """KGEModel.filtered_ranks end to end (host triples in, host ranks out), entity-sharded over the ranks: once cold
+        (filter index built from the python list + uploads) and warm (index cached, as across valid/test of one run)."""
+        model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, ntrue = WORKLOADS[wl]
+        all_true, rng = synthetic_triples(nentity, nrel, ntrue, seed=2)
+        test = [all_true[i] for i in rng.choice(len(all_true), nq, replace=False)]
+        self.barrier()
+        t0 = time.perf_counter()
         for mode in ("head-batch", "tail-batch"):
-            m.filtered_ranks(test, all_true, mode)                 # host triples in, host ranks out
-    barrier()
-    eval_s = (time.perf_counter() - t0) / reps
-    m._ws['eval_events'] = None
-    eval_qps = 2 * nq / eval_s
-    eval_kernel_ms = sum(a.elapsed_time(b) for a, b in eval_events) / reps
+            m.filtered_ranks(test, all_true, mode)
+        self.barrier()
+        cold_s = time.perf_counter() - t0
+        m._ws['eval_events'] = eval_events = []
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for mode in ("head-batch", "tail-batch"):
+                m.filtered_ranks(test, all_true, mode)                 # host triples in, host ranks out
+        self.barrier()
+        eval_s = (time.perf_counter() - t0) / reps
+        m._ws['eval_events'] = None
+        kernel_ms = sum(a.elapsed_time(b) for a, b in eval_events) / reps
+        return {"metric": "filtered_eval_queries_per_sec", "value": 2 * nq / eval_s, "queries": 2 * nq, "seconds": eval_s,
+                "what": "KGEModel.filtered_ranks end to end, warm: host triples -> H2D -> filter lookup + count kernels -> "
+                        "host ranks; the filter index of all_true_triples is cached from the cold call",
+                "cold": {"value": 2 * nq / cold_s, "seconds": cold_s,
+                         "what": "first call: builds the filter index from the python list of all true triples, uploads it"},
+                "count_kernel_ms": kernel_ms, "count_kernel_queries_per_sec": 2 * nq / (kernel_ms * 1e-3) if kernel_ms else None,
+                "sharding": f"entities/{self.world}", "filter_triples": len(all_true)}, all_true, test
+
+
+def run_gpu(args):
+    b = Bench(args)
+    torch, world, rank, dev = b.torch, b.world, b.rank, b.dev
+    wl = args.workload
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
+    pk, peak_src = peaks()
+    sampler = ClockSampler(b.local)
+    sampler.start()
+    tr = b.train(wl, args.steps, args.warmup)
+    clocks = sampler.stop()
+    m = tr["model"]
+    De, Dr = m.entity_dim, m.relation_dim
+    ev, all_true, test = b.eval(wl, m, args.eval_queries)
+
+    # ---- the other BASELINE configs (cfg 2, 4, 5), shorter runs ------------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        del tr["model"], tr["opt"]
+        m = None
+        torch.cuda.empty_cache()
+        for name in ("transe_fb15k237", "complex_wn18rr", "rotate_yago310"):
+            if name == wl:
+                continue
+            w = WORKLOADS[name]
+            t2 = b.train(name, 10, 3)
+            m2 = t2["model"]
+            a_tr = train_bytes(w[5], w[6], m2.entity_dim, m2.relation_dim)
+            a_ad = adam_bytes(m2.entity_embedding.numel() + m2.relation_embedding.numel())
+            e2, _, _ = b.eval(name, m2, 2048 if name != "rotate_yago310" else 1024, reps=2)
+            entry = {"config": make_config(name, world), "value": t2["value"], "unit": "scores/s",
+                     "ms_per_step": t2["ms_per_step"], "e2e": {"value": t2["e2e_value"], "ms_per_step": t2["ms_e2e"]},
+                     "fused_entity_adam": t2["fused_entity_adam"],
+                     "full_step_roofline": {"bound": "hbm", "algorithmic_bytes": a_tr + a_ad,
+                                            "achieved": (a_tr + a_ad) / (t2["ms_per_step"] * 1e-3) / 1e9,
+                                            "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": (a_tr + a_ad) / (t2["ms_per_step"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                     "eval": e2}
+            if name == "complex_wn18rr" and e2["count_kernel_ms"]:
+                # tcgen05 path: 3 TF32 MMAs (hi*hi + hi*lo + lo*hi) per product => 3 x 2 x Q x nentity x 2d tensor flops
+                flops = 3 * 2.0 * e2["queries"] * w[1] * m2.entity_dim / world
+                tf = flops / (e2["count_kernel_ms"] * 1e-3) / 1e12
+                tpeak = pk.get("bf16_tflops_sustained", 1418.0) / 2.0
+                entry["eval"]["roofline"] = {"bound": "tensor", "kernel": "gemm_count_kernel (tcgen05.mma kind::tf32, 3xTF32 split)",
+                                             "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                             "peak_source": peak_src + " bf16_tflops_sustained / 2 (TF32 rate)",
+                                             "note": "kernel time includes the exact re-score of the ambiguous band"}
+            extras[name] = entry
+            del t2, m2
+            torch.cuda.empty_cache()
+
+    parity = b.parity(wl) if (world == 1 and not args.no_parity) else None
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            b.dist.destroy_process_group()
         return
-    # what bounds the distance-model ranking kernel: one square root per (query, entity, complex dimension) on the MUFU
-    # pipe, 16 results per clock and SM (DESIGN.md section 3.3 / SURVEY 8d); peak at the SM clock sampled under load
-    eval_roofline = None
-    if model in ("RotatE",) and eval_kernel_ms > 0:
-        sm_mhz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-        sqrt_per_s = 2 * nq * nentity * d / (eval_kernel_ms * 1e-3) / world      # per GPU: its entity slice
+
+    # ---- rooflines -----------------------------------------------------------------------------------------------------
+    sm_mhz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    if model == "RotatE" and ev["count_kernel_ms"]:
+        # what bounds the distance-model ranking kernel: one square root per (query, entity, complex dimension) on the
+        # MUFU pipe, 16 results per clock and SM (DESIGN.md section 3.3 / SURVEY 8d); peak at the sampled SM clock
+        sqrt_per_s = ev["queries"] * nentity * d / (ev["count_kernel_ms"] * 1e-3) / world      # per GPU: its entity slice
         peak_sqrt = 148 * 16 * sm_mhz * 1e6
-        eval_roofline = {"bound": "mufu (1 sqrt per query x entity x complex dim, 16/clk/SM)",
-                         "achieved": sqrt_per_s / 1e9, "peak": peak_sqrt / 1e9, "unit": "Gsqrt/s per GPU",
-                         "frac": sqrt_per_s / peak_sqrt}
-    peak, peak_src = peaks()
-    De, Dr = m.entity_dim, m.relation_dim
-    a_bytes = train_bytes(B, N, De, Dr)
+        ev["roofline"] = {"bound": "mufu (1 sqrt per query x entity x complex dim, 16/clk/SM)",
+                          "achieved": sqrt_per_s / 1e9, "peak": peak_sqrt / 1e9, "unit": "Gsqrt/s per GPU",
+                          "frac": sqrt_per_s / peak_sqrt}
+    a_train = train_bytes(B, N, De, Dr)
+    a_adam_e = adam_bytes(nentity * De)
+    fused = tr["fused_entity_adam"]
     roofline = None
-    if row_ms:
-        ach = a_bytes / (row_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "kge_train_rows: row_kernel_split + counting sort + entity_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": ncu_traffic(wl), "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes,
-                    "avg_launch_ms": row_ms}
+    if tr["row_ms"]:
+        a_bytes = a_train + (a_adam_e if fused else 0)
+        ach = a_bytes / (tr["row_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(wl)
+        roofline = {"bound": "hbm",
+                    "kernel": ("kge_train_rows_adam: row_kernel_split + counting sort + entity_kernel with the entity table's "
+                               "Adam update fused in" if fused else
+                               "kge_train_rows: row_kernel_split + counting sort + entity_kernel"),
+                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " hbm_gbs",
+                    "algorithmic_bytes_per_launch": a_bytes,
+                    "algorithmic_bytes_what": "A_train (gather + scatter formulation of the reference, SURVEY 8d)"
+                                              + (" + A_adam of the entity table (7 streams)" if fused else ""),
+                    "avg_launch_ms": tr["row_ms"]}
+        l2 = os.path.join(ROOT, "profiles", "l2_gather_r2.json")
+        if os.path.exists(l2):
+            try:
+                rows = [json.loads(x) for x in open(l2) if x.strip().startswith("{")]
+                best = max(r["gather_gbs_depth2"] for r in rows if "fits_L2" in r["table"])
+                roofline["l2_gather"] = {"what": "the kernel does not stream from HBM: the 120 MB table is L2-resident; measured "
+                                                 "L2->SM ceiling for this access pattern (tools/l2_gather_bench.cu, 8 KB rows, "
+                                                 "cp.async.bulk, random ids), not measured in this run",
+                                         "peak_gbs": best, "gather_bytes_per_launch": B * N * De * 4}
+            except Exception:
+                pass
+    cores = host_cores()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, kind = cpu_train_sample(wl, args.cpu_rows, 3, 1)
-        cpu = {"value": v, "unit": "scores/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_rows or B} of {B} positive rows x {N} negatives per step at full width, full-table "
-                         f"dense Adam included, 3 steps after 1 warm-up; {kind}"}
+        mods = load_reference()
+        if mods is not None:
+            torch.set_num_threads(cores)
+            rows = args.cpu_rows or 16
+            v, dt = time_reference_train(mods, wl, rows, 3, 1, cuda=False)
+            cpu = {"value": v, "unit": "scores/s", "cores": cores, "kind": "reference",
+                   "sample": f"unmodified reference (baseline/_ref/codes/model.py KGEModel.train_step, torch CPU, {cores} "
+                             f"threads): {rows} of {B} positive rows x {N} negatives per step at full width, full tables, "
+                             f"stock Adam; 3 steps after 1 warm-up ({dt:.2f} s/step)"}
+            qv, qdt, _ = time_reference_eval(mods, wl, all_true, test[:16], cuda=False)
+            ev["cpu_baseline"] = {"value": qv, "unit": "queries/s", "cores": cores, "kind": "reference",
+                                  "sample": f"unmodified reference KGEModel.test_step (TestDataset + DataLoader + forward + "
+                                            f"argsort) on 16 test triples x 2 modes, same tables and filter list ({qdt:.1f} s)"}
+            try:                                    # the practical bar: the reference's own eager torch-CUDA path, same B200
+                torch.cuda.empty_cache()
+                cv, cdt = time_reference_train(mods, wl, B, 5, 2, cuda=True)
+                cq, cqdt, _ = time_reference_eval(mods, wl, all_true, test[:64], cuda=True)
+                ref_cuda = {"what": "unmodified reference with args.cuda=True on this GPU (eager torch kernels)",
+                            "train_value": cv, "train_unit": "scores/s", "train_ms_per_step": cdt * 1e3,
+                            "eval_value": cq, "eval_unit": "queries/s", "eval_queries": 128,
+                            "speedup_e2e_train": tr["e2e_value"] / cv, "speedup_eval": ev["value"] / cq}
+            except Exception as exc:                # e.g. out of memory on a smaller device
+                ref_cuda = {"unavailable": repr(exc)[:200]}
+        else:
+            ref_cuda = {"unavailable": "baseline/_ref/codes absent"}
+        pv, pdt, pthreads = cpu_port_train(wl, B, 3, 1, cores)
+        port = {"value": pv, "unit": "scores/s", "cores": pthreads, "kind": "port",
+                "sample": f"oracle/kge_oracle.c (C/OpenMP restatement), full {B}-row batch, 3 steps after 1 warm-up"}
+        if cpu is None:
+            cpu = port
+    else:
+        ref_cuda = port = None
+    px = tr["peer"]
+    exchange_path = ("nvlink_peer_memory/%s%s (kge_peer_reduce_adam)" % (px.backend, "+nvswitch_multicast" if px.multicast else "")
+                     if px else ("nccl_allreduce + kge_adam_step" if world > 1 else
+                                 ("entity Adam fused in kge_train_rows_adam + kge_adam_step over R" if fused else "kge_adam_step")))
+    # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan_tiles, scan_apply, scatter_pairs,
+    # entity_kernel per region, loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish per region
+    nreg = tr["nreg"]
     line = {
-        "metric": METRIC, "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "score_function": model, "nentity": nentity, "nrelation": nrel, "hidden_dim": d,
-                   "negative_sample_size": N, "batch_size_per_gpu": B, "positives_per_step": Bg, "gamma": gamma,
-                   "adversarial": True, "double_entity_embedding": de,
-                   "sharding": f"positive rows over {world} rank(s), tables replicated; eval: entity slices",
-                   "l2_policy": "no flush: each step streams 0.6 GB of tables+moments+grads (> 126 MB L2)"},
-        # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan_tiles, scan_apply, scatter_pairs,
-        # entity_kernel per region, loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish
-        # per region
+        "metric": METRIC, "value": tr["value"], "unit": "scores/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(wl, world),
         "clocks": clocks, "gpu_launches": (6 + nreg + (2 * nreg if px else 1)) * args.steps,
-        "e2e": {"value": e2e_value, "unit": "scores/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "last_loss": last.get("loss")},
-        "roofline": roofline, "cpu_baseline": cpu,
-        "exchange": {"path": exchange_path, "exposed_exchange_and_optimizer_ms": exchange_ms,
+        "e2e": {"value": tr["e2e_value"], "unit": "scores/s", "ms_per_step": tr["ms_e2e"], "h2d_bytes_per_step": tr["h2d"],
+                "d2h_bytes_per_step": tr["d2h"], "last_loss": tr["last_loss"],
+                "what": "KGEModel.train_step (default settings: one next() per call, H2D on the compute stream) on pinned "
+                        "host batches, log dict read back every step"},
+        "roofline": roofline, "cpu_baseline": cpu, "cpu_port": port, "reference_cuda": ref_cuda, "parity_check": parity,
+        "full_step_roofline": {"bound": "hbm", "algorithmic_bytes": a_train + adam_bytes(nentity * De + nrel * Dr),
+                               "achieved": (a_train + adam_bytes(nentity * De + nrel * Dr)) / (tr["ms_per_step"] * 1e-3) / 1e9,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": (a_train + adam_bytes(nentity * De + nrel * Dr)) / (tr["ms_per_step"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "exchange": {"path": exchange_path, "exposed_exchange_and_optimizer_ms": tr["exchange_ms"],
                      "regions_per_step": nreg,
-                     "bytes_reduced_per_rank": 4 * (m.entity_embedding.numel() + m.relation_embedding.numel())},
-        "eval": {"metric": "filtered_eval_queries_per_sec", "value": eval_qps, "queries": 2 * nq, "seconds": eval_s,
-                 "what": "KGEModel.filtered_ranks end to end: host triples -> CSR filter -> H2D -> kernels -> host ranks",
-                 "count_kernel_ms": eval_kernel_ms, "count_kernel_queries_per_sec": 2 * nq / (eval_kernel_ms * 1e-3),
-                 "one_table_pass_per_query_equiv_gbs": 2 * nq * nentity * De * 4 / (eval_kernel_ms * 1e-3) / 1e9 / world,
-                 "sharding": f"entities/{world}", "filter_triples": len(all_true), "roofline": eval_roofline},
+                     "bytes_reduced_per_rank": 4 * (nentity * De + nrel * Dr) if world > 1 else 0},
+        "eval": ev, "workloads": extras,
     }
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        b.dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -368,11 +647,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rotate_fb15k", choices=list(WORKLOADS))
-    ap.add_argument("--cpu-rows", type=int, default=0, help="positive rows per CPU step (0 = the full batch)")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="positive rows per CPU step (0 = 16 for the reference's torch-CPU path, the full batch for the port)")
+    ap.add_argument("--reference-kind", default="auto", choices=["auto", "port"],
+                    help="--impl reference: 'auto' = the unmodified reference when baseline/_ref exists, else the C port")
     ap.add_argument("--eval-queries", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly
+        os.environ["OMP_NUM_THREADS"] = str(host_cores())
         run_reference(args)
     else:
         if args.warmup < 3:

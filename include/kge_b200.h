@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 
 /* model.py:151-157 `model_func` keys */
 enum { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_ROTATE = 3, KGE_PROTATE = 4 };
@@ -93,6 +93,38 @@ int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversar
                    float *grad_modulus, float *score_out, void *workspace, int64_t workspace_bytes,
                    int32_t *err_flag, void *stream);
 
+/* ---- fused train step for one device: the call above + the Adam update of the entity table (model.py:301-303) ----
+ * When kge_train_plan(m, rows, N) reports KGE_PLAN_ENTITY_ADAM, the entity-major half of the backward keeps each
+ * entity's summed gradient in registers and applies torch.optim.Adam to the row in place (entity_embedding, exp_avg,
+ * exp_avg_sq are updated; *m->entity is WRITTEN despite the const in kge_model_t): the dense entity gradient is never
+ * materialised, zeroed or re-read (optimizer.zero_grad() at model.py:259 has nothing to clear for it).  Every entity is
+ * updated, also those without a gradient this step (dense Adam semantics).  The relation table (and pRotatE's
+ * modulus) keep dense gradients in grad_relation / grad_modulus and go through kge_adam_step as before.
+ * With l3_coefficient != 0 the entity share of the L3 regulariser (model.py:290-297) is folded in: 3*l3*x*|x| is added
+ * to the gradient and sum|x|^3 of the pre-update values is accumulated into reg_partials (zeroed here).
+ * A non-zero *err_flag (bad index in this batch) cancels the update.  The whole batch must be local (row_count == B). */
+typedef struct kge_entity_adam {
+  float *exp_avg;            /* optimizer.state[entity_embedding]['exp_avg']     [nentity, entity_dim]  */
+  float *exp_avg_sq;         /* optimizer.state[entity_embedding]['exp_avg_sq']                         */
+  int32_t step;              /* 1-based, after increment (state['step'])                                */
+  int32_t reserved;
+  double lr, beta1, beta2, eps;
+  double l3_coefficient;     /* args.regularization or 0                                                */
+  double *reg_partials;      /* device doubles (>= 148 recommended) or NULL when l3_coefficient == 0     */
+  int64_t n_reg_partials;
+} kge_entity_adam_t;
+
+enum { KGE_PLAN_SINGLE_READ = 1, KGE_PLAN_ENTITY_ADAM = 2 };
+/* which path kge_train_rows takes for `rows` local positive rows x N candidates (bit mask of KGE_PLAN_*)        */
+int kge_train_plan(const kge_model_t *m, int64_t rows, int64_t N);
+
+int kge_train_rows_adam(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                        const int64_t *positive, const int64_t *negative, const float *weight,
+                        const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N, float *row_loss,
+                        float *pos_row_loss, float *grad_relation, float *grad_modulus, void *workspace,
+                        int64_t workspace_bytes, int32_t *err_flag, const kge_entity_adam_t *host_entity_adam,
+                        void *stream);
+
 /* Device scratch for the single-read backward (kge_train_rows / kge_score_backward): per-pair dL/ds, the query
  * table, and the counting-sort arrays of the entity-major pass.  With workspace == NULL (or too small) the
  * two-sweep atomic kernel is used instead; results agree to rounding.                                        */
@@ -138,7 +170,7 @@ typedef struct kge_adam_tensor {
 
 int kge_adam_step(const kge_adam_tensor_t *host_tensors, int n_tensors, double lr, double beta1,
                   double beta2, double eps, double l3_coefficient, double *reg_partials,
-                  int64_t n_reg_partials, void *stream);
+                  int64_t n_reg_partials, const int32_t *skip_flag, void *stream);
 
 /* ---- filtered ranking: KGEModel.test_step (model.py:346-427) with dataloader.py:134-154's filter ----
  * Step 1: per query the fixed side is folded into a query vector (model.py:214-223 etc.)
@@ -187,7 +219,11 @@ int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const float *qvec,
                               const float *qnorm, const int64_t *queries, int64_t Q, const float *pos_score,
                               const uint32_t *filter_bits, const float *ehi, const float *elo, const float *enorm,
                               int64_t ent_begin, int64_t ent_end, int32_t *counts, void *amb_pairs,
-                              int64_t amb_capacity, int32_t *amb_count, void *stream);
+                              int64_t amb_capacity, int32_t *amb_count, float *approx_scores_out, void *stream);
+/* band(K): the relative half-width the kernel above uses, |approx - canonical| <= band * |q| * |E_j| (what the band
+ * test in tests/ pins against measured tensor-core errors); approx_scores_out (tests, may be NULL): [Q, nentity] dump
+ * of the tensor-core approximations for the entities in [ent_begin, ent_end).                                    */
+float kge_eval_gemm_band(int64_t entity_dim);
 
 /* filter bitmap from a CSR of true entities per query (dataloader.py:138-144)                     */
 int kge_eval_filter_bits(const int64_t *csr_offsets, const int32_t *csr_entities, int64_t Q,

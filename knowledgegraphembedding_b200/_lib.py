@@ -27,6 +27,13 @@ class KgeAdamTensor(Structure):
                 ("numel", c_int64), ("step", c_int32), ("l3", c_int32)]
 
 
+class KgeEntityAdam(Structure):
+    _fields_ = [("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("step", c_int32), ("reserved", c_int32),
+                ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("l3_coefficient", c_double), ("reg_partials", c_void_p), ("n_reg_partials", c_int64)]
+
+
+PLAN_SINGLE_READ, PLAN_ENTITY_ADAM = 1, 2
 PEER_MAX_RANKS, PEER_HANDLE_BYTES = 16, 64
 
 
@@ -48,6 +55,10 @@ PROTOTYPES = {
                                c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p]),
     "kge_train_workspace_bytes": (c_int64, [_M, c_int64, c_int64]),
+    "kge_train_plan": (c_int, [_M, c_int64, c_int64]),
+    "kge_train_rows_adam": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                    POINTER(KgeEntityAdam), c_void_p]),
     "kge_train_rows_begin": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                      c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_void_p, POINTER(c_int32), c_void_p]),
@@ -58,7 +69,7 @@ PROTOTYPES = {
     "kge_loss_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int64,
                                   c_void_p, c_void_p]),
     "kge_adam_step": (c_int, [POINTER(KgeAdamTensor), c_int, c_double, c_double, c_double, c_double, c_double,
-                              c_void_p, c_int64, c_void_p]),
+                              c_void_p, c_int64, c_void_p, c_void_p]),
     "kge_eval_query_vectors": (c_int, [_M, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "kge_eval_phase_table": (c_int, [_M, c_void_p, c_void_p]),
     "kge_eval_positive_scores": (c_int, [_M, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -70,7 +81,8 @@ PROTOTYPES = {
     "kge_eval_gemm_split": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kge_eval_gemm_count_ranks": (c_int, [_M, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
-                                          c_int64, c_void_p, c_void_p]),
+                                          c_int64, c_void_p, c_void_p, c_void_p]),
+    "kge_eval_gemm_band": (c_float, [c_int64]),
     "kge_sample_negatives": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.c_uint64,
                                      ctypes.c_uint64, c_void_p, c_void_p]),
     "kge_eval_filter_bits": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -105,7 +117,7 @@ def load():
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.kge_abi_version() != 1:
+    if lib.kge_abi_version() != 2:
         raise KgeError("libkge_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -12,7 +12,14 @@ namespace kge {
 // ---- error plumbing (no exceptions across the C ABI) --------------------------------------------
 void set_error(const char *fmt, ...);
 int check_model(const kge_model_t *m);
-int set_device(const kge_model_t *m);
+// Makes `device` current for the duration of an ABI call and restores the caller's current device on return (a model
+// on cuda:1 must not silently change the calling thread's device for later allocations).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  int enter(int device);
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
 
 #define KGE_CUDA_OK(expr)                                                                   \
   do {                                                                                      \
@@ -102,6 +109,37 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
   return r;
 }
 constexpr float kFltMin = 1.17549435e-38f;
+
+// ---- packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two IEEE-rn operations ------------
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 a, float &lo, float &hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
 
 __device__ __forceinline__ float log_sigmoid(float x) {     // F.logsigmoid: min(x,0) - log1p(exp(-|x|))
   return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));

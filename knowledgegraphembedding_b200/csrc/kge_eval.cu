@@ -426,7 +426,8 @@ extern "C" int kge_eval_query_vectors(const kge_model_t *m, int mode, const int6
   if ((rc = eval_mode(mode, head))) return rc;
   KGE_REQUIRE(queries && qvec, "null pointer");
   if (Q <= 0) return KGE_OK;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
   const int d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
   const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
@@ -459,7 +460,8 @@ extern "C" int kge_eval_phase_table(const kge_model_t *m, float *phase_table, vo
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(phase_table, "null pointer");
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   phase_table_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(m->entity, m->nentity * m->entity_dim, phase_scale(m),
                                                               phase_table);
   KGE_CUDA_OK(cudaGetLastError());
@@ -492,7 +494,8 @@ extern "C" int kge_eval_positive_scores(const kge_model_t *m, int mode, const fl
   if ((rc = eval_mode(mode, head))) return rc;
   KGE_REQUIRE(qvec && queries && pos_score, "null pointer");
   if (Q <= 0) return KGE_OK;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   EvalArgs a{};
   if ((rc = fill_eval_args(m, head, qvec, queries, Q, phase_table, a))) return rc;
   const int grid = (int)((Q + 3) / 4);                   // 4 warps per CTA, one warp per query
@@ -547,7 +550,8 @@ static int count_ranks_impl(const kge_model_t *m, int mode, const float *qvec, c
               (long long)ent_begin, (long long)ent_end, (long long)m->nentity);
   if (Q <= 0 || ent_begin == ent_end) return KGE_OK;
   KGE_REQUIRE((Q + TQ - 1) / TQ <= 65535, "at most %d queries per call", 65535 * TQ);
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   EvalArgs a{};
   if ((rc = fill_eval_args(m, head, qvec, queries, Q, phase_table, a))) return rc;
   a.pos_score = pos_score; a.filter_bits = filter_bits; a.counts = counts; a.scores_out = scores_out;

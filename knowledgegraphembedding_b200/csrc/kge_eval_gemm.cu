@@ -47,6 +47,7 @@ struct GemmArgs {
   int64_t nentity, ent_begin, ent_end;
   int K;                         // contraction length (entity_dim)
   float band;
+  float *approx_out;             // tests: [Q, nentity] dump of the tensor-core approximations (or NULL)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -239,6 +240,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int64_t j = jb + i;
+            if (a.approx_out && j < a.ent_end) a.approx_out[(int64_t)qi * a.nentity + j] = __uint_as_float(v[i]);
             if (j >= a.ent_end || j == pid || ((fw >> i) & 1u)) continue;
             const float s = __uint_as_float(v[i]);
             const float eps = qn * enorm_s[as * GN + c * 32 + i];
@@ -356,6 +358,10 @@ extern "C" int kge_eval_gemm_supported(const kge_model_t *m) {
          (((uintptr_t)m->entity) & 15) == 0 && m->nentity < (1ll << 31);
 }
 
+extern "C" float kge_eval_gemm_band(int64_t entity_dim) {
+  return kBandSplit + kBandPerKBlock * (float)(3 * ((entity_dim + GK - 1) / GK));
+}
+
 extern "C" int kge_eval_gemm_split(const float *x, int64_t rows, int64_t cols, float *hi, float *lo, float *norm,
                                    void *stream) {
   KGE_REQUIRE(x && hi && lo && norm && rows > 0 && cols > 0, "bad arguments");
@@ -370,7 +376,7 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
                                          const float *pos_score, const uint32_t *filter_bits, const float *ehi,
                                          const float *elo, const float *enorm, int64_t ent_begin, int64_t ent_end,
                                          int32_t *counts, void *amb_pairs, int64_t amb_capacity, int32_t *amb_count,
-                                         void *stream) {
+                                         float *approx_scores_out, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(kge_eval_gemm_supported(m), "the tcgen05 path serves DistMult / ComplEx with 16-byte aligned rows");
@@ -381,7 +387,8 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   KGE_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= m->nentity && ent_begin % 32 == 0,
               "entity slice must start on a multiple of 32");
   if (Q <= 0 || ent_begin == ent_end) return KGE_OK;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t K = m->entity_dim;
   CUtensorMap tQhi, tQlo, tEhi, tElo;
@@ -394,7 +401,8 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   a.counts = counts; a.amb = (int2 *)amb_pairs; a.amb_count = amb_count; a.amb_capacity = (int)amb_capacity;
   a.Q = (int)Q; a.pos_col = mode == KGE_HEAD_BATCH ? 0 : 2; a.words = (int)((m->nentity + 31) / 32);
   a.nentity = m->nentity; a.ent_begin = ent_begin; a.ent_end = ent_end; a.K = (int)K;
-  a.band = kBandSplit + kBandPerKBlock * (float)(3 * ((K + GK - 1) / GK));
+  a.band = kge_eval_gemm_band(K);
+  a.approx_out = approx_scores_out;
   KGE_CUDA_OK(cudaMemsetAsync(amb_count, 0, 2 * sizeof(int), st));
   const size_t smem = 2 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
   KGE_CUDA_OK(cudaFuncSetAttribute(gemm_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

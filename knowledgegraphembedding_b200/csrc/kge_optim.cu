@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "kge_common.cuh"
+#include "kge_adam.cuh"
 
 namespace kge {
 
@@ -39,8 +40,12 @@ int check_model(const kge_model_t *m) {
   return KGE_OK;
 }
 
-int set_device(const kge_model_t *m) {
-  KGE_CUDA_OK(cudaSetDevice(m->device));
+int DeviceGuard::enter(int device) {
+  KGE_CUDA_OK(cudaGetDevice(&prev));
+  if (prev != device) {
+    KGE_CUDA_OK(cudaSetDevice(device));
+    changed = true;
+  }
   return KGE_OK;
 }
 
@@ -99,52 +104,39 @@ __global__ void loss_finalize_kernel(const float *__restrict__ pos_row, const fl
 struct AdamTensor {
   float *p, *g, *m, *v;
   int64_t n;
-  float step_size, bc2_sqrt;     // -(lr / (1 - beta1^t)),  sqrt(1 - beta2^t)
+  AdamScalars s;
   int l3;
 };
 struct AdamArgs {
   AdamTensor t[4];
   int nt;
-  float w1, b2, w2, eps, l3x3;   // 1-beta1, beta2, 1-beta2, eps, 3*l3
   double *reg_partials;
+  const int32_t *skip_flag;      // device flag (or NULL): a non-zero value (bad index in this step) cancels the update
 };
 
-__device__ __forceinline__ void adam_elem(float &p, float &g, float &m, float &v, const AdamArgs &a,
-                                          const AdamTensor &t, bool l3, double &racc) {
-  if (l3) {
-    const float ax = fabsf(p);
-    racc += (double)(ax * ax * ax);
-    g = g + a.l3x3 * p * ax;                               // d/dx of l3 * sum|x|^3
-  }
-  m = m + (g - m) * a.w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * a.b2;                                            // exp_avg_sq.mul_(beta2)
-  v = v + a.w2 * g * g;                                    //   .addcmul_(grad, grad, value=1 - beta2)
-  const float denom = sqrtf(v) / t.bc2_sqrt + a.eps;       // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
-  p = p + t.step_size * (m / denom);                       // param.addcdiv_(exp_avg, denom, value=-step_size)
-}
-
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+  if (a.skip_flag && *a.skip_flag) return;                 // model.py:86-146 would have raised before optimizer.step()
   double racc = 0.0;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int ti = 0; ti < a.nt; ++ti) {
     const AdamTensor t = a.t[ti];
-    const bool l3 = t.l3 != 0 && a.l3x3 != 0.f;
+    const bool l3 = t.l3 != 0 && t.s.l3x3 != 0.f;
     const int64_t n4 = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) ? t.n / 4 : 0;
     float4 *p4 = reinterpret_cast<float4 *>(t.p), *g4 = reinterpret_cast<float4 *>(t.g);
     float4 *m4 = reinterpret_cast<float4 *>(t.m), *v4 = reinterpret_cast<float4 *>(t.v);
     for (int64_t i = tid; i < n4; i += nth) {
       float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
-      adam_elem(p.x, g.x, m.x, v.x, a, t, l3, racc);
-      adam_elem(p.y, g.y, m.y, v.y, a, t, l3, racc);
-      adam_elem(p.z, g.z, m.z, v.z, a, t, l3, racc);
-      adam_elem(p.w, g.w, m.w, v.w, a, t, l3, racc);
+      adam_elem(p.x, g.x, m.x, v.x, t.s, l3, racc);
+      adam_elem(p.y, g.y, m.y, v.y, t.s, l3, racc);
+      adam_elem(p.z, g.z, m.z, v.z, t.s, l3, racc);
+      adam_elem(p.w, g.w, m.w, v.w, t.s, l3, racc);
       p4[i] = p; m4[i] = m; v4[i] = v;
       if (l3) g4[i] = g;
     }
     for (int64_t i = n4 * 4 + tid; i < t.n; i += nth) {
       float p = t.p[i], g = t.g[i], m = t.m[i], v = t.v[i];
-      adam_elem(p, g, m, v, a, t, l3, racc);
+      adam_elem(p, g, m, v, t.s, l3, racc);
       t.p[i] = p; t.m[i] = m; t.v[i] = v;
       if (l3) t.g[i] = g;
     }
@@ -206,22 +198,20 @@ extern "C" int kge_loss_finalize(const float *pos_row, const float *neg_row, con
 }
 
 extern "C" int kge_adam_step(const kge_adam_tensor_t *ts, int nt, double lr, double beta1, double beta2, double eps,
-                             double l3, double *reg_partials, int64_t n_reg_partials, void *stream) {
+                             double l3, double *reg_partials, int64_t n_reg_partials, const int32_t *skip_flag,
+                             void *stream) {
   KGE_REQUIRE(ts && nt >= 1 && nt <= 4, "kge_adam_step takes 1..4 tensors");
   AdamArgs a{};
   a.nt = nt;
+  a.skip_flag = skip_flag;
   int64_t total = 0;
   for (int i = 0; i < nt; ++i) {
     KGE_REQUIRE(ts[i].param && ts[i].grad && ts[i].exp_avg && ts[i].exp_avg_sq && ts[i].numel > 0 && ts[i].step >= 1,
                 "bad Adam tensor %d", i);
-    const double bc1 = 1.0 - pow(beta1, (double)ts[i].step);
-    const double bc2 = 1.0 - pow(beta2, (double)ts[i].step);
     a.t[i] = AdamTensor{ts[i].param, ts[i].grad, ts[i].exp_avg, ts[i].exp_avg_sq, ts[i].numel,
-                        (float)(-(lr / bc1)), (float)sqrt(bc2), ts[i].l3};
+                        adam_scalars(lr, beta1, beta2, eps, l3, ts[i].step), ts[i].l3};
     total += ts[i].numel;
   }
-  a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
-  a.l3x3 = (float)(3.0 * l3);
   int grid = (int)((total / 4 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;

@@ -15,550 +15,100 @@
 // candidate (model.py:83-102 uses the non-head-batch association of every score function).
 #include <stdlib.h>
 
-#include "kge_rows.cuh"
+#include "kge_train_args.cuh"
 
 namespace kge {
 
-struct RowArgs {
-  const float *E, *R, *modulus;
-  const int64_t *positive;     // [B_total, 3]
-  const int64_t *cand;         // candidate (b, n) = cand[b * cand_stride + n]
-  int64_t cand_stride;
-  int64_t row_begin;
-  int row_count, N;
-  int64_t nentity, nrelation;
-  int d;                       // k-extent: hidden_dim for complex ops, entity_dim for real ops
-  int De, Dr;
-  float gamma, scale;
-  int do_loss, loss_kind;
-  float alpha;
-  const float *weight, *wsum;
-  float uniform_u;
-  float *row_loss;
-  float *pos_row_loss;         // split path only: also do the positive triple of each row (fused 'single' pass)
-  float *score_out;
-  const float *dscore;
-  float *gE, *gR, *gM;
-  int32_t *err;
-  int *fused_positive;         // host-side out flag: the launched variant handled pos_row_loss itself
-  int defer_entity;            // host: do not launch the entity-major pass (caller slices it, kge_train_entity_pass)
-  int *entity_deferred;        // host out flag: the split path ran and its entity pass is still due
-};
-
-constexpr int kChunks = 8;     // units per lane per k-tile: 8 x float4 x (re,im) = 64 accumulator registers
-
-template <int V>
-__device__ __forceinline__ void load_global(float (&o)[V], const float *p) {
-  if constexpr (V == 4) {
-    float4 t = ldg_stream4(p);
-    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-  } else {
-    o[0] = __ldg(p);
+// Exclusive scan of the histogram cnt[0..n) -> offsets (in place), cursor = copy, cnt[n] = total.  Two launches over
+// 1024-entry tiles (a single-CTA scan cost 18 us at FB15k's 14,951 entities and 157 us at YAGO3-10's 123,182):
+// scan_tiles_kernel scans each tile and leaves its total, scan_apply_kernel adds the totals of the preceding tiles.
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int *warp_tot, int &total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-}
-template <int V>
-__device__ __forceinline__ void load_shared(float (&o)[V], const float *p) {
-  if constexpr (V == 4) {
-    float4 t = *reinterpret_cast<const float4 *>(p);
-    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-  } else {
-    o[0] = *p;
-  }
-}
-template <int V>
-__device__ __forceinline__ void red_global(float *p, const float (&v)[V]) {
-  if constexpr (V == 4) red_add4(p, v[0], v[1], v[2], v[3]);
-  else red_add1(p, v[0]);
-}
-
-__device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_max) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = is_max ? warp_max(v) : warp_sum(v);
-  __syncthreads();                       // protect scratch from the previous use
-  if (lane == 0) scratch[warp] = v;
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  float r = is_max ? -INFINITY : 0.f;
-  for (int w = 0; w < nw; ++w) r = is_max ? fmaxf(r, scratch[w]) : r + scratch[w];   // fixed order
-  return r;
-}
-
-template <int MODEL, bool HEAD, int V>
-__global__ void __launch_bounds__(512, 1) row_kernel(const RowArgs a) {
-  constexpr int OP = op_of(MODEL, HEAD);
-  constexpr bool CPLX = op_is_complex(OP);
-  constexpr int H = CPLX ? 2 : 1;              // halves per unit
-  extern __shared__ __align__(16) float smem[];
-  const int Dq = CPLX ? 2 * a.d : a.d;
-  float *q = smem;                             // [Dq]
-  float *dq = q + ((Dq + 3) & ~3);             // [Dq]
-  float *sc = dq + ((Dq + 3) & ~3);            // [N] scores (only when do_loss)
-  float *gg = sc + (a.do_loss ? a.N : 0);      // [N] dL/ds   (only when do_loss)
-  float *scratch = gg + (a.do_loss ? a.N : 0); // [32]
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int nunits = a.d / V;                  // host guarantees divisibility
-  const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
-  const bool do_bwd = a.gE != nullptr;
-
-  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
-    const int64_t b = a.row_begin + rl;
-    int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
-    int64_t fid = HEAD ? tidx : hid;
-    if ((uint64_t)fid >= (uint64_t)a.nentity || (uint64_t)rid >= (uint64_t)a.nrelation) {
-      if (tid == 0 && a.err) *a.err = 1;
-      fid = 0; rid = 0;
+  if (warp == 0) {
+    int t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int s = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += s;
     }
-    const float *F = a.E + fid * a.De;
-    const float *Rr = a.R + rid * a.Dr;
-    const int64_t *cand = a.cand + b * a.cand_stride;
-
-    // ---- phase 0: query vector -------------------------------------------------------------------
-    __syncthreads();
-    for (int k = tid; k < a.d; k += blockDim.x) {
-      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q);
-      dq[k] = 0.f;
-      if (CPLX) dq[a.d + k] = 0.f;
-    }
-    __syncthreads();
-
-    // ---- phase 1: scores -------------------------------------------------------------------------
-    if (a.do_loss || a.score_out) {
-      for (int n = warp; n < a.N; n += nwarps) {
-        int64_t id = cand[n];
-        if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
-        const float *x = a.E + id * a.De;
-        float part = 0.f;
-        for (int kt = 0; kt < nunits; kt += 32 * kChunks) {
-#pragma unroll
-          for (int i = 0; i < kChunks; ++i) {
-            const int u = kt + lane + 32 * i;
-            if (u < nunits) {
-              float x0[V], x1[V], q0[V], q1[V];
-              load_global<V>(x0, x + u * V);
-              load_shared<V>(q0, q + u * V);
-              if constexpr (CPLX) {
-                load_global<V>(x1, x + a.d + u * V);
-                load_shared<V>(q1, q + a.d + u * V);
-              }
-#pragma unroll
-              for (int j = 0; j < V; ++j)
-                part += op_forward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale);
-            }
-          }
-        }
-        part = warp_sum(part);
-        const float s = finish_score<MODEL>(part, a.gamma, modulus);
-        if (lane == 0) {
-          if (a.do_loss) sc[n] = s;
-          if (a.score_out) a.score_out[(int64_t)rl * a.N + n] = s;
-        }
-      }
-    }
-    if (!a.do_loss && !do_bwd) continue;
-
-    // ---- phase 2: loss of this row (model.py:270-288) and dL/ds ---------------------------------------
-    if (a.do_loss) {
-      __syncthreads();
-      const float u = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
-      float row_val;
-      if (a.loss_kind == KGE_LOSS_POSITIVE) {              // model.py:277-279
-        const float s = sc[0];
-        row_val = log_sigmoid(s);
-        if (tid == 0) gg[0] = -0.5f * u * sigmoid(-s);
-      } else {
-        float zmax = -INFINITY;
-        if (a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL) {     // softmax(alpha * s).detach(), model.py:272
-          for (int n = tid; n < a.N; n += blockDim.x) zmax = fmaxf(zmax, sc[n] * a.alpha);
-          zmax = block_reduce(zmax, scratch, true);
-        }
-        float zsum = 0.f;
-        for (int n = tid; n < a.N; n += blockDim.x) {
-          const float e = a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL ? expf(sc[n] * a.alpha - zmax) : 1.f;
-          gg[n] = e;
-          zsum += e;
-        }
-        zsum = block_reduce(zsum, scratch, false);
-        float acc = 0.f;
-        for (int n = tid; n < a.N; n += blockDim.x) {
-          const float w = gg[n] / zsum;                    // = 1/N for the uniform case (model.py:275)
-          const float s = sc[n];
-          acc += w * log_sigmoid(-s);
-          gg[n] = 0.5f * u * w * sigmoid(s);
-        }
-        row_val = block_reduce(acc, scratch, false);
-      }
-      if (tid == 0) a.row_loss[b] = row_val;
-      __syncthreads();
-    }
-    if (!do_bwd) continue;
-    const float *gsrc = a.do_loss ? gg : a.dscore + (int64_t)rl * a.N;
-
-    // ---- phase 3/4: backward over the candidates, k-tiled so dL/dq stays in registers -----------------
-    float gmod = 0.f;
-    for (int kt = 0; kt < nunits; kt += 32 * kChunks) {
-      float acc[kChunks][H][V];
-#pragma unroll
-      for (int i = 0; i < kChunks; ++i)
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
-
-      for (int n = warp; n < a.N; n += nwarps) {
-        int64_t id = cand[n];
-        if ((uint64_t)id >= (uint64_t)a.nentity) id = 0;
-        const float g = gsrc[n];
-        const float go = dsum_of<MODEL>(g, modulus);
-        const float *x = a.E + id * a.De;
-        float *gx = a.gE + id * a.De;
-        float vsum = 0.f;
-#pragma unroll
-        for (int i = 0; i < kChunks; ++i) {
-          const int u = kt + lane + 32 * i;
-          if (u < nunits) {
-            float x0[V], x1[V], q0[V], q1[V], dx0[V], dx1[V];
-            load_global<V>(x0, x + u * V);
-            load_shared<V>(q0, q + u * V);
-            if constexpr (CPLX) {
-              load_global<V>(x1, x + a.d + u * V);
-              load_shared<V>(q1, q + a.d + u * V);
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              float dq0 = 0.f, dq1 = 0.f, ex0 = 0.f, ex1 = 0.f;
-              vsum += op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, go,
-                                      dq0, dq1, ex0, ex1);
-              acc[i][0][j] += dq0;
-              dx0[j] = ex0;
-              if constexpr (CPLX) { acc[i][1][j] += dq1; dx1[j] = ex1; }
-            }
-            red_global<V>(gx + u * V, dx0);
-            if constexpr (CPLX) red_global<V>(gx + a.d + u * V, dx1);
-          }
-        }
-        if constexpr (MODEL == KGE_PROTATE) {
-          vsum = warp_sum(vsum);
-          gmod += -g * vsum;                               // d/dmodulus of gamma - modulus * sum
-        }
-      }
-      // phase 4: fixed-order fold of the per-warp partial dL/dq into shared memory
-      for (int w = 0; w < nwarps; ++w) {
-        if (warp == w) {
-#pragma unroll
-          for (int i = 0; i < kChunks; ++i) {
-            const int u = kt + lane + 32 * i;
-            if (u < nunits) {
-#pragma unroll
-              for (int j = 0; j < V; ++j) {
-                dq[u * V + j] += acc[i][0][j];
-                if constexpr (CPLX) dq[a.d + u * V + j] += acc[i][1][j];
-              }
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-
-    // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
-    float *gF = a.gE + fid * a.De;
-    float *gRr = a.gR + rid * a.Dr;
-    for (int k = tid; k < a.d; k += blockDim.x) {
-      float dF0, dF1, dR0, dR1;
-      chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
-      red_add1(gF + k, dF0);
-      red_add1(gRr + k, dR0);
-      if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
-      if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
-    }
-    if constexpr (MODEL == KGE_PROTATE) {
-      if (lane == 0 && gmod != 0.f && a.gM) red_add1(a.gM, gmod);
-    }
+    warp_tot[lane] = t;                                    // inclusive totals of the warps
   }
-}
-
-// ======================================================================================================
-// TMA variant: candidate rows are gathered by the bulk-copy engine (cp.async.bulk global -> shared, one
-// 1-D copy of the whole D_e*4-byte row per candidate, completion on an mbarrier) into a per-warp double
-// buffer.  The bytes in flight are then bounded by shared memory (W warps x 2 slots x row bytes, ~200 KB
-// per SM) instead of by registers, which is what the direct-load kernel above is limited by (ncu r1a:
-// 68% of issue slots stalled on long-scoreboard with 16 KB in flight per SM).  Phases are the same.
-// ======================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <int MODEL, bool HEAD>
-__global__ void __launch_bounds__(512, 1) row_kernel_tma(const RowArgs a) {
-  constexpr int OP = op_of(MODEL, HEAD);
-  constexpr bool CPLX = op_is_complex(OP);
-  constexpr int H = CPLX ? 2 : 1;
-  constexpr int V = 4;
-  constexpr int CH = CPLX ? 8 : 16;            // units per lane: 64 accumulator registers either way
-  extern __shared__ __align__(128) float smem[];
-  const int Dq = a.De;
-  const int Dq4 = (Dq + 3) & ~3;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  // layout: [slots: nwarps x 2 x De | q | dq | sc | gg | scratch(32) | mbarriers]; every pointer is derived from
-  // `smem` by element offsets so that the compiler keeps the shared address space (LDS, not generic LD)
-  float *slot0 = smem + (size_t)(2 * warp) * a.De, *slot1 = slot0 + a.De;
-  float *q = smem + (size_t)(2 * nwarps) * a.De;
-  float *dq = q + Dq4;
-  float *sc = dq + Dq4;
-  float *gg = sc + (a.do_loss ? a.N : 0);
-  float *scratch = gg + (a.do_loss ? a.N : 0);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
-  const uint32_t rowbytes = (uint32_t)a.De * 4u;
-  uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
-  uint32_t par0 = 0, par1 = 0;
-  int64_t id0 = 0, id1 = 0;
-
-  const int nunits = a.d / V;                  // <= 32 * CH (host)
-  const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
-  const bool do_bwd = a.gE != nullptr;
-
-  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-
-  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
-    const int64_t b = a.row_begin + rl;
-    int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
-    int64_t fid = HEAD ? tidx : hid;
-    if ((uint64_t)fid >= (uint64_t)a.nentity || (uint64_t)rid >= (uint64_t)a.nrelation) {
-      if (tid == 0 && a.err) *a.err = 1;
-      fid = 0; rid = 0;
-    }
-    const float *F = a.E + fid * a.De;
-    const float *Rr = a.R + rid * a.Dr;
-    const int64_t *cand = a.cand + b * a.cand_stride;
-
-    // issue the bulk copy of candidate n into this warp's slot s (all lanes run it; lane 0 talks to the engine)
-    auto issue = [&](int s, int n) {
-      int64_t id = cand[n];
-      if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
-      if (s) id1 = id; else id0 = id;
-      if (lane == 0) {
-        uint64_t *bar = s ? bar1 : bar0;
-        mbar_expect_tx(bar, rowbytes);
-        bulk_g2s(s ? slot1 : slot0, a.E + id * a.De, rowbytes, bar);
-      }
-    };
-    // first two candidates of phase 1 (or of phase 3 for the backward-only call) overlap the q build
-    if (warp < a.N) issue(0, warp);
-    if (warp + nwarps < a.N) issue(1, warp + nwarps);
-
-    // ---- phase 0: query vector -------------------------------------------------------------------
-    for (int k = tid; k < a.d; k += blockDim.x) {
-      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q);
-      dq[k] = 0.f;
-      if (CPLX) dq[a.d + k] = 0.f;
-    }
-    __syncthreads();
-
-    // ---- phase 1: scores -------------------------------------------------------------------------
-    const bool do_fwd = a.do_loss || a.score_out;
-    if (do_fwd) {
-      int it = 0;
-      for (int n = warp; n < a.N; n += nwarps, ++it) {
-        const int s = it & 1;
-        if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-        const float *x = s ? slot1 : slot0;
-        float part = 0.f;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int u = lane + 32 * i;
-          if (u < nunits) {
-            float x0[V], x1[V], q0[V], q1[V];
-            load_shared<V>(x0, x + u * V);
-            load_shared<V>(q0, q + u * V);
-            if constexpr (CPLX) {
-              load_shared<V>(x1, x + a.d + u * V);
-              load_shared<V>(q1, q + a.d + u * V);
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-              part += op_forward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale);
-          }
-        }
-        __syncwarp();                                   // every lane is done reading the slot
-        if (n + 2 * nwarps < a.N) issue(s, n + 2 * nwarps);
-        part = warp_sum(part);
-        const float sv = finish_score<MODEL>(part, a.gamma, modulus);
-        if (lane == 0) {
-          if (a.do_loss) sc[n] = sv;
-          if (a.score_out) a.score_out[(int64_t)rl * a.N + n] = sv;
-        }
-      }
-      if (do_bwd) {                                     // restart the ring for phase 3 while the loss is computed
-        if (warp < a.N) issue(0, warp);
-        if (warp + nwarps < a.N) issue(1, warp + nwarps);
-      }
-    }
-    if (!a.do_loss && !do_bwd) { __syncthreads(); continue; }
-
-    // ---- phase 2: loss of this row (model.py:270-288) and dL/ds ---------------------------------------
-    if (a.do_loss) {
-      __syncthreads();
-      const float u = a.weight ? a.weight[b] / a.wsum[0] : a.uniform_u;
-      float row_val;
-      if (a.loss_kind == KGE_LOSS_POSITIVE) {
-        const float sv = sc[0];
-        row_val = log_sigmoid(sv);
-        if (tid == 0) gg[0] = -0.5f * u * sigmoid(-sv);
-      } else {
-        float zmax = -INFINITY;
-        if (a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL) {
-          for (int n = tid; n < a.N; n += blockDim.x) zmax = fmaxf(zmax, sc[n] * a.alpha);
-          zmax = block_reduce(zmax, scratch, true);
-        }
-        float zsum = 0.f;
-        for (int n = tid; n < a.N; n += blockDim.x) {
-          const float e = a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL ? expf(sc[n] * a.alpha - zmax) : 1.f;
-          gg[n] = e;
-          zsum += e;
-        }
-        zsum = block_reduce(zsum, scratch, false);
-        float acc = 0.f;
-        for (int n = tid; n < a.N; n += blockDim.x) {
-          const float w = gg[n] / zsum;
-          const float sv = sc[n];
-          acc += w * log_sigmoid(-sv);
-          gg[n] = 0.5f * u * w * sigmoid(sv);
-        }
-        row_val = block_reduce(acc, scratch, false);
-      }
-      if (tid == 0) a.row_loss[b] = row_val;
-      __syncthreads();
-    }
-    if (!do_bwd) continue;
-    const float *gsrc = a.do_loss ? gg : a.dscore + (int64_t)rl * a.N;
-
-    // ---- phase 3: backward over the candidates; dL/dq stays in registers ------------------------------------
-    float gmod = 0.f;
-    float acc[CH][H][V];
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
-    {
-      int it = 0;
-      for (int n = warp; n < a.N; n += nwarps, ++it) {
-        const int s = it & 1;
-        if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-        const float *x = s ? slot1 : slot0;
-        const int64_t id = s ? id1 : id0;
-        const float g = gsrc[n];
-        const float go = dsum_of<MODEL>(g, modulus);
-        float *gx = a.gE + id * a.De;
-        float vsum = 0.f;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int u = lane + 32 * i;
-          if (u < nunits) {
-            float x0[V], x1[V], q0[V], q1[V], dx0[V], dx1[V];
-            load_shared<V>(x0, x + u * V);
-            load_shared<V>(q0, q + u * V);
-            if constexpr (CPLX) {
-              load_shared<V>(x1, x + a.d + u * V);
-              load_shared<V>(q1, q + a.d + u * V);
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              float dq0 = 0.f, dq1 = 0.f, ex0 = 0.f, ex1 = 0.f;
-              vsum += op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, go,
-                                      dq0, dq1, ex0, ex1);
-              acc[i][0][j] += dq0;
-              dx0[j] = ex0;
-              if constexpr (CPLX) { acc[i][1][j] += dq1; dx1[j] = ex1; }
-            }
-            red_global<V>(gx + u * V, dx0);
-            if constexpr (CPLX) red_global<V>(gx + a.d + u * V, dx1);
-          }
-        }
-        __syncwarp();
-        if (n + 2 * nwarps < a.N) issue(s, n + 2 * nwarps);
-        if constexpr (MODEL == KGE_PROTATE) {
-          vsum = warp_sum(vsum);
-          gmod += -g * vsum;
-        }
-      }
-    }
-    // ---- phase 4: fixed-order fold of the per-warp partial dL/dq into shared memory -----------------------
-    for (int w = 0; w < nwarps; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int u = lane + 32 * i;
-          if (u < nunits) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              dq[u * V + j] += acc[i][0][j];
-              if constexpr (CPLX) dq[a.d + u * V + j] += acc[i][1][j];
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
-    float *gF = a.gE + fid * a.De;
-    float *gRr = a.gR + rid * a.Dr;
-    for (int k = tid; k < a.d; k += blockDim.x) {
-      float dF0, dF1, dR0, dR1;
-      chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
-      red_add1(gF + k, dF0);
-      red_add1(gRr + k, dR0);
-      if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
-      if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
-    }
-    if constexpr (MODEL == KGE_PROTATE) {
-      if (lane == 0 && gmod != 0.f && a.gM) red_add1(a.gM, gmod);
-    }
-    __syncthreads();                                    // q / dq are rebuilt by the next row
-  }
+  total = warp_tot[31];
+  return (warp ? warp_tot[warp - 1] : 0) + incl - v;
 }
 
-}  // namespace kge
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int *__restrict__ cnt, int *__restrict__ cursor,
+                                                          int *__restrict__ tile_tot, int64_t n) {
+  __shared__ int warp_tot[32];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int total;
+  const int excl = block_exclusive_scan_1024(i < n ? cnt[i] : 0, warp_tot, total);
+  if (i < n) cursor[i] = excl;                             // offset inside the tile
+  if (threadIdx.x == 0) tile_tot[blockIdx.x] = total;
+}
 
-#include "kge_train_split.cuh"
+__global__ void __launch_bounds__(1024) scan_apply_kernel(int *__restrict__ cnt, int *__restrict__ cursor,
+                                                          const int *__restrict__ tile_tot, int64_t n) {
+  __shared__ int warp_tot[32];
+  __shared__ int prefix_sh;
+  // sum of the totals of tiles [0, blockIdx.x): every thread adds a strided share, one block reduction
+  int part = 0;
+  for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) part += tile_tot[t];
+  int total;
+  block_exclusive_scan_1024(part, warp_tot, total);
+  if (threadIdx.x == 0) prefix_sh = total;
+  __syncthreads();
+  const int prefix = prefix_sh;
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) {
+    const int o = cursor[i] + prefix;
+    cnt[i] = o;
+    cursor[i] = o;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cnt[n] = prefix + tile_tot[blockIdx.x];
+}
 
-namespace kge {
+__global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
+                                     int N, int64_t nentity, const float *__restrict__ G, const int *__restrict__ dids,
+                                     int *__restrict__ cursor, int *__restrict__ perm, float *__restrict__ gsorted) {
+  const int64_t pairs = (int64_t)rows * N;
+  const int64_t total = pairs + (dids ? 3 * (int64_t)rows : 0);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    if (p < pairs) {
+      const int rl = (int)(p / N), n = (int)(p % N);
+      int64_t id = cand[(row_begin + rl) * cand_stride + n];
+      if ((uint64_t)id >= (uint64_t)nentity) id = 0;
+      const int pos = atomicAdd(cursor + id, 1);
+      perm[pos] = rl;                                      // the entity pass only needs the q row and dL/ds
+      gsorted[pos] = G[p];
+    } else {                                               // direct gradient row i of the positive triples (fused optimizer)
+      const int i = (int)(p - pairs);
+      const int pos = atomicAdd(cursor + dids[i], 1);
+      perm[pos] = -(1 + i);
+      gsorted[pos] = 0.f;
+    }
+  }
+}
 
 // ---- host side ---------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
+size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
   return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 64) +
-         align256(((nentity + 1023) / 1024) * 4) + 2 * align256(rows * N * 4);
+         align256(((nentity + 1023) / 1024) * 4) + 2 * align256(rows * (N + 3) * 4) + align256(rows * 3 * De * 4) +
+         align256(rows * 3 * 4);
 }
 
-static SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity) {
+SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity) {
   char *wp = (char *)workspace;
   SplitWs ws;
   ws.G = (float *)wp;      wp += align256((size_t)rows * N * 4);
@@ -568,149 +118,21 @@ static SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t 
   ws.queue = ws.cursor + nentity;                          // 16 queue counters (one per entity slice)
   wp += align256((size_t)(nentity + 1) * 4 + (size_t)nentity * 4 + 64);
   ws.tile_tot = (int *)wp; wp += align256((size_t)((nentity + 1023) / 1024) * 4);
-  ws.perm = (int *)wp;     wp += align256((size_t)rows * N * 4);
-  ws.gsorted = (float *)wp;
+  ws.perm = (int *)wp;     wp += align256((size_t)rows * (N + 3) * 4);
+  ws.gsorted = (float *)wp; wp += align256((size_t)rows * (N + 3) * 4);
+  ws.Dvec = (float *)wp;   wp += align256((size_t)rows * 3 * De * 4);
+  ws.dids = (int *)wp;
   return ws;
 }
 
-template <int MODEL, bool HEAD>
-static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_begin, int64_t ent_end, int slot,
-                              cudaStream_t st, int reserve_sms = 0) {
-  constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
-  if (ent_end <= ent_begin) return KGE_OK;
-  const int nunits = a.d / 4;
-  EntArgs e{};
-  e.E = a.E; e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.gsorted = ws.gsorted; e.Qtab = ws.Qtab;
-  e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue + slot; e.nentity = a.nentity;
-  e.ent_begin = ent_begin; e.ent_count = ent_end - ent_begin;
-  e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
-  e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (reserve_sms > 0 && sms > 2 * reserve_sms) sms -= reserve_sms;   // leave SMs for the concurrent NCCL kernel
-  const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
-  e.upp = two ? (nunits + 1) / 2 : nunits;
-  // slots have the kernel's compile-time half stride: CH chunks of 32 float4 units, CH = (complex ? 8 : 16) / parts
-  const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * ((CPLX ? 8 : 16) / (two ? 2 : 1)) * 32 * 16;
-  int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
-  const int wmax = two ? 20 : 12;
-  if (We > wmax) We = wmax;
-  const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
-  if (two) {
-    auto k = entity_kernel<MODEL, HEAD, 2>;
-    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-    k<<<sms, We * 32, esmem, st>>>(e);
-  } else {
-    auto k = entity_kernel<MODEL, HEAD, 1>;
-    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-    k<<<sms, We * 32, esmem, st>>>(e);
-  }
-  KGE_CUDA_OK(cudaGetLastError());
-  return KGE_OK;
-}
-
-template <int MODEL, bool HEAD>
-static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, void *workspace, size_t workspace_bytes,
-                         cudaStream_t st) {
-  int grid = a.row_count;
-  // TMA ring variants: rows are 16-byte multiples, one k-tile covers the row, and >= 4 warps get a double buffer
-  constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
-  const int nunits = a.d / 4;
-  if (vec4 && nunits <= 32 * (CPLX ? 8 : 16) && !getenv("KGE_NO_TMA")) {
-    const size_t rowbytes = (size_t)a.De * 4;
-    const bool split = workspace && a.gE && a.N >= 8 && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
-                       workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
-                       a.nentity < (1ll << 31) && (int64_t)a.row_count * a.N < (1ll << 31) && !getenv("KGE_NO_SPLIT") &&
-                       // the entity-major pass pays a fixed cost per touched entity: it wins when an entity collects
-                       // several pairs (17 at FB15k shapes: 0.73 vs 0.96 ms) and loses when pairs are sparse
-                       // (3.3 at YAGO3-10 shapes: 1.59 vs 0.99 ms)
-                       ((int64_t)a.row_count * a.N >= 6 * a.nentity || getenv("KGE_FORCE_SPLIT"));
-    // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
-    if (split) {
-      constexpr int Hs = CPLX ? 2 : 1;
-      const int chunks = (nunits + 31) / 32;                 // 128-float chunks per half row
-      const int nch = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16);
-      const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
-      const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
-      const size_t per_warp = 2 * hs * sizeof(float) + 16;
-      int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
-      const int wcap = split_max_threads(CPLX, nch) / 32;
-      if (Ws > wcap) Ws = wcap;
-      if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
-      if (Ws > wcap) Ws = wcap;
-      if (Ws >= 4 && fixed_s + Ws * per_warp <= 227 * 1024) {
-        const size_t total = fixed_s + Ws * per_warp;
-        SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
-        KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
-        // persistent CTAs (one per SM: the slots take the whole shared memory), rows are dealt round-robin
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int sgrid = grid < sms ? grid : sms;
-#define KGE_SPLIT_LAUNCH(NCH)                                                                          \
-  do {                                                                                                 \
-    auto k = row_kernel_split<MODEL, HEAD, NCH>;                                                       \
-    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
-    k<<<sgrid, Ws * 32, total, st>>>(a, ws);                                                           \
-  } while (0)
-        if (nch == 4) KGE_SPLIT_LAUNCH(4);
-        else if (nch == 8) KGE_SPLIT_LAUNCH(8);
-        else {
-          if constexpr (CPLX) { set_error("row too wide"); return KGE_ERR_INVALID; }      // unreachable: nunits <= 256
-          else KGE_SPLIT_LAUNCH(16);
-        }
-#undef KGE_SPLIT_LAUNCH
-        KGE_CUDA_OK(cudaGetLastError());
-        if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
-        {
-          const int tiles = (int)((a.nentity + 1023) / 1024);
-          scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
-          KGE_CUDA_OK(cudaGetLastError());
-          scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
-          KGE_CUDA_OK(cudaGetLastError());
-        }
-        {
-          const int64_t pairs = (int64_t)a.row_count * a.N;
-          int g2 = (int)((pairs + 255) / 256);
-          if (g2 > 148 * 16) g2 = 148 * 16;
-          scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
-                                                   ws.G, ws.cursor, ws.perm, ws.gsorted);
-          KGE_CUDA_OK(cudaGetLastError());
-        }
-        if (a.defer_entity) {
-          if (a.entity_deferred) *a.entity_deferred = 1;
-          return KGE_OK;
-        }
-        return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
-      }
-    }
-    // ---- two-sweep TMA kernel ------------------------------------------------------------------------------
-    const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
-    const size_t fixed = base + 16;
-    int W = (int)((227 * 1024 - fixed) / (2 * rowbytes + 16));
-    if (W > 16) W = 16;
-    if (a.N < 4 * W) W = a.N >= 16 ? (a.N + 3) / 4 : 4;                // short candidate lists: fewer, busier warps
-    if (W >= 4 && fixed + W * (2 * rowbytes + 16) <= 227 * 1024) {
-      const size_t total = fixed + W * (2 * rowbytes + 16);
-      auto k = row_kernel_tma<MODEL, HEAD>;
-      KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-      k<<<grid, W * 32, total, st>>>(a);
-      KGE_CUDA_OK(cudaGetLastError());
-      return KGE_OK;
-    }
-  }
-  if (vec4) {
-    auto k = row_kernel<MODEL, HEAD, 4>;
-    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, threads, smem, st>>>(a);
-  } else {
-    auto k = row_kernel<MODEL, HEAD, 1>;
-    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, threads, smem, st>>>(a);
-  }
-  KGE_CUDA_OK(cudaGetLastError());
-  return KGE_OK;
+// The single-read path needs 16-byte rows that fit one k-tile, >= 8 candidates and 32-bit pair counts; it pays a fixed
+// cost per touched entity, so it wins when an entity collects several pairs (17 at FB15k shapes: 0.73 vs 0.96 ms) and
+// loses when pairs are sparse (3.3 at YAGO3-10 shapes: 1.59 vs 0.99 ms).  KGE_FORCE_SPLIT / KGE_NO_SPLIT override.
+bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity) {
+  if (getenv("KGE_NO_SPLIT") || getenv("KGE_NO_TMA")) return false;
+  if (d % 4 || De % 4 || d / 4 > 32 * (cplx ? 8 : 16)) return false;
+  if (N < 8 || nentity >= (1ll << 31) || rows * (N + 3) >= (1ll << 31)) return false;
+  return rows * N >= 6 * nentity || getenv("KGE_FORCE_SPLIT");
 }
 
 static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t st, void *workspace = nullptr,
@@ -731,10 +153,8 @@ static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t
               Dq, a.N, smem);
   // one warp per candidate in flight; a single-candidate pass ('single' mode) only needs a few warps for q
   int threads = a.N >= 16 ? 512 : (a.N >= 4 ? 256 : 128);
-#define KGE_ROWS(MODEL)                                                            \
-  case MODEL:                                                                      \
-    return head ? launch_rows_v<MODEL, true>(a, vec4, threads, smem, workspace, workspace_bytes, st)           \
-                : launch_rows_v<MODEL, false>(a, vec4, threads, smem, workspace, workspace_bytes, st);
+#define KGE_ROWS(MODEL) \
+  case MODEL: return launch_rows_model<MODEL>(head, a, vec4, threads, smem, workspace, workspace_bytes, st);
   switch (m->model) {
     KGE_ROWS(KGE_TRANSE)
     KGE_ROWS(KGE_DISTMULT)
@@ -774,7 +194,8 @@ extern "C" int kge_score_forward(const kge_model_t *m, int mode, const int64_t *
   RowArgs a{};
   bool head;
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   a.positive = positive; a.row_begin = 0; a.row_count = (int)B; a.N = (int)N;
   a.score_out = score; a.err = err_flag;
   return launch_rows(m, head, a, (cudaStream_t)stream);
@@ -791,21 +212,24 @@ extern "C" int kge_score_backward(const kge_model_t *m, int mode, const int64_t 
   RowArgs a{};
   bool head;
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   a.positive = positive; a.row_begin = 0; a.row_count = (int)B; a.N = (int)N;
   a.dscore = dscore; a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
   return launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
 }
 
-extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
-                              const int64_t *positive, const int64_t *negative, const float *weight,
-                              const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
-                              int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity,
-                              float *grad_relation, float *grad_modulus, float *score_out, void *workspace,
-                              int64_t workspace_bytes, int32_t *err_flag, void *stream) {
+extern "C" int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N);
+
+static int train_rows_impl(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                           const int64_t *positive, const int64_t *negative, const float *weight,
+                           const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
+                           int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity,
+                           float *grad_relation, float *grad_modulus, float *score_out, void *workspace,
+                           int64_t workspace_bytes, int32_t *err_flag, const EntityAdam *entity_adam, void *stream) {
   int rc = check_model(m);
   if (rc) return rc;
-  KGE_REQUIRE(positive && row_loss && grad_entity && grad_relation, "null pointer");
+  KGE_REQUIRE(positive && row_loss && grad_relation && (grad_entity || entity_adam), "null pointer");
   KGE_REQUIRE(m->model != KGE_PROTATE || grad_modulus, "pRotatE needs grad_modulus");
   KGE_REQUIRE(loss_kind >= KGE_LOSS_NEG_ADVERSARIAL && loss_kind <= KGE_LOSS_POSITIVE, "bad loss_kind %d", loss_kind);
   KGE_REQUIRE(!weight || weight_sum, "subsampling weights need their sum (kge_weight_sum)");
@@ -815,21 +239,78 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
   bool head;
   if (loss_kind == KGE_LOSS_POSITIVE) { mode = KGE_SINGLE; N = 1; }
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   a.positive = positive; a.row_begin = row_begin; a.row_count = (int)row_count; a.N = (int)N;
   a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
   a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
   a.row_loss = row_loss; a.score_out = score_out;
   a.pos_row_loss = loss_kind == KGE_LOSS_POSITIVE ? nullptr : pos_row_loss;
   a.gE = grad_entity; a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
-  int fused_positive = 0;
+  int fused_positive = 0, adam_applied = 0;
   a.fused_positive = &fused_positive;
+  a.entity_adam = entity_adam;
+  a.entity_adam_applied = &adam_applied;
   rc = launch_rows(m, head, a, (cudaStream_t)stream, workspace, (size_t)workspace_bytes);
-  if (rc || !a.pos_row_loss || fused_positive) return rc;
+  if (rc) return rc;
+  KGE_REQUIRE(!entity_adam || adam_applied || row_count == 0,
+              "internal: kge_train_plan promised the fused entity optimizer for this shape but the launcher declined");
+  if (!a.pos_row_loss || fused_positive) return rc;
   // the kernel variant that ran has no fused positive pass: run the 'single' pass as its own launch
-  return kge_train_rows(m, KGE_SINGLE, KGE_LOSS_POSITIVE, 1.0f, positive, negative, weight, weight_sum, B_total, row_begin,
-                        row_count, 1, pos_row_loss, nullptr, grad_entity, grad_relation, grad_modulus, nullptr, nullptr, 0,
-                        err_flag, stream);
+  return train_rows_impl(m, KGE_SINGLE, KGE_LOSS_POSITIVE, 1.0f, positive, negative, weight, weight_sum, B_total,
+                         row_begin, row_count, 1, pos_row_loss, nullptr, grad_entity, grad_relation, grad_modulus,
+                         nullptr, nullptr, 0, err_flag, nullptr, stream);
+}
+
+extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                              const int64_t *positive, const int64_t *negative, const float *weight,
+                              const float *weight_sum, int64_t B_total, int64_t row_begin, int64_t row_count,
+                              int64_t N, float *row_loss, float *pos_row_loss, float *grad_entity,
+                              float *grad_relation, float *grad_modulus, float *score_out, void *workspace,
+                              int64_t workspace_bytes, int32_t *err_flag, void *stream) {
+  KGE_REQUIRE(grad_entity, "null pointer");
+  return train_rows_impl(m, mode, loss_kind, adversarial_temperature, positive, negative, weight, weight_sum, B_total,
+                         row_begin, row_count, N, row_loss, pos_row_loss, grad_entity, grad_relation, grad_modulus,
+                         score_out, workspace, workspace_bytes, err_flag, nullptr, stream);
+}
+
+static bool plan_split(const kge_model_t *m, int64_t rows, int64_t N) {
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  const int64_t d = cplx ? m->entity_dim / 2 : m->entity_dim;
+  return ((uintptr_t)m->entity & 15) == 0 && split_path_shape_ok(rows, N, m->entity_dim, d, cplx, m->nentity);
+}
+
+extern "C" int kge_train_plan(const kge_model_t *m, int64_t rows, int64_t N) {
+  if (check_model(m) || rows <= 0 || N <= 0) return 0;
+  // the fit of the kernel's shared-memory carve-up (>= 4 warps next to q, dq, 2N scores) holds for every N that passes
+  // launch_rows' own limit when rows fit one k-tile, except absurdly long candidate lists
+  const bool split = plan_split(m, rows, N) && N <= 8192;
+  return split ? (KGE_PLAN_SINGLE_READ | KGE_PLAN_ENTITY_ADAM) : 0;
+}
+
+extern "C" int kge_train_rows_adam(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                                   const int64_t *positive, const int64_t *negative, const float *weight,
+                                   const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N,
+                                   float *row_loss, float *pos_row_loss, float *grad_relation, float *grad_modulus,
+                                   void *workspace, int64_t workspace_bytes, int32_t *err_flag,
+                                   const kge_entity_adam_t *host_entity_adam, void *stream) {
+  KGE_REQUIRE(m && host_entity_adam && host_entity_adam->exp_avg && host_entity_adam->exp_avg_sq &&
+              host_entity_adam->step >= 1, "bad entity optimizer state");
+  KGE_REQUIRE(loss_kind == KGE_LOSS_NEG_ADVERSARIAL || loss_kind == KGE_LOSS_NEG_UNIFORM, "bad loss_kind %d", loss_kind);
+  KGE_REQUIRE(pos_row_loss && workspace, "the fused optimizer needs pos_row_loss and the workspace");
+  KGE_REQUIRE(row_count == B_total, "the fused entity optimizer is a single-device path (whole batch)");
+  KGE_REQUIRE(kge_train_plan(m, row_count, N) & KGE_PLAN_ENTITY_ADAM,
+              "kge_train_plan does not offer the fused entity optimizer for this shape");
+  KGE_REQUIRE(workspace_bytes >= kge_train_workspace_bytes(m, row_count, N), "workspace too small");
+  const kge_entity_adam_t &o = *host_entity_adam;
+  EntityAdam ea{};
+  ea.exp_avg = o.exp_avg; ea.exp_avg_sq = o.exp_avg_sq;
+  ea.s = adam_scalars(o.lr, o.beta1, o.beta2, o.eps, o.l3_coefficient, o.step);
+  ea.l3 = o.l3_coefficient != 0.0;
+  ea.reg_partials = o.reg_partials; ea.n_reg_partials = o.n_reg_partials;
+  return train_rows_impl(m, mode, loss_kind, adversarial_temperature, positive, negative, weight, weight_sum, B_total, 0,
+                         row_count, N, row_loss, pos_row_loss, nullptr, grad_relation, grad_modulus, nullptr, workspace,
+                         workspace_bytes, err_flag, &ea, stream);
 }
 
 extern "C" int64_t kge_train_workspace_bytes(const kge_model_t *m, int64_t rows, int64_t N) {
@@ -856,7 +337,8 @@ extern "C" int kge_train_rows_begin(const kge_model_t *m, int mode, int loss_kin
   RowArgs a{};
   bool head;
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   a.positive = positive; a.row_begin = row_begin; a.row_count = (int)row_count; a.N = (int)N;
   a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
   a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
@@ -883,23 +365,23 @@ extern "C" int kge_train_entity_pass(const kge_model_t *m, int mode, void *works
   KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "mode %d not supported", mode);
   KGE_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= m->nentity && slice_index >= 0 && slice_index < 16,
               "bad entity slice");
-  if ((rc = set_device(m))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
   const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
   RowArgs a{};
   a.E = m->entity; a.modulus = m->modulus; a.nentity = m->nentity;
   a.De = (int)m->entity_dim; a.d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
   a.scale = phase_scale(m); a.N = (int)N; a.row_count = (int)row_count;
   a.gE = grad_entity; a.gM = grad_modulus; a.do_loss = 1;
-  const SplitWs ws = carve_split_ws(workspace, row_count, N, m->entity_dim, m->nentity);
+  SplitWs ws = carve_split_ws(workspace, row_count, N, m->entity_dim, m->nentity);
+  ws.Dvec = nullptr;                                      // (the sliced multi-GPU flow keeps the dense gradient)
   const bool head = mode == KGE_HEAD_BATCH;
   cudaStream_t st = (cudaStream_t)stream;
   // the persistent entity kernel would otherwise hold every SM and the all-reduce of the previous slice could not start
   const char *rs = getenv("KGE_ENTITY_SMS_RESERVE");
   const int reserve = rs ? atoi(rs) : 0;       // measured at 2 GPUs: 0, 8, 24 equal, 48 slower
-#define KGE_ENT(MODEL)                                                                            \
-  case MODEL:                                                                                     \
-    return head ? launch_entity_pass<MODEL, true>(a, ws, ent_begin, ent_end, slice_index, st, reserve)     \
-                : launch_entity_pass<MODEL, false>(a, ws, ent_begin, ent_end, slice_index, st, reserve);
+#define KGE_ENT(MODEL) \
+  case MODEL: return launch_entity_model<MODEL>(head, a, ws, ent_begin, ent_end, slice_index, st, reserve);
   switch (m->model) {
     KGE_ENT(KGE_TRANSE)
     KGE_ENT(KGE_DISTMULT)

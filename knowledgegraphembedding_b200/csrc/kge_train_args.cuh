@@ -1,0 +1,74 @@
+// kge_train_args.cuh -- argument blocks of the train-path kernels and the host entry points that are instantiated
+// per model in their own translation units (kge_train_inst.cu, built once per model: parallel compiles).
+#pragma once
+#include "kge_adam.cuh"
+#include "kge_rows.cuh"
+
+namespace kge {
+
+// Adam update of the entity table fused into the entity-major pass (kge_train_rows_adam): host-side description
+struct EntityAdam {
+  float *exp_avg, *exp_avg_sq;   // [nentity, De]
+  AdamScalars s;
+  int l3;                        // 1: add 3*l3*x*|x| to the gradient and accumulate sum|x|^3 (model.py:290-297)
+  double *reg_partials;          // [>= grid] doubles, zeroed by the launcher
+  int64_t n_reg_partials;
+};
+
+struct RowArgs {
+  const float *E, *R, *modulus;
+  const int64_t *positive;     // [B_total, 3]
+  const int64_t *cand;         // candidate (b, n) = cand[b * cand_stride + n]
+  int64_t cand_stride;
+  int64_t row_begin;
+  int row_count, N;
+  int64_t nentity, nrelation;
+  int d;                       // k-extent: hidden_dim for complex ops, entity_dim for real ops
+  int De, Dr;
+  float gamma, scale;
+  int do_loss, loss_kind;
+  float alpha;
+  const float *weight, *wsum;
+  float uniform_u;
+  float *row_loss;
+  float *pos_row_loss;         // split path only: also do the positive triple of each row (fused 'single' pass)
+  float *score_out;
+  const float *dscore;
+  float *gE, *gR, *gM;
+  int32_t *err;
+  int *fused_positive;         // host-side out flag: the launched variant handled pos_row_loss itself
+  int defer_entity;            // host: do not launch the entity-major pass (caller slices it, kge_train_entity_pass)
+  int *entity_deferred;        // host out flag: the split path ran and its entity pass is still due
+  const EntityAdam *entity_adam;   // host: fuse the entity table's Adam update into the entity-major pass (or NULL)
+  int *entity_adam_applied;    // host out flag: the update was applied (gE was not written; the caller skips E in Adam)
+};
+
+struct SplitWs {             // carved from the caller's workspace
+  float *G;                  // [rows, N]   dL/ds of every negative pair
+  float *Qtab;               // [rows, De]  query vectors
+  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets
+  int *cursor;               // [nentity]   scatter cursors
+  int *queue;                // [16]        dynamic entity queues of entity_kernel (one per entity slice)
+  int *tile_tot;             // [ceil(nentity / 1024)] totals of the scan tiles
+  int *perm;                 // [rows * (N + 3)]  per entity: row index (b - row_begin) of each of its pairs, or
+                             //             -(1 + i) for the direct gradient row i of Dvec
+  float *gsorted;            // [rows * (N + 3)]  dL/ds of every pair in the same order
+  float *Dvec;               // [rows * 3, De] direct gradient rows (fixed entity, positive head, positive tail), or NULL:
+                             //             those rows are added to gE with atomics instead
+  int *dids;                 // [rows * 3]  target entity of every direct row
+};
+
+size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity);
+SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity);
+// does the launcher take the single-read path for this shape (same predicate in kge_train_plan and launch_rows_model)?
+bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity);
+
+// per-model entry points (explicitly instantiated in kge_train_inst.cu)
+template <int MODEL>
+int launch_rows_model(bool head, const RowArgs &a, bool vec4, int threads, size_t smem, void *workspace,
+                      size_t workspace_bytes, cudaStream_t st);
+template <int MODEL>
+int launch_entity_model(bool head, const RowArgs &a, const SplitWs &ws, int64_t ent_begin, int64_t ent_end, int slot,
+                        cudaStream_t st, int reserve_sms);
+
+}  // namespace kge

@@ -1,0 +1,194 @@
+// kge_train_launch.cuh -- host-side launch logic of the train-path kernels for one model (template over MODEL; the
+// explicit instantiations live in kge_train_inst.cu, one translation unit per model).
+#pragma once
+#include <stdlib.h>
+
+#include "kge_train_split.cuh"
+
+namespace kge {
+
+template <int MODEL, bool HEAD>
+static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_begin, int64_t ent_end, int slot,
+                              cudaStream_t st, int reserve_sms = 0) {
+  constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
+  if (ent_end <= ent_begin) return KGE_OK;
+  const int nunits = a.d / 4;
+  EntArgs e{};
+  e.E = const_cast<float *>(a.E); e.modulus = a.modulus; e.gE = a.gE; e.gM = a.gM; e.gsorted = ws.gsorted;
+  e.Qtab = ws.Qtab; e.Dvec = ws.Dvec;
+  e.off = ws.cnt; e.perm = ws.perm; e.queue = ws.queue + slot; e.nentity = a.nentity;
+  e.ent_begin = ent_begin; e.ent_count = ent_end - ent_begin;
+  e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
+  e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (reserve_sms > 0 && sms > 2 * reserve_sms) sms -= reserve_sms;   // leave SMs for the concurrent NCCL kernel
+  const bool fused = a.entity_adam != nullptr && ws.Dvec != nullptr;
+  if (fused) {
+    const EntityAdam &o = *a.entity_adam;
+    e.exp_avg = o.exp_avg; e.exp_avg_sq = o.exp_avg_sq; e.adam = o.s; e.l3 = o.l3 && o.s.l3x3 != 0.f;
+    e.err = a.err;
+    if (e.l3) {
+      KGE_REQUIRE(o.reg_partials && o.n_reg_partials >= 1, "L3 regularisation needs reg_partials");
+      if (sms > o.n_reg_partials) sms = (int)o.n_reg_partials;
+      KGE_CUDA_OK(cudaMemsetAsync(o.reg_partials, 0, sizeof(double) * o.n_reg_partials, st));
+      e.reg_partials = o.reg_partials;
+    }
+  }
+  const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
+  e.upp = two ? (nunits + 1) / 2 : nunits;
+  // slots have the kernel's compile-time half stride: CH chunks of 32 float4 units, CH = (complex ? 8 : 16) / parts
+  const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * ((CPLX ? 8 : 16) / (two ? 2 : 1)) * 32 * 16;
+  int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
+  const int wmax = entity_warps(two ? 2 : 1, fused);
+  if (We > wmax) We = wmax;
+  const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
+#define KGE_ENT_LAUNCH(S, F)                                                                         \
+  do {                                                                                               \
+    auto k = entity_kernel<MODEL, HEAD, S, F>;                                                       \
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));   \
+    k<<<sms, We * 32, esmem, st>>>(e);                                                               \
+  } while (0)
+  if (two) { if (fused) KGE_ENT_LAUNCH(2, true); else KGE_ENT_LAUNCH(2, false); }
+  else { if (fused) KGE_ENT_LAUNCH(1, true); else KGE_ENT_LAUNCH(1, false); }
+#undef KGE_ENT_LAUNCH
+  KGE_CUDA_OK(cudaGetLastError());
+  if (fused && a.entity_adam_applied) *a.entity_adam_applied = 1;
+  return KGE_OK;
+}
+
+// which register / shared-memory variant of row_kernel_split runs (KGE_SPLIT_VARIANT=0|1|2 overrides; see split_warps)
+static int split_variant() {
+  const char *v = getenv("KGE_SPLIT_VARIANT");
+  if (v && v[0] >= '0' && v[0] <= '2' && !v[1]) return v[0] - '0';
+  return 2;
+}
+
+template <int MODEL, bool HEAD>
+static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, void *workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
+  int grid = a.row_count;
+  // TMA ring variants: rows are 16-byte multiples, one k-tile covers the row, and >= 4 warps get a double buffer
+  constexpr bool CPLX = op_is_complex(op_of(MODEL, HEAD));
+  const int nunits = a.d / 4;
+  const bool want_adam = a.entity_adam != nullptr;
+  if (vec4 && nunits <= 32 * (CPLX ? 8 : 16) && !getenv("KGE_NO_TMA")) {
+    const size_t rowbytes = (size_t)a.De * 4;
+    const bool split = workspace && (a.gE || want_adam) && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
+                       workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
+                       split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity);
+    // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
+    if (split) {
+      constexpr int Hs = CPLX ? 2 : 1;
+      const int chunks = (nunits + 31) / 32;                 // 128-float chunks per half row
+      const int nch = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16);
+      const int var = split_variant();
+      const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
+      const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
+      const size_t per_warp = 2 * hs * sizeof(float) + 16;
+      int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
+      const int wcap = split_warps(CPLX, nch, var);
+      if (Ws > wcap) Ws = wcap;
+      if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
+      if (Ws > wcap) Ws = wcap;
+      if (Ws >= 4 && fixed_s + Ws * per_warp <= 227 * 1024) {
+        const size_t total = fixed_s + Ws * per_warp;
+        SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
+        // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
+        // through ws.Dvec); without it the entity-side rows of the positives go to gE with atomics
+        if (!(want_adam && a.pos_row_loss && !a.defer_entity)) ws.Dvec = nullptr;
+        KGE_REQUIRE(ws.Dvec || a.gE, "grad_entity is required when the entity optimizer is not fused");
+        KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
+        // persistent CTAs (one per SM: the slots take the whole shared memory), rows are dealt round-robin
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int sgrid = grid < sms ? grid : sms;
+#define KGE_SPLIT_LAUNCH2(NCH, VAR)                                                                    \
+  do {                                                                                                 \
+    auto k = row_kernel_split<MODEL, HEAD, NCH, VAR>;                                                  \
+    KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
+    k<<<sgrid, Ws * 32, total, st>>>(a, ws);                                                           \
+  } while (0)
+#define KGE_SPLIT_LAUNCH(NCH)                                                                          \
+  do {                                                                                                 \
+    if (var == 0) KGE_SPLIT_LAUNCH2(NCH, 0);                                                           \
+    else if (var == 1) KGE_SPLIT_LAUNCH2(NCH, 1);                                                      \
+    else KGE_SPLIT_LAUNCH2(NCH, 2);                                                                    \
+  } while (0)
+        if (nch == 4) KGE_SPLIT_LAUNCH(4);
+        else if (nch == 8) KGE_SPLIT_LAUNCH(8);
+        else {
+          if constexpr (CPLX) { set_error("row too wide"); return KGE_ERR_INVALID; }      // unreachable: nunits <= 256
+          else KGE_SPLIT_LAUNCH(16);
+        }
+#undef KGE_SPLIT_LAUNCH
+#undef KGE_SPLIT_LAUNCH2
+        KGE_CUDA_OK(cudaGetLastError());
+        if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
+        {
+          const int tiles = (int)((a.nentity + 1023) / 1024);
+          scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+          KGE_CUDA_OK(cudaGetLastError());
+          scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
+          KGE_CUDA_OK(cudaGetLastError());
+        }
+        {
+          const int64_t pairs = (int64_t)a.row_count * (a.N + (ws.Dvec ? 3 : 0));
+          int g2 = (int)((pairs + 255) / 256);
+          if (g2 > 148 * 16) g2 = 148 * 16;
+          scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
+                                                   ws.G, ws.Dvec ? ws.dids : nullptr, ws.cursor, ws.perm, ws.gsorted);
+          KGE_CUDA_OK(cudaGetLastError());
+        }
+        if (a.defer_entity) {
+          if (a.entity_deferred) *a.entity_deferred = 1;
+          return KGE_OK;
+        }
+        return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
+      }
+    }
+    // ---- two-sweep TMA kernel ------------------------------------------------------------------------------
+    const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
+    const size_t fixed = base + 16;
+    int W = (int)((227 * 1024 - fixed) / (2 * rowbytes + 16));
+    if (W > 16) W = 16;
+    if (a.N < 4 * W) W = a.N >= 16 ? (a.N + 3) / 4 : 4;                // short candidate lists: fewer, busier warps
+    if (W >= 4 && fixed + W * (2 * rowbytes + 16) <= 227 * 1024) {
+      const size_t total = fixed + W * (2 * rowbytes + 16);
+      auto k = row_kernel_tma<MODEL, HEAD>;
+      KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+      k<<<grid, W * 32, total, st>>>(a);
+      KGE_CUDA_OK(cudaGetLastError());
+      return KGE_OK;
+    }
+  }
+  if (vec4) {
+    auto k = row_kernel<MODEL, HEAD, 4>;
+    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, threads, smem, st>>>(a);
+  } else {
+    auto k = row_kernel<MODEL, HEAD, 1>;
+    if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, threads, smem, st>>>(a);
+  }
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+template <int MODEL>
+int launch_rows_model(bool head, const RowArgs &a, bool vec4, int threads, size_t smem, void *workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
+  return head ? launch_rows_v<MODEL, true>(a, vec4, threads, smem, workspace, workspace_bytes, st)
+              : launch_rows_v<MODEL, false>(a, vec4, threads, smem, workspace, workspace_bytes, st);
+}
+
+template <int MODEL>
+int launch_entity_model(bool head, const RowArgs &a, const SplitWs &ws, int64_t ent_begin, int64_t ent_end, int slot,
+                        cudaStream_t st, int reserve_sms) {
+  return head ? launch_entity_pass<MODEL, true>(a, ws, ent_begin, ent_end, slot, st, reserve_sms)
+              : launch_entity_pass<MODEL, false>(a, ws, ent_begin, ent_end, slot, st, reserve_sms);
+}
+
+}  // namespace kge

@@ -1,49 +1,79 @@
-// kge_train_split.cuh -- single-read train path: row-major forward + dL/dq, entity-major dL/dx.
+// kge_train_split.cuh -- single-read train path: row-major forward + dL/dq, entity-major dL/dx (+ Adam).
 //
-// The two-sweep row kernel (kge_train.cu) reads every candidate row twice and scatters dL/dx with
+// The two-sweep row kernel (kge_train_kernels.cuh) reads every candidate row twice and scatters dL/dx with
 // 2.1 GB of atomics into a gradient table that does not fit L2 next to the entity table (ncu r1b:
 // 4.78 GB of DRAM traffic, L2 hit 33 %).  This path reads each candidate row ONCE from global memory:
 //
-//   row_kernel_split   (one CTA per positive row, TMA ring as before)
-//       per candidate: sweep 1 over the shared-memory slot -> score; sweep 2 over the same slot ->
-//       dL/dq contribution, accumulated in registers with a *deferred* softmax normalisation (each warp
-//       keeps a running max M_w of alpha*s and rescales its accumulator when the max grows, exactly like
-//       an online softmax); after the row's loss is known the accumulators are brought to the common
-//       max, folded, scaled by  -/+ u/(2 Z)  and pushed through the chain rule.  It also writes q[b] and
-//       g[b,n] = dL/ds to a workspace and histograms the candidate ids.
+//   row_kernel_split   (persistent, one CTA per SM walking its positive rows, TMA ring per warp)
+//       per candidate: one sweep over the shared-memory slot -> score and u = d(value)/dq, both in registers;
+//       then acc += coef * u with a *deferred* softmax normalisation (each warp keeps a running max M_w of
+//       alpha*s and rescales its accumulator when the max grows, exactly like an online softmax); after the
+//       row's loss is known the accumulators are brought to the common max, folded, scaled by  -/+ u/(2 Z)
+//       and pushed through the chain rule.  It also writes q[b] and g[b,n] = dL/ds to a workspace and
+//       histograms the candidate ids.
 //   scan_tiles + scan_apply / scatter_pairs   counting sort of the (b,n) pairs by candidate entity
-//   entity_kernel      (one warp per entity, dynamic queue) the entity row x_e sits in registers; the q rows
-//       of its pairs (8 MB table, L2 resident) arrive through a TMA double buffer; dL/dx is summed in
-//       registers and added to the gradient row once -- no atomics, no second read of the entity table.
+//   entity_kernel      (one warp per (entity, half row), dynamic queue) the entity row x_e sits in registers; the
+//       q rows of its pairs (8 MB table, L2 resident) arrive through a TMA double buffer; dL/dx is summed in
+//       registers.  Then either the sum is added to the gradient row once (no atomics), or -- fused optimizer,
+//       kge_train_rows_adam -- the gradient rows of the positive triples arrive through the same buffer, and the warp
+//       applies torch.optim.Adam to its slice of the entity row in place: the dense entity gradient never exists.
 //
-// DRAM traffic drops from ~1.1 x A to the first touch of the entity table plus one read-modify-write of the
-// gradient table; the passes become L2-bandwidth / issue bound.
+// DRAM traffic drops from ~1.1 x A to the first touch of the entity table plus (fused optimizer) one read of the two
+// moment tables and one write of tables and moments; the passes are shared-memory-bandwidth / issue bound.
 #pragma once
+#include "kge_train_kernels.cuh"
 
 namespace kge {
-
-struct SplitWs {             // carved from the caller's workspace
-  float *G;                  // [rows, N]   dL/ds of every negative pair
-  float *Qtab;               // [rows, De]  query vectors
-  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets
-  int *cursor;               // [nentity]   scatter cursors
-  int *queue;                // [16]        dynamic entity queues of entity_kernel (one per entity slice)
-  int *tile_tot;             // [ceil(nentity / 1024)] totals of the scan tiles
-  int *perm;                 // [rows * N]  row index (b - row_begin) of every pair, grouped by entity
-  float *gsorted;            // [rows * N]  dL/ds of every pair in the same order
-};
 
 // NCH = 128-float chunks per half row (4, 8 or 16): the halves of a row sit at a fixed padded stride DP = 128 * NCH
 // floats in every shared-memory slot and in q, the pad is zero (and stays zero: every element op maps (q, x) = (0, 0) to
 // value 0 and u 0), so the per-lane loops over the row have compile-time trip counts and immediate address offsets --
 // no bounds guards, no divergence bookkeeping (the guarded version spent 11 % of its instructions on them).
-// 8 KB slots (complex NCH = 8, real NCH = 16) leave room for 13 warps.  Registers stay capped at 128 per thread: one
-// SM sub-partition holds 4 of the 13 warps (4 x 32 x 128 = its 16 K registers).  Measured alternative: 12 warps with
-// 168 registers (no cap) is 1 % slower (0.705 vs 0.699 ms per cfg-3 launch) -- the extra warp is worth more than the ILP.
-__host__ __device__ constexpr int split_max_threads(bool cplx, int nch) { return (cplx ? 2 : 1) * nch >= 16 ? 416 : 512; }
+//
+// VAR picks where a lane keeps u = d(value)/dq between the score sweep and the accumulate step, and where q lives:
+//   0  u parked in the slot (STS + second LDS pass + a proxy fence per candidate), q in shared memory   [round 1]
+//   1  u in registers, q in shared memory
+//   2  u and q in registers: per candidate the only shared-memory traffic is one read of the row
+// ncu r1l showed variant 0 bound by shared-memory bandwidth (40 KB moved per 8 KB candidate row: TMA write, x, q,
+// u out, u back); variants 1 / 2 move 24 / 16 KB.  The register footprint (acc + u [+ q] = 2-3 x the lane's share of the
+// row) sets the warp count: f = chunks per lane (H * NCH).
+__host__ __device__ constexpr int split_warps(bool cplx, int nch, int var) {
+  const int f = (cplx ? 2 : 1) * nch;
+  if (var == 0) return f >= 16 ? 13 : 16;                 // 13 x 32 x 128 registers; 8 KB slots
+  if (var == 1) return f >= 16 ? 12 : 16;                 // 128 + ~45 registers -> 168 at 12 warps (3 per sub-partition)
+  return f >= 16 ? 8 : (f >= 8 ? 12 : 16);                // 192 + ~45 -> 255 at 8 warps; 96 + 45 -> 168 at 12
+}
 
-template <int MODEL, bool HEAD, int NCH>
-__global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, HEAD)), NCH), 1)
+// element value and u for one 4-float group (both halves); OP_CDIST runs on packed pairs (FADD2 / FMUL2 / FFMA2)
+template <int OP>
+__device__ __forceinline__ void unit_group(const float (&q0)[4], const float (&q1)[4], const float (&x0)[4],
+                                           const float (&x1)[4], float scale, f2 (&u0)[2], f2 (&u1)[2], float &part,
+                                           f2 &part2) {
+  if constexpr (OP == OP_CDIST) {
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      const f2 av = sub2(pack2(q0[j], q0[j + 1]), pack2(x0[j], x0[j + 1]));
+      const f2 bv = sub2(pack2(q1[j], q1[j + 1]), pack2(x1[j], x1[j + 1]));
+      const f2 m2 = fma2(bv, bv, mul2(av, av));
+      float m2a, m2b;
+      unpack2(m2, m2a, m2b);
+      // 1/|q - x|; at q == x the differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
+      const f2 inv = pack2(rsqrt_fast(fmaxf(m2a, kFltMin)), rsqrt_fast(fmaxf(m2b, kFltMin)));
+      u0[j >> 1] = mul2(av, inv);
+      u1[j >> 1] = mul2(bv, inv);
+      part2 = fma2(m2, inv, part2);                        // += |q - x|
+    }
+  } else {
+    float a0[4], a1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part += op_unit<OP>(q0[j], q1[j], x0[j], x1[j], scale, a0[j], a1[j]);
+    u0[0] = pack2(a0[0], a0[1]); u0[1] = pack2(a0[2], a0[3]);
+    u1[0] = pack2(a1[0], a1[1]); u1[1] = pack2(a1[2], a1[3]);
+  }
+}
+
+template <int MODEL, bool HEAD, int NCH, int VAR>
+__global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)), NCH, VAR) * 32, 1)
     row_kernel_split(const RowArgs a, const SplitWs ws) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
@@ -51,6 +81,7 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
   constexpr int V = 4;
   constexpr int DP = 128 * NCH;                 // padded half length (floats)
   constexpr int HS = H * DP;                    // slot size (floats)
+  constexpr bool UREG = VAR >= 1, QREG = VAR >= 2;
   extern __shared__ __align__(128) float smem[];
   const int Dq4 = (a.De + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -138,43 +169,76 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
     __syncthreads();
 
     // ---- phase 1: per candidate, score (sweep 1) and deferred-normalised dL/dq (sweep 2) ------------------
-    float acc[NCH][H][V];
+    f2 acc[NCH][H][2];
 #pragma unroll
     for (int i = 0; i < NCH; ++i)
 #pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[i][h][j] = 0.f;
+      for (int h = 0; h < H; ++h) { acc[i][h][0] = pack2(0.f, 0.f); acc[i][h][1] = pack2(0.f, 0.f); }
     float Mw = -INFINITY;                                  // running max of alpha * s over this warp's rows
     const float *ql = q + lane * V;
+    float qr[QREG ? NCH : 1][H][V];
+    if constexpr (QREG) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        load_shared<V>(qr[i][0], ql + i * 128);
+        if constexpr (CPLX) load_shared<V>(qr[i][1], ql + DP + i * 128);
+      }
+    }
     {
       int it = 0;
       for (int n = warp; n < a.N; n += nwarps, ++it) {
         const int s = (it + fs) & 1;
         if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
         float *xl = (s ? slot1 : slot0) + lane * V;
-        // sweep 1: element values -> score; u = d(value)/dq is parked in the slot (in place of x)
+        // sweep 1: element values -> score; u = d(value)/dq stays in registers (VAR >= 1) or is parked in the slot
         float part = 0.f;
+        f2 part2 = pack2(0.f, 0.f);
+        f2 u[UREG ? NCH : 1][H][2];
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          float x0[V], x1[V], q0[V], q1[V], u0[V], u1[V];
+          float x0[V], x1[V], q0[V], q1[V];
           load_shared<V>(x0, xl + i * 128);
-          load_shared<V>(q0, ql + i * 128);
-          if constexpr (CPLX) {
-            load_shared<V>(x1, xl + DP + i * 128);
-            load_shared<V>(q1, ql + DP + i * 128);
-          }
+          if constexpr (CPLX) load_shared<V>(x1, xl + DP + i * 128);
+          if constexpr (QREG) {
 #pragma unroll
-          for (int j = 0; j < V; ++j)
-            part += op_unit<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[j], CPLX ? x1[j] : 0.f, a.scale, u0[j], u1[j]);
-          if constexpr (!op_unit_is_x(OP)) {
-            *reinterpret_cast<float4 *>(xl + i * 128) = make_float4(u0[0], u0[1], u0[2], u0[3]);
-            if constexpr (CPLX) *reinterpret_cast<float4 *>(xl + DP + i * 128) = make_float4(u1[0], u1[1], u1[2], u1[3]);
+            for (int j = 0; j < V; ++j) { q0[j] = qr[i][0][j]; if constexpr (CPLX) q1[j] = qr[i][1][j]; }
+          } else {
+            load_shared<V>(q0, ql + i * 128);
+            if constexpr (CPLX) load_shared<V>(q1, ql + DP + i * 128);
           }
+          if constexpr (!CPLX) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) { x1[j] = 0.f; q1[j] = 0.f; }
+          }
+          f2 u0[2], u1[2];
+          unit_group<OP>(q0, q1, x0, x1, a.scale, u0, u1, part, part2);
+          if constexpr (UREG) {
+            u[i][0][0] = u0[0]; u[i][0][1] = u0[1];
+            if constexpr (CPLX) { u[i][1][0] = u1[0]; u[i][1][1] = u1[1]; }
+          } else if constexpr (!op_unit_is_x(OP)) {
+            float t0, t1, t2, t3;
+            unpack2(u0[0], t0, t1); unpack2(u0[1], t2, t3);
+            *reinterpret_cast<float4 *>(xl + i * 128) = make_float4(t0, t1, t2, t3);
+            if constexpr (CPLX) {
+              unpack2(u1[0], t0, t1); unpack2(u1[1], t2, t3);
+              *reinterpret_cast<float4 *>(xl + DP + i * 128) = make_float4(t0, t1, t2, t3);
+            }
+          }
+        }
+        if constexpr (OP == OP_CDIST) {
+          float pa, pb;
+          unpack2(part2, pa, pb);
+          part = pa + pb;
         }
         float coef;
         if (a.do_loss) {
           part = warp_sum(part);
+          if constexpr (UREG) {
+            // every lane's reads of the slot fed the reduction above: the slot can take the next row already, while
+            // the softmax bookkeeping and the accumulate step run from registers
+            __syncwarp();
+            if (n + 2 * nwarps < a.N) issue(s, it + 2);
+          }
           const float sv = finish_score<MODEL>(part, a.gamma, modulus);
           if (lane == 0) {
             sc[n] = sv;
@@ -184,12 +248,11 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
             const float z = sv * a.alpha;
             if (z > Mw) {
               const float r = expf(Mw - z);                // 0 on the first row (Mw = -inf)
+              const f2 r2 = pack2(r, r);
 #pragma unroll
               for (int i = 0; i < NCH; ++i)
 #pragma unroll
-                for (int h = 0; h < H; ++h)
-#pragma unroll
-                  for (int j = 0; j < V; ++j) acc[i][h][j] *= r;
+                for (int h = 0; h < H; ++h) { acc[i][h][0] = mul2(acc[i][h][0], r2); acc[i][h][1] = mul2(acc[i][h][1], r2); }
               Mw = z;
             }
             coef = expf(z - Mw) * sigmoid(sv);
@@ -198,23 +261,39 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
           }
         } else {
           coef = a.dscore[(int64_t)rl * a.N + n];          // autograd backward: dL/ds is given
-        }
-        // sweep 2: acc += coef * u  (each lane re-reads exactly the slot words it wrote)
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          float u0[V], u1[V];
-          load_shared<V>(u0, xl + i * 128);
-          if constexpr (CPLX) load_shared<V>(u1, xl + DP + i * 128);
-#pragma unroll
-          for (int j = 0; j < V; ++j) {
-            acc[i][0][j] = fmaf(coef, u0[j], acc[i][0][j]);
-            if constexpr (CPLX) acc[i][1][j] = fmaf(coef, u1[j], acc[i][1][j]);
+          if constexpr (UREG) {
+            __syncwarp();
+            if (n + 2 * nwarps < a.N) issue(s, it + 2);
           }
         }
-        // the slot was rewritten with generic stores: order them before the bulk engine's next write to it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (n + 2 * nwarps < a.N) issue(s, it + 2);
+        // sweep 2: acc += coef * u
+        const f2 c2 = pack2(coef, coef);
+        if constexpr (UREG) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              acc[i][h][0] = fma2(c2, u[i][h][0], acc[i][h][0]);
+              acc[i][h][1] = fma2(c2, u[i][h][1], acc[i][h][1]);
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {                  // each lane re-reads exactly the slot words it wrote
+            float u0[V], u1[V];
+            load_shared<V>(u0, xl + i * 128);
+            if constexpr (CPLX) load_shared<V>(u1, xl + DP + i * 128);
+            acc[i][0][0] = fma2(c2, pack2(u0[0], u0[1]), acc[i][0][0]);
+            acc[i][0][1] = fma2(c2, pack2(u0[2], u0[3]), acc[i][0][1]);
+            if constexpr (CPLX) {
+              acc[i][1][0] = fma2(c2, pack2(u1[0], u1[1]), acc[i][1][0]);
+              acc[i][1][1] = fma2(c2, pack2(u1[2], u1[3]), acc[i][1][1]);
+            }
+          }
+          // the slot was rewritten with generic stores: order them before the bulk engine's next write to it
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (n + 2 * nwarps < a.N) issue(s, it + 2);
+        }
       }
     }
     if (has_next) {                                        // next row, candidate 0 -> slot 1 (slot 0 parks the fold)
@@ -274,13 +353,16 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
     // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
     {
       float *pl = slot0 + lane * V;
+      const f2 f2v = pack2(factor, factor);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        *reinterpret_cast<float4 *>(pl + i * 128) =
-            make_float4(acc[i][0][0] * factor, acc[i][0][1] * factor, acc[i][0][2] * factor, acc[i][0][3] * factor);
-        if constexpr (CPLX)
-          *reinterpret_cast<float4 *>(pl + DP + i * 128) =
-              make_float4(acc[i][1][0] * factor, acc[i][1][1] * factor, acc[i][1][2] * factor, acc[i][1][3] * factor);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float t0, t1, t2, t3;
+          unpack2(mul2(acc[i][h][0], f2v), t0, t1);
+          unpack2(mul2(acc[i][h][1], f2v), t2, t3);
+          *reinterpret_cast<float4 *>(pl + h * DP + i * 128) = make_float4(t0, t1, t2, t3);
+        }
       }
     }
     __syncthreads();
@@ -294,14 +376,21 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
     __syncthreads();
     if (has_next && warp + nwarps < a.N) issue(0, 1);      // next row, candidate 1 -> slot 0
     // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
-    float *gF = a.gE + fid * a.De;
+    // With the fused optimizer (ws.Dvec) the entity-side gradient rows are written to the workspace and reach the
+    // entity-major pass as "direct" entries of their target entity; otherwise they are added to gE with atomics.
+    float *gF = ws.Dvec ? ws.Dvec + (size_t)(3 * rl) * a.De : a.gE + fid * a.De;
     float *gRr = a.gR + rid * a.Dr;
     for (int k = tid; k < a.d; k += blockDim.x) {
       float dF0, dF1, dR0, dR1;
       chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
-      red_add1(gF + k, dF0);
+      if (ws.Dvec) {
+        gF[k] = dF0;
+        if constexpr (CPLX) gF[a.d + k] = dF1;
+      } else {
+        red_add1(gF + k, dF0);
+        if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
+      }
       red_add1(gRr + k, dR0);
-      if constexpr (CPLX) red_add1(gF + a.d + k, dF1);
       if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
     }
     // ---- fused positive triple (model.py:277-279, 'single' mode = the non-head-batch association): the block
@@ -312,6 +401,11 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
       int64_t ph = hid, pt = tidx;
       if ((uint64_t)ph >= (uint64_t)a.nentity) ph = 0;
       if ((uint64_t)pt >= (uint64_t)a.nentity) pt = 0;
+      if (ws.Dvec && tid < 3) {                             // direct entries of this row: (fixed, head, tail)
+        const int64_t target = tid == 0 ? fid : (tid == 1 ? ph : pt);
+        ws.dids[3 * rl + tid] = (int)target;
+        atomicAdd(ws.cnt + target, 1);
+      }
       const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
       for (int k = tid; k < a.d; k += blockDim.x) build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q, DP);
       __syncthreads();
@@ -327,22 +421,33 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
         if constexpr (MODEL == KGE_PROTATE) { if (a.gM) red_add1(a.gM, -gp * part); }
       }
       const float gop = dsum_of<MODEL>(gp, modulus);
-      float *gT = a.gE + pt * a.De;
+      float *gT = ws.Dvec ? ws.Dvec + (size_t)(3 * rl + 2) * a.De : a.gE + pt * a.De;
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dq0 = 0.f, dq1 = 0.f, dx0 = 0.f, dx1 = 0.f;
         op_backward<OPS>(q[k], CPLX ? q[DP + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale, gop, dq0, dq1, dx0, dx1);
         dq[k] = dq0;
-        red_add1(gT + k, dx0);
-        if constexpr (CPLX) { dq[a.d + k] = dq1; red_add1(gT + a.d + k, dx1); }
+        if constexpr (CPLX) dq[a.d + k] = dq1;
+        if (ws.Dvec) {
+          gT[k] = dx0;
+          if constexpr (CPLX) gT[a.d + k] = dx1;
+        } else {
+          red_add1(gT + k, dx0);
+          if constexpr (CPLX) red_add1(gT + a.d + k, dx1);
+        }
       }
       __syncthreads();
-      float *gH = a.gE + ph * a.De;
+      float *gH = ws.Dvec ? ws.Dvec + (size_t)(3 * rl + 1) * a.De : a.gE + ph * a.De;
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dF0, dF1, dR0, dR1;
         chain_q<MODEL, false>(Hrow, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
-        red_add1(gH + k, dF0);
+        if (ws.Dvec) {
+          gH[k] = dF0;
+          if constexpr (CPLX) gH[a.d + k] = dF1;
+        } else {
+          red_add1(gH + k, dF0);
+          if constexpr (CPLX) red_add1(gH + a.d + k, dF1);
+        }
         red_add1(gRr + k, dR0);
-        if constexpr (CPLX) red_add1(gH + a.d + k, dF1);
         if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
       }
     }
@@ -352,83 +457,20 @@ __global__ void __launch_bounds__(split_max_threads(op_is_complex(op_of(MODEL, H
   }
 }
 
-// Exclusive scan of the histogram cnt[0..n) -> offsets (in place), cursor = copy, cnt[n] = total.  Two launches over
-// 1024-entry tiles (a single-CTA scan cost 18 us at FB15k's 14,951 entities and 157 us at YAGO3-10's 123,182):
-// scan_tiles_kernel scans each tile and leaves its total, scan_apply_kernel adds the totals of the preceding tiles.
-__device__ __forceinline__ int block_exclusive_scan_1024(int v, int *warp_tot, int &total) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_tot[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int t = warp_tot[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int s = __shfl_up_sync(0xffffffffu, t, o);
-      if (lane >= o) t += s;
-    }
-    warp_tot[lane] = t;                                    // inclusive totals of the warps
-  }
-  __syncthreads();
-  total = warp_tot[31];
-  return (warp ? warp_tot[warp - 1] : 0) + incl - v;
-}
-
+// counting sort of the pairs by candidate entity (definitions in kge_train.cu)
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(const int *__restrict__ cnt, int *__restrict__ cursor,
-                                                          int *__restrict__ tile_tot, int64_t n) {
-  __shared__ int warp_tot[32];
-  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-  int total;
-  const int excl = block_exclusive_scan_1024(i < n ? cnt[i] : 0, warp_tot, total);
-  if (i < n) cursor[i] = excl;                             // offset inside the tile
-  if (threadIdx.x == 0) tile_tot[blockIdx.x] = total;
-}
-
+                                                          int *__restrict__ tile_tot, int64_t n);
 __global__ void __launch_bounds__(1024) scan_apply_kernel(int *__restrict__ cnt, int *__restrict__ cursor,
-                                                          const int *__restrict__ tile_tot, int64_t n) {
-  __shared__ int warp_tot[32];
-  __shared__ int prefix_sh;
-  // sum of the totals of tiles [0, blockIdx.x): every thread adds a strided share, one block reduction
-  int part = 0;
-  for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) part += tile_tot[t];
-  int total;
-  block_exclusive_scan_1024(part, warp_tot, total);
-  if (threadIdx.x == 0) prefix_sh = total;
-  __syncthreads();
-  const int prefix = prefix_sh;
-  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-  if (i < n) {
-    const int o = cursor[i] + prefix;
-    cnt[i] = o;
-    cursor[i] = o;
-  }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cnt[n] = prefix + tile_tot[blockIdx.x];
-}
-
+                                                          const int *__restrict__ tile_tot, int64_t n);
 __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
-                                     int N, int64_t nentity, const float *__restrict__ G, int *__restrict__ cursor,
-                                     int *__restrict__ perm, float *__restrict__ gsorted) {
-  const int64_t total = (int64_t)rows * N;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    const int rl = (int)(p / N), n = (int)(p % N);
-    int64_t id = cand[(row_begin + rl) * cand_stride + n];
-    if ((uint64_t)id >= (uint64_t)nentity) id = 0;
-    const int pos = atomicAdd(cursor + id, 1);
-    perm[pos] = rl;                                        // the entity pass only needs the q row and dL/ds
-    gsorted[pos] = G[p];
-  }
-}
+                                     int N, int64_t nentity, const float *__restrict__ G, const int *__restrict__ dids,
+                                     int *__restrict__ cursor, int *__restrict__ perm, float *__restrict__ gsorted);
 
 struct EntArgs {
-  const float *E;
+  float *E;                  // read; written in place by the fused optimizer
   const float *modulus;
   float *gE, *gM;
-  const float *gsorted, *Qtab;
+  const float *gsorted, *Qtab, *Dvec;
   const int *off, *perm;
   int *queue;
   int64_t nentity;
@@ -437,13 +479,26 @@ struct EntArgs {
   int upp;                   // units (float4) per part: ceil(nunits / S)
   float scale;
   int need_gmod;             // backward-only pRotatE: accumulate d/dmodulus here
+  // fused optimizer (FUSED instantiations)
+  float *exp_avg, *exp_avg_sq;
+  AdamScalars adam;
+  int l3;
+  double *reg_partials;      // [gridDim.x]
+  const int32_t *err;        // a bad index in this step cancels the update (model.py:86-146 raises before the optimizer)
 };
 
 // One warp per (entity, part) task, S parts per row.  dL/dx is element-wise (no row reduction), so splitting the
 // k axis needs no exchange between warps; S = 2 halves the per-thread registers (x and the accumulators) and the
-// slot size, which doubles the resident warps (24 per SM) for latency hiding.
-template <int MODEL, bool HEAD, int S>
-__global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const EntArgs a) {
+// slot size, which doubles the resident warps (20 per SM; 16 with the fused optimizer, whose epilogue holds a half
+// row of both moments next to x and the sums: 128 registers) for latency hiding.
+__host__ __device__ constexpr int entity_warps(int parts, bool fused) { return parts == 1 ? 12 : (fused ? 16 : 20); }
+
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int MODEL, bool HEAD, int S, bool FUSED>
+__global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(const EntArgs a) {
   constexpr int OP = op_of(MODEL, HEAD);
   constexpr bool CPLX = op_is_complex(OP);
   constexpr int H = CPLX ? 2 : 1;
@@ -460,9 +515,13 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
   uint32_t par0 = 0, par1 = 0;
   float g0 = 0.f, g1 = 0.f;
+  int r0 = 0, r1 = 0;                                       // perm entries of the two slots (FUSED: < 0 = direct row)
   const int nunits = a.d / V;
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const int64_t ntasks = a.ent_count * S;
+  if constexpr (FUSED) {
+    if (a.err && *a.err) return;
+  }
 
   for (int i = tid; i < 2 * nwarps * slot_floats; i += blockDim.x) smem[i] = 0.f;     // finite pads from the start
   if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
@@ -471,6 +530,7 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
   __syncthreads();
 
   float gmod = 0.f;
+  double racc = 0.0;
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(a.queue, 1);
@@ -480,7 +540,8 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
     const int beg = a.off[e], end = a.off[e + 1];
     const int ubeg = part * a.upp;                          // first unit of this part
     const int ucnt = min(a.upp, nunits - ubeg);             // units in this part
-    if (beg == end || ucnt <= 0) continue;
+    if (ucnt <= 0) continue;
+    if (!FUSED && beg == end) continue;                     // (the fused optimizer also updates untouched entities)
     const uint32_t segbytes = (uint32_t)ucnt * V * 4u;
 
     // (row index, dL/ds) of the entity's pairs are fetched 32 at a time, one coalesced load per lane, and handed out
@@ -497,26 +558,39 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
       if (i >= pbase + 32) refill(i);
       const int row = __shfl_sync(0xffffffffu, prow, i - pbase);
       const float g = __shfl_sync(0xffffffffu, pg, i - pbase);
-      if (s) g1 = g; else g0 = g;
+      if (s) { g1 = g; r1 = row; } else { g0 = g; r0 = row; }
       if (lane == 0) {
         uint64_t *bar = s ? bar1 : bar0;
         float *dst = s ? slot1 : slot0;
-        const float *src = a.Qtab + (size_t)row * a.De + ubeg * V;
+        const float *src = (FUSED && row < 0 ? a.Dvec + (size_t)(-row - 1) * a.De : a.Qtab + (size_t)row * a.De) + ubeg * V;
         mbar_expect_tx(bar, segbytes * H);
         bulk_g2s(dst, src, segbytes, bar);
         if constexpr (CPLX) bulk_g2s(dst + HSTR, src + a.d, segbytes, bar);
       }
     };
-    issue(0, beg);
+    if (beg < end) issue(0, beg);
     if (beg + 1 < end) issue(1, beg + 1);
+    if constexpr (FUSED) {
+      if (lane == 0) {                                      // the moments of this slice are needed at the end of the task
+        const size_t mb = (size_t)e * a.De + ubeg * V;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          prefetch_l2(a.exp_avg + mb + (size_t)h * a.d, segbytes);
+          prefetch_l2(a.exp_avg_sq + mb + (size_t)h * a.d, segbytes);
+        }
+      }
+    }
 
-    const float *xrow = a.E + (size_t)e * a.De + ubeg * V;
-    float x0[CH][V], x1[CPLX ? CH : 1][V], acc[CH][H][V];
+    float *xrow = a.E + (size_t)e * a.De + ubeg * V;
+    float x0[CH][V], x1[CPLX ? CH : 1][V];
+    f2 acc[CH][H][2];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int u = lane + 32 * i;
 #pragma unroll
-      for (int j = 0; j < V; ++j) { x0[i][j] = 0.f; acc[i][0][j] = 0.f; if constexpr (CPLX) { x1[i][j] = 0.f; acc[i][1][j] = 0.f; } }
+      for (int j = 0; j < V; ++j) { x0[i][j] = 0.f; if constexpr (CPLX) x1[i][j] = 0.f; }
+#pragma unroll
+      for (int h = 0; h < H; ++h) { acc[i][h][0] = pack2(0.f, 0.f); acc[i][h][1] = pack2(0.f, 0.f); }
       if (u < ucnt) {
         load_global<V>(x0[i], xrow + u * V);
         if constexpr (CPLX) load_global<V>(x1[i], xrow + a.d + u * V);
@@ -530,23 +604,65 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
       if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
       const float *ql = (s ? slot1 : slot0) + lane * V;
       const float g = s ? g1 : g0;
+      const int row = s ? r1 : r0;
       const float go = dsum_of<MODEL>(g, modulus);
       float vsum = 0.f;
+      if (FUSED && row < 0) {
+        // a gradient row of a positive triple (written by the row kernel): plain sum
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        if (c < nact) {                                     // warp-uniform; no per-lane bounds guard (see HSTR)
-          float q0[V], q1[V];
-          load_shared<V>(q0, ql + c * 128);
-          if constexpr (CPLX) load_shared<V>(q1, ql + HSTR + c * 128);
+        for (int c = 0; c < CH; ++c) {
+          if (c < nact) {
+            float q0[V], q1[V];
+            load_shared<V>(q0, ql + c * 128);
+            acc[c][0][0] = add2(acc[c][0][0], pack2(q0[0], q0[1]));
+            acc[c][0][1] = add2(acc[c][0][1], pack2(q0[2], q0[3]));
+            if constexpr (CPLX) {
+              load_shared<V>(q1, ql + HSTR + c * 128);
+              acc[c][1][0] = add2(acc[c][1][0], pack2(q1[0], q1[1]));
+              acc[c][1][1] = add2(acc[c][1][1], pack2(q1[2], q1[3]));
+            }
+          }
+        }
+      } else {
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            float dq0, dq1, ex0 = 0.f, ex1 = 0.f;
-            float xb = 0.f;
-            if constexpr (CPLX) xb = x1[c][j];
-            const float val = op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[c][j], xb, a.scale, go, dq0, dq1, ex0, ex1);
-            if constexpr (MODEL == KGE_PROTATE) vsum += (lane + 32 * c < ucnt) ? val : 0.f;   // pads must not count
-            acc[c][0][j] += ex0;
-            if constexpr (CPLX) acc[c][1][j] += ex1;
+        for (int c = 0; c < CH; ++c) {
+          if (c < nact) {                                   // warp-uniform; no per-lane bounds guard (see HSTR)
+            float q0[V], q1[V];
+            load_shared<V>(q0, ql + c * 128);
+            if constexpr (CPLX) load_shared<V>(q1, ql + HSTR + c * 128);
+            if constexpr (OP == OP_CDIST) {
+              // RotatE: d|q - x| / dx on packed pairs (FADD2 / FMUL2 / FFMA2): acc -= (q - x) * go / |q - x|,
+              // zero at q == x like the scalar form
+              const f2 ngo = pack2(-go, -go);
+#pragma unroll
+              for (int j = 0; j < V; j += 2) {
+                const f2 av = sub2(pack2(q0[j], q0[j + 1]), pack2(x0[c][j], x0[c][j + 1]));
+                const f2 bv = sub2(pack2(q1[j], q1[j + 1]), pack2(x1[c][j], x1[c][j + 1]));
+                const f2 m2 = fma2(bv, bv, mul2(av, av));
+                float m2a, m2b;
+                unpack2(m2, m2a, m2b);
+                const f2 inv = mul2(pack2(rsqrt_fast(fmaxf(m2a, kFltMin)), rsqrt_fast(fmaxf(m2b, kFltMin))), ngo);
+                acc[c][0][j >> 1] = fma2(av, inv, acc[c][0][j >> 1]);
+                acc[c][1][j >> 1] = fma2(bv, inv, acc[c][1][j >> 1]);
+              }
+            } else {
+              float ex0[V], ex1[V];
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                float dq0, dq1;
+                ex0[j] = 0.f; ex1[j] = 0.f;
+                float xb = 0.f;
+                if constexpr (CPLX) xb = x1[c][j];
+                const float val = op_backward<OP>(q0[j], CPLX ? q1[j] : 0.f, x0[c][j], xb, a.scale, go, dq0, dq1, ex0[j], ex1[j]);
+                if constexpr (MODEL == KGE_PROTATE) vsum += (lane + 32 * c < ucnt) ? val : 0.f;   // pads must not count
+              }
+              acc[c][0][0] = add2(acc[c][0][0], pack2(ex0[0], ex0[1]));
+              acc[c][0][1] = add2(acc[c][0][1], pack2(ex0[2], ex0[3]));
+              if constexpr (CPLX) {
+                acc[c][1][0] = add2(acc[c][1][0], pack2(ex1[0], ex1[1]));
+                acc[c][1][1] = add2(acc[c][1][1], pack2(ex1[2], ex1[3]));
+              }
+            }
           }
         }
       }
@@ -556,20 +672,67 @@ __global__ void __launch_bounds__(S == 1 ? 384 : 640, 1) entity_kernel(const Ent
         if (a.need_gmod) gmod += -g * warp_sum(vsum);
       }
     }
-    // one fire-and-forget 16-byte reduction per float4 of the (half) gradient row: this warp is the only writer of
-    // these words in this kernel, so the sum is as deterministic as a store, and no load latency is exposed
-    float *grow = a.gE + (size_t)e * a.De + ubeg * V;
+    if constexpr (FUSED) {
+      // torch.optim.Adam on this warp's slice of the entity row, in place: p is in registers (x), g is the sum above
+      const size_t base = (size_t)e * a.De + ubeg * V;
+      const bool l3 = a.l3 != 0;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int u = lane + 32 * c;
-      if (u < ucnt) {
-        red_add4(grow + u * V, acc[c][0][0], acc[c][0][1], acc[c][0][2], acc[c][0][3]);
-        if constexpr (CPLX) red_add4(grow + a.d + u * V, acc[c][1][0], acc[c][1][1], acc[c][1][2], acc[c][1][3]);
+      for (int h = 0; h < H; ++h) {
+        const size_t hb = base + (size_t)h * a.d;
+        float mm[CH][V], vv[CH][V];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int u = lane + 32 * c;
+          if (u < ucnt) {
+            load_global<V>(mm[c], a.exp_avg + hb + u * V);
+            load_global<V>(vv[c], a.exp_avg_sq + hb + u * V);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int u = lane + 32 * c;
+          if (u < ucnt) {
+            float p[V], g[V];
+            unpack2(acc[c][h][0], g[0], g[1]);
+            unpack2(acc[c][h][1], g[2], g[3]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              p[j] = h == 0 ? x0[c][j] : x1[CPLX ? c : 0][j];
+              adam_elem(p[j], g[j], mm[c][j], vv[c][j], a.adam, l3, racc);
+            }
+            *reinterpret_cast<float4 *>(a.E + hb + u * V) = make_float4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<float4 *>(a.exp_avg + hb + u * V) = make_float4(mm[c][0], mm[c][1], mm[c][2], mm[c][3]);
+            *reinterpret_cast<float4 *>(a.exp_avg_sq + hb + u * V) = make_float4(vv[c][0], vv[c][1], vv[c][2], vv[c][3]);
+          }
+        }
+      }
+    } else {
+      // one fire-and-forget 16-byte reduction per float4 of the (half) gradient row: this warp is the only writer of
+      // these words in this kernel, so the sum is as deterministic as a store, and no load latency is exposed
+      float *grow = a.gE + (size_t)e * a.De + ubeg * V;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int u = lane + 32 * c;
+        if (u < ucnt) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            float t0, t1, t2, t3;
+            unpack2(acc[c][h][0], t0, t1);
+            unpack2(acc[c][h][1], t2, t3);
+            red_add4(grow + h * a.d + u * V, t0, t1, t2, t3);
+          }
+        }
       }
     }
   }
   if constexpr (MODEL == KGE_PROTATE) {
     if (a.need_gmod && lane == 0 && gmod != 0.f && a.gM) red_add1(a.gM, gmod);
+  }
+  if constexpr (FUSED) {
+    if (a.l3 && a.reg_partials) {                           // sum |x|^3 of the pre-update values (model.py:292-295)
+      for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+      if (lane == 0) atomicAdd(a.reg_partials + blockIdx.x, racc);
+    }
   }
 }
 

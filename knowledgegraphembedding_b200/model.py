@@ -143,6 +143,8 @@ class KGEModel(nn.Module):
 
         self._ws = {}           # lazily allocated device workspaces (not part of state_dict)
         self._filter_cache = None
+        self._prefetched = {}   # id(iterator) -> batch held ahead (opt-in input pipelining, see _prefetch_batch)
+        self.prefetch_batches = False
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _device(self):
@@ -181,7 +183,8 @@ class KGEModel(nn.Module):
                 raise ValueError('embedding tables must be contiguous float32')
         dev = entity.device
         return _lib.KgeModelStruct(
-            model=_lib.MODEL_IDS[name or self.model_name], device=dev.index or 0,
+            model=_lib.MODEL_IDS[name or self.model_name],
+            device=dev.index if dev.index is not None else torch.cuda.current_device(),
             nentity=entity.shape[0], nrelation=relation.shape[0],
             hidden_dim=entity.shape[1] // 2 if (name or self.model_name) in ('RotatE', 'ComplEx') else entity.shape[1],
             entity_dim=entity.shape[1], relation_dim=relation.shape[1],
@@ -195,6 +198,7 @@ class KGEModel(nn.Module):
             buf = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
             self._ws[key] = buf
             self._ws.pop('grad_views', None)
+            self._ws.pop('grad_views_small', None)
         return buf
 
     def _err_flag(self):
@@ -313,25 +317,28 @@ class KGEModel(nn.Module):
             self._ws['peer'] = peer
         return peer
 
-    def _grad_workspace(self, B):
+    def _grad_workspace(self, B, entity_grad=True):
         """One flat fp32 buffer [dE | dR | dModulus(4) | pos_row[B] | neg_row[B]] so that the multi-GPU
         exchange covers it in one piece (peer-visible memory when the NVLink exchange is active), plus the small
-        scalar buffers."""
+        scalar buffers.  With entity_grad=False (the entity table's Adam update is fused into the backward,
+        kge_train_rows_adam) the dE part does not exist."""
         dev = self.entity_embedding.device
         nE, nR = self.entity_embedding.numel(), self.relation_embedding.numel()
         nE4, nR4 = (nE + 3) // 4 * 4, (nR + 3) // 4 * 4
+        if not entity_grad:
+            nE = nE4 = 0
         total = nE4 + nR4 + 4 + 2 * B
-        peer = self._peer_exchange(total)
-        cached = self._ws.get('grad_views')
+        peer = self._peer_exchange(total) if entity_grad else None
+        cached = self._ws.get('grad_views' if entity_grad else 'grad_views_small')
         if cached is not None and cached[0] == (B, dev, peer is not None):
             return dict(cached[1])
         if peer is not None:
             flat = peer.workspace[:total]
         else:
-            flat = self._buffer('grad_flat', total, torch.float32, dev)[:total]
+            flat = self._buffer('grad_flat' if entity_grad else 'grad_small', total, torch.float32, dev)[:total]
         views = {
             'flat': flat,
-            'gE': flat[:nE].view_as(self.entity_embedding),
+            'gE': flat[:nE].view_as(self.entity_embedding) if entity_grad else None,
             'gR': flat[nE4:nE4 + nR].view_as(self.relation_embedding),
             'gM': flat[nE4 + nR4:nE4 + nR4 + 1].view(1, 1),
             'pos_row': flat[nE4 + nR4 + 4:nE4 + nR4 + 4 + B],
@@ -342,7 +349,8 @@ class KGEModel(nn.Module):
             'wsum': self._buffer('wsum', 1, torch.float32, dev),
             'reg': self._buffer('reg_partials', 148 * 8, torch.float64, dev),
         }
-        self._ws['grad_views'] = ((B, dev, peer is not None), views)   # slicing costs ~10 us per view: once per batch size
+        # slicing costs ~10 us per view: once per batch size
+        self._ws['grad_views' if entity_grad else 'grad_views_small'] = ((B, dev, peer is not None), views)
         return dict(views)
 
     def _gather_moments(self, optimizer):
@@ -387,7 +395,7 @@ class KGEModel(nn.Module):
         else:
             optimizer.zero_grad()
         out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
-        model._prefetch_batch(train_iterator)     # next batch's next() + H2D overlap this step's kernels
+        model._prefetch_batch(train_iterator)     # opt-in (KGE_PREFETCH=1): next batch's next() + H2D under this step
         reg = float(getattr(args, 'regularization', 0.0))
         host = out.cpu()                          # the step's single device->host sync (model.py:305-310 has 3-4)
         code = int(host.view(torch.int32)[4])
@@ -396,6 +404,12 @@ class KGEModel(nn.Module):
             model._err_flag().zero_()
             if code == 2:
                 raise _lib.KgeError('NVLink peer exchange timed out: a rank died or the ranks fell out of step')
+            if model._ws.get('update_cancelled_on_error'):
+                # the optimizer kernels saw the flag and left parameters and moments untouched (the reference raises
+                # in index_select before backward): undo the host-side step counters too
+                for p in model._trainable():
+                    if len(optimizer.state[p]):
+                        optimizer.state[p]['step'] -= 1
             raise IndexError('index out of range in sample (entity/relation id outside the embedding table)')
         regularization_log = {'regularization': out[3]} if reg != 0.0 else {}
         log = {
@@ -406,10 +420,12 @@ class KGEModel(nn.Module):
         }
         return log
 
-    # ---- input pipelining: the reference pulls one batch per step (model.py:261) and copies it synchronously
-    # (model.py:263-266).  We pull the batch of step i+1 right after launching step i and copy it on a side stream,
-    # so next() and the H2D copy run under step i's kernels.  One batch is held ahead per iterator; exhaustion is
-    # re-raised at the call that would have hit it.  KGE_NO_PREFETCH=1 restores strict pull-at-call behaviour.
+    # ---- input pipelining.  Default = the reference's contract: exactly one next(train_iterator) per train_step call,
+    # at the call (model.py:261), copied on the current stream (model.py:263-266).  Opt-in with KGE_PREFETCH=1 (or
+    # model.prefetch_batches = True): the batch of step i+1 is pulled right after launching step i and copied on a
+    # side stream, so next() and the H2D copy run under step i's kernels.  One batch is then held ahead PER ITERATOR
+    # (alternating several iterators loses nothing); exhaustion or a loader error is re-raised at the call that
+    # would have hit it; one extra batch is drawn after the last step of a run.
     def _stage_batch(self, batch, stream=None):
         dev = self.entity_embedding.device
         if stream is None:
@@ -423,7 +439,7 @@ class KGEModel(nn.Module):
         return staged
 
     def _next_batch(self, iterator):
-        held = self._ws.pop('prefetched', None)
+        held = self._prefetched.pop(id(iterator), None) if self._prefetched else None
         if held is not None and held[0] is iterator:
             _, batch, error, stream = held
             if error is not None:
@@ -438,12 +454,12 @@ class KGEModel(nn.Module):
         return next(iterator)
 
     def _prefetch_batch(self, iterator):
-        if os.environ.get('KGE_NO_PREFETCH') or self.entity_embedding.device.type != 'cuda':
+        if not (self.prefetch_batches or os.environ.get('KGE_PREFETCH')) or self.entity_embedding.device.type != 'cuda':
             return
         try:
             batch = next(iterator)
         except Exception as exc:                  # StopIteration (finite iterators) or a loader error: re-raise next call
-            self._ws['prefetched'] = (iterator, None, exc, None)
+            self._prefetched[id(iterator)] = (iterator, None, exc, None)
             return
         stream = None
         if not batch[1].is_cuda:
@@ -451,7 +467,7 @@ class KGEModel(nn.Module):
             if stream is None:
                 stream = self._ws['copy_stream'] = torch.cuda.Stream(self.entity_embedding.device)
             batch = self._stage_batch(batch, stream)
-        self._ws['prefetched'] = (iterator, batch, None, stream)
+        self._prefetched[id(iterator)] = (iterator, batch, None, stream)    # keeps the iterator alive: id() stays unique
 
     def _exchange_slices(self, B, world, N):
         """How many regions the multi-GPU exchange of one step is cut into (KGE_PEER_SLICES, default 1 = no slicing).
@@ -488,18 +504,28 @@ class KGEModel(nn.Module):
         loss_kind = _lib.LOSS_NEG_ADVERSARIAL if adversarial else _lib.LOSS_NEG_UNIFORM
         mode_id = _lib.MODE_IDS[mode]
 
-        ws = model._grad_workspace(B)
         err = model._err_flag()
-        ws['out'] = model._ws['loss_out']
         desc = model._own_descriptor()
+        rank, world = _dist()
+        fused_adam = KGEModel._fusable_adam(model, optimizer)
+        # which kernels run for this shape (cached per shape): the single-read path can also apply the entity table's
+        # Adam update inside the backward -- on one device, with a stock Adam, unless the caller wants p.grad
+        wkey = (rows, N, desc.entity_dim, desc.nentity)
+        held = model._ws.get('train_ws_bytes')
+        if held is None or held[0] != wkey:
+            lib = _lib.load()
+            held = model._ws['train_ws_bytes'] = (wkey, lib.kge_train_workspace_bytes(ctypes.byref(desc), rows, N),
+                                                  lib.kge_train_plan(ctypes.byref(desc), rows, N))
+        wbytes, plan = held[1], held[2]
+        fuse_entity = bool(fused_adam and world == 1 and rows == B and (plan & _lib.PLAN_ENTITY_ADAM)
+                           and not os.environ.get('KGE_KEEP_GRADS'))
+        ws = model._grad_workspace(B, entity_grad=not fuse_entity)
+        ws['out'] = model._ws['loss_out']
         events = model._ws.get('kernel_events')       # bench.py: CUDA events around the dominant kernel
         xevents = model._ws.get('exchange_events')    # bench.py: CUDA events around the exposed exchange + optimizer
-        rank, world = _dist()
         params = model._trainable()
         grads = [ws['gE'], ws['gR']] + ([ws['gM']] if model.model_name == 'pRotatE' else [])
         gM = ws['gM'] if model.model_name == 'pRotatE' else None
-
-        fused_adam = KGEModel._fusable_adam(model, optimizer)
 
         def adam_entries():
             """torch.optim.Adam bookkeeping (host only; state created lazily exactly like torch/optim/adam.py
@@ -514,8 +540,9 @@ class KGEModel(nn.Module):
                     state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state['step'] += 1
-                entries.append((p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
-                                p.numel(), int(state['step'].item()), 1 if (reg != 0.0 and i < 2) else 0))
+                entries.append((p.data_ptr(), g.data_ptr() if g is not None else None, state['exp_avg'].data_ptr(),
+                                state['exp_avg_sq'].data_ptr(), p.numel(), int(state['step'].item()),
+                                1 if (reg != 0.0 and i < 2) else 0))
             return entries, hyper
 
         # ---- multi-GPU plan: NVLink peer-memory exchange (csrc/kge_peer.cu) when it is set up and Adam is fused,
@@ -547,17 +574,31 @@ class KGEModel(nn.Module):
         common = (_ptr(positive), _ptr(negative), _ptr(weight[row_begin:]) if weight is not None else None,
                   _ptr(ws['wsum']) if weight is not None else None, B, 0, rows, N)
         neg_row, pos_row = ws['neg_row'][row_begin:], ws['pos_row'][row_begin:]
-        wkey = (rows, N, desc.entity_dim, desc.nentity)
-        held = model._ws.get('train_ws_bytes')
-        if held is None or held[0] != wkey:
-            held = model._ws['train_ws_bytes'] = (wkey, _lib.load().kge_train_workspace_bytes(ctypes.byref(desc), rows, N))
-        wbytes = held[1]
         wsp = model._buffer('train_ws', wbytes, torch.uint8, dev)
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         pos_rows, neg_rows = ws['pos_row'], ws['neg_row']
-        if peer is None or len(regions) == 1:
+        model._ws['update_cancelled_on_error'] = fused_adam and peer is None and world == 1
+        if fuse_entity:
+            # one device: negatives + positive triple + backward, with torch.optim.Adam for the entity table applied
+            # inside the entity-major pass (no dense entity gradient); R (and modulus) follow through kge_adam_step
+            entries, hyper = adam_entries()
+            e0 = entries[0]
+            ea = _lib.KgeEntityAdam(exp_avg=e0[2], exp_avg_sq=e0[3], step=e0[5], lr=hyper[0], beta1=hyper[1],
+                                    beta2=hyper[2], eps=hyper[3], l3_coefficient=reg,
+                                    reg_partials=ws['reg'].data_ptr() if reg != 0.0 else None, n_reg_partials=148)
+            _lib.call("kge_train_rows_adam", ctypes.byref(desc), mode_id, loss_kind, alpha, *common[:5], rows, N,
+                      _ptr(neg_row), _ptr(pos_row), _ptr(ws['gR']), _ptr(gM), _ptr(wsp), wbytes, _ptr(err),
+                      ctypes.byref(ea), st)
+            entries = entries[1:]
+            if events is not None:
+                ev1.record()
+                events.append((ev0, ev1))
+            if xevents is not None:
+                xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                xev0.record()
+        elif peer is None or len(regions) == 1:
             if rows:                                  # (a rank can be left without rows by a short last batch)
                 _lib.call("kge_train_rows", ctypes.byref(desc), mode_id, loss_kind, alpha, *common,
                           _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), None, _ptr(wsp),
@@ -612,12 +653,15 @@ class KGEModel(nn.Module):
         # ---- optimizer ---------------------------------------------------------------------------------------------
         if fused_adam:
             if peer is None:
+                # with the fused entity pass the first 148 partial sums of |x|^3 are the entity kernel's
+                rp = ws['reg'][148:] if fuse_entity else ws['reg']
                 tensors = (_lib.KgeAdamTensor * len(entries))(*[_lib.KgeAdamTensor(*c) for c in entries])
                 _lib.call("kge_adam_step", tensors, len(entries), *hyper, reg,
-                          _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel(), st)
+                          _ptr(rp) if reg != 0.0 else None, rp.numel(), _ptr(err) if world == 1 else None, st)
             reg_partials = ws['reg'] if reg != 0.0 else None
             for p, g in zip(params, grads):
-                p.grad = g if peer is None else None    # peer path: the workspace slots now carry parameter values
+                p.grad = g if peer is None else None    # peer path: the workspace slots now carry parameter values;
+                #                                         fused entity pass: entity_embedding.grad stays None
         else:
             # any other optimizer object: hand it our gradients and let it do its own update
             reg_partials = None
@@ -644,14 +688,17 @@ class KGEModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------ evaluation
     def _filter_index(self, all_true_triples, nentity, nrelation):
-        key = (id(all_true_triples), len(all_true_triples), nentity, nrelation)
-        if self._filter_cache is None or self._filter_cache[0] != key:
-            self._filter_cache = (key, FilterIndex(all_true_triples, nentity, nrelation), {})
-        return self._filter_cache[1]
+        # the cache holds the list itself (an id() alone can be reused by a later temporary such as train+valid+test)
+        # and is keyed on identity + length; a list mutated in place to the same length must be passed as a new object
+        key = (len(all_true_triples), nentity, nrelation)
+        held = self._filter_cache
+        if held is None or held[0] is not all_true_triples or held[1] != key:
+            self._filter_cache = held = (all_true_triples, key, FilterIndex(all_true_triples, nentity, nrelation), {})
+        return held[2]
 
     def _filter_tables(self, index, mode, dev):
         """The index of all true triples, resident on the device (uploaded once per list, mode and device)."""
-        held = self._filter_cache[2]
+        held = self._filter_cache[3]
         if (mode, dev) not in held:
             keys, offsets, values = index.table(mode)
             held[(mode, dev)] = (torch.from_numpy(np.ascontiguousarray(keys)).to(dev),
@@ -660,7 +707,8 @@ class KGEModel(nn.Module):
                                  torch.zeros(1, dtype=torch.int32, device=dev), int(keys.size))
         return held[(mode, dev)]
 
-    def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False, exact=False):
+    def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False, exact=False,
+                       return_approx=False):
         """Filtered rank of every test triple in `mode` (model.py:382-418 without the sort): int64 [len].
         Entities are sharded across the ranks of an initialised process group; the integer counts are
         all-reduced (bit-exact)."""
@@ -705,6 +753,8 @@ class KGEModel(nn.Module):
                       _ptr(enorm), st)
         counts_all = tally[:nq_all]
         scores = torch.empty((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if return_scores else None
+        # tests: the tensor-core approximations of the tcgen05 path (to pin its error band against exact scores)
+        approx = torch.zeros((queries_all.shape[0], nentity), dtype=torch.float32, device=dev) if (return_approx and gemm) else None
         m = _lib.MODE_IDS[mode]
         for ci, lo in enumerate(range(0, queries_all.shape[0], query_chunk)):
             queries = queries_dev[lo:lo + query_chunk]
@@ -732,7 +782,8 @@ class KGEModel(nn.Module):
                 _lib.call("kge_eval_gemm_split", _ptr(qvec), Q, self.entity_dim, _ptr(qhi), _ptr(qlo), _ptr(qnorm), st)
                 _lib.call("kge_eval_gemm_count_ranks", ctypes.byref(desc), m, _ptr(qvec), _ptr(qhi), _ptr(qlo),
                           _ptr(qnorm), _ptr(queries), Q, _ptr(pos), _ptr(bits), _ptr(ehi), _ptr(elo), _ptr(enorm),
-                          ent_begin, ent_end, _ptr(counts), _ptr(amb), cap, _ptr(amb_counts[ci]), st)
+                          ent_begin, ent_end, _ptr(counts), _ptr(amb), cap, _ptr(amb_counts[ci]),
+                          _ptr(approx[lo:lo + Q]) if approx is not None else None, st)
             elif two_stage:
                 cap = int(os.environ.get('KGE_EVAL_AMB_CAP', Q * 256))
                 amb = self._buffer('gemm_amb', cap * 2, torch.int32, dev)
@@ -759,6 +810,8 @@ class KGEModel(nn.Module):
                 chunk = [tuple(int(v) for v in row) for row in queries_all[lo:lo + query_chunk]]
                 ranks[lo:lo + query_chunk] = self.filtered_ranks(chunk, all_true_triples, mode, query_chunk, exact=True)
         self._raise_if_bad_index()
+        if return_approx:
+            return ranks, approx
         return (ranks, scores) if return_scores else ranks
 
     @staticmethod

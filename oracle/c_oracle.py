@@ -60,6 +60,10 @@ def num_threads():
     return load().ko_num_threads()
 
 
+def set_num_threads(n):
+    load().ko_set_num_threads(int(n))
+
+
 def sincos(x):
     x = _f32(x)
     s, c = np.empty_like(x), np.empty_like(x)

@@ -34,6 +34,14 @@ int ko_num_threads(void) {
 #endif
 }
 
+void ko_set_num_threads(int n) {      /* bench.py: torchrun exports OMP_NUM_THREADS=1; the CPU arm asks for every core */
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ---- sin/cos: Cody-Waite reduction by pi/2 + degree-7/8 minimax polynomials (restated from the
  * published Cephes sinf/cosf scheme); every step is a correctly rounded IEEE op, so any conforming
  * platform gives the same bits. ---- */

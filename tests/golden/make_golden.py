@@ -12,6 +12,8 @@ time except the .npz files this script writes; the GPU box has no /root/referenc
 Files written
   small_<Model>_d<d>.npz   forward scores (3 modes), 4 train steps x 4 loss configs, filtered ranks
   countries_S1.npz         real dataset: 4 RotatE train steps on reference-sampled batches, AUC-PR, ranks
+  fullwidth_RotatE_fb15k.npz  BASELINE configs[2] row shape (14,951 x 2000 table, N=256), 192 rows, 3 train steps
+  runpy_logs.json          codes/run.py end to end (countries_S1 train/valid/test + resume, wn18rr --do_test -init): log lines
   wn18rr_eval.npz          real dataset: filtered ranks of a seeded RotatE model on 400 test triples
 """
 import argparse
@@ -194,18 +196,20 @@ def countries_case(out):
     e2id, r2id, tr, va, te = load_dataset("countries_S1")
     with open(os.path.join(REF, "data", "countries_S1", "regions.list")) as f:
         regions = [e2id[line.strip()] for line in f]
-    nentity, nrelation, d, gamma, B, N = len(e2id), len(r2id), 64, 0.1, 128, 64
+    # BASELINE.json configs[0] at its stated shape: -n 64 -b 512 -d 500 -g 0.1 -adv -de (512 rows > 148 SMs)
+    nentity, nrelation, d, gamma, B, N = len(e2id), len(r2id), 500, 0.1, 512, 64
     np.random.seed(7)                                   # TrainDataset samples with the global numpy RNG
     torch.manual_seed(7)
     batches = []
-    order = np.random.permutation(len(tr))
-    for step in range(4):
+    order = np.random.permutation(len(tr))              # 1111 train triples: 512, 512, a ragged 87, then 512 again
+    cuts = [(0, B), (B, 2 * B), (2 * B, len(tr)), (0, B)]
+    for step, (lo, hi) in enumerate(cuts):
         mode = "tail-batch" if step % 2 == 0 else "head-batch"
         ds = ref_data.TrainDataset(tr, nentity, nrelation, N, mode)
-        items = [ds[int(i)] for i in order[step * B:(step + 1) * B]]
+        items = [ds[int(i)] for i in order[lo:hi]]
         batches.append(ref_data.TrainDataset.collate_fn(items))
     m, st = make_ref("RotatE", nentity, nrelation, d, gamma, seed=3)
-    lr = 1e-3                                           # best_config uses 2e-6; larger so 4 steps move the tables
+    lr = 1e-4                                           # best_config uses 2e-6; larger so 4 steps move the tables
     opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
     args = ns(negative_adversarial_sampling=True, adversarial_temperature=1.0, countries=True,
               regions=regions, nentity=nentity, nrelation=nrelation)
@@ -220,9 +224,10 @@ def countries_case(out):
     all_true = tr + va + te
     metrics = ref_model.KGEModel.test_step(m, te, all_true, args)
     ranks, _ = stable_ranks(m, te, all_true, nentity, nrelation)
-    data = dict(nentity=nentity, nrelation=nrelation, d=d, gamma=gamma, regions=np.asarray(regions),
+    data = dict(nentity=nentity, nrelation=nrelation, d=d, gamma=gamma, lr=lr, init_seed=3, regions=np.asarray(regions),
                 train=np.asarray(tr, dtype=np.int32), valid=np.asarray(va, dtype=np.int32),
-                test=np.asarray(te, dtype=np.int32), init_E=st["entity_embedding"], init_R=st["relation_embedding"],
+                test=np.asarray(te, dtype=np.int32),      # initial tables: O.init_tables(seed=init_seed), checksummed
+                init_checksum=np.float64(st["entity_embedding"].astype(np.float64).sum()),
                 logs=np.asarray(logs), final_E=m.entity_embedding.detach().numpy(),
                 final_R=m.relation_embedding.detach().numpy(), auc_pr=auc, y_score=y_score, y_true=y_true,
                 ranks=ranks, metrics=np.asarray([metrics[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")]))
@@ -230,6 +235,57 @@ def countries_case(out):
         data[f"pos{i}"], data[f"neg{i}"], data[f"w{i}"] = p.numpy().astype(np.int16), n.numpy().astype(np.int16), w.numpy()
     np.savez_compressed(out, **data)
     print("wrote", out, "auc_pr", auc, metrics)
+
+
+def fullwidth_batches(nentity, nrelation, B, N, steps, seed):
+    """Seeded batches of the full-width case (the tests regenerate them with the same call)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for step in range(steps):
+        pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrelation, size=B), rng.randint(nentity, size=B)], 1)
+        neg = rng.randint(nentity, size=(B, N))
+        w = np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)
+        out.append((pos.astype(np.int64), neg.astype(np.int64), w, "tail-batch" if step % 2 == 0 else "head-batch"))
+    return out
+
+
+def fullwidth_case(out):
+    """BASELINE.json configs[2] row shape through the UNMODIFIED reference: RotatE, 14,951 x 2000 entity table,
+    1,345 relations, N = 256 negatives, gamma 24, -adv, lr 1e-4 -- with B = 192 positive rows (more rows than the
+    148 SMs and not a multiple of them: the persistent multi-row loop of the CUDA row kernel), 3 alternating
+    steps.  The reference needs ~50 s per 1024-row step on this container, hence 192 rows.  Tables and batches
+    are regenerated from seeds by the tests; stored are the losses and, because whole tables would be 120 MB,
+    per-row sums of |gradient| (no cancellation) plus sampled full rows of the gradients and the updated tables."""
+    nentity, nrelation, d, gamma, B, N, lr = 14951, 1345, 1000, 24.0, 192, 256, 1e-4
+    torch.set_num_threads(8)
+    m, st = make_ref("RotatE", nentity, nrelation, d, gamma, seed=0)
+    batches = fullwidth_batches(nentity, nrelation, B, N, 3, seed=77)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
+    args = ns(negative_adversarial_sampling=True, adversarial_temperature=1.0)
+    rng = np.random.RandomState(5)
+    touched = np.unique(np.concatenate([batches[0][1].reshape(-1), batches[0][0][:, 0], batches[0][0][:, 2]]))
+    ent_rows = np.sort(rng.choice(touched, 48, replace=False))
+    rel_rows = np.sort(rng.choice(np.unique(batches[0][0][:, 1]), 24, replace=False))
+    data = dict(nentity=nentity, nrelation=nrelation, d=d, gamma=gamma, B=B, N=N, lr=lr, batch_seed=77, init_seed=0,
+                ent_rows=ent_rows, rel_rows=rel_rows,
+                init_checksum=np.float64(st["entity_embedding"].astype(np.float64).sum()))
+    logs = []
+    for step, b in enumerate(batches):
+        tb = (torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2]), b[3])
+        log = ref_model.KGEModel.train_step(m, opt, iter([tb]), args)
+        logs.append([log["positive_sample_loss"], log["negative_sample_loss"], log["loss"]])
+        gE, gR = m.entity_embedding.grad.numpy(), m.relation_embedding.grad.numpy()
+        data[f"gE{step}_abs_rowsum"] = np.abs(gE.astype(np.float64)).sum(1)
+        data[f"gR{step}_abs_rowsum"] = np.abs(gR.astype(np.float64)).sum(1)
+        data[f"gE{step}_abs_colsum"] = np.abs(gE.astype(np.float64)).sum(0)
+        if step == 0:
+            data["gE0_rows"], data["gR0_rows"] = gE[ent_rows].copy(), gR[rel_rows].copy()
+        print("full-width step", step, log)
+    data["logs"] = np.asarray(logs, dtype=np.float64)
+    data["final_E_rows"] = m.entity_embedding.detach().numpy()[ent_rows].copy()
+    data["final_R_rows"] = m.relation_embedding.detach().numpy()[rel_rows].copy()
+    np.savez_compressed(out, **data)
+    print("wrote", out)
 
 
 def wn18rr_case(out, nq=400):
@@ -249,6 +305,29 @@ def wn18rr_case(out, nq=400):
     print("wrote", out, metrics, "stable-rank metrics", O.metrics_from_ranks(ranks))
 
 
+def runpy_case(out):
+    """codes/run.py end to end on the UNMODIFIED reference (CPU): the logged training losses, AUC-PR and filtered metrics
+    that tests/test_gpu_runpy.py expects from the same commands on the drop-in (tests/runpy_cases.py)."""
+    import json
+    import tempfile
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import runpy_cases as RC
+    data, run_py = os.path.join(REF, "data"), os.path.join(REF, "codes", "run.py")
+    work = tempfile.mkdtemp(prefix="kge_runpy_golden_")
+    RC.prepare_wn18rr(data, work)
+    cmds = RC.commands(data, work)
+    logs = {}
+    for name in ("countries_train", "countries_resume", "wn18rr_test"):
+        RC.run_case(run_py, cmds[name], reference=True, cuda=False)
+        log_dir = {"countries_train": f"{work}/countries", "countries_resume": f"{work}/countries_resumed",
+                   "wn18rr_test": f"{work}/wn18rr_ckpt"}[name]
+        logs[name] = RC.parse_log(os.path.join(log_dir, "train.log" if "countries" in name else "test.log"))
+        print(name, len(logs[name]), "metric lines; last:", logs[name][-1])
+    with open(out, "w") as f:
+        json.dump({"torch": torch.__version__, "seed": 0, "logs": logs}, f, indent=1)
+    print("wrote", out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -259,5 +338,9 @@ if __name__ == "__main__":
                 small_case(name, d, os.path.join(HERE, f"small_{name}_d{d}.npz"))
     if a.only in ("", "countries"):
         countries_case(os.path.join(HERE, "countries_S1.npz"))
+    if a.only in ("", "fullwidth"):
+        fullwidth_case(os.path.join(HERE, "fullwidth_RotatE_fb15k.npz"))
+    if a.only in ("", "runpy"):
+        runpy_case(os.path.join(HERE, "runpy_logs.json"))
     if a.only in ("", "wn18rr"):
         wn18rr_case(os.path.join(HERE, "wn18rr_eval.npz"))

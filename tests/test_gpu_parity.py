@@ -119,12 +119,18 @@ CFGS = {
 @pytest.mark.parametrize("model", MODELS)
 @pytest.mark.parametrize("d", [12, 10])
 @pytest.mark.parametrize("cfg", list(CFGS))
-@pytest.mark.parametrize("path", ["default", "single_read"])
+@pytest.mark.parametrize("path", ["default", "single_read", "single_read_fused_adam"])
 def test_train_steps_vs_reference_golden(model, d, cfg, path, monkeypatch):
     """4 train_steps with the run.py call sequence (incl. the Adam re-creation of run.py:315-322), through the kernel
-    variant the launcher would pick for this shape and through the single-read (split + entity-major) path."""
-    if path == "single_read":
+    variant the launcher would pick for this shape, through the single-read (split + entity-major) path with dense
+    gradients, and through the single-read path with the entity table's Adam update fused into the entity pass (no
+    entity gradient is materialised there: entity_embedding.grad stays None)."""
+    if path != "default":
         monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
+    if path == "single_read":
+        monkeypatch.setenv("KGE_KEEP_GRADS", "1")
+    else:
+        monkeypatch.delenv("KGE_KEEP_GRADS", raising=False)
     g = np.load(os.path.join(GOLDEN, f"small_{model}_d{d}.npz"))
     m = make_model(model, int(g["nentity"]), int(g["nrelation"]), d, float(g["gamma"]), golden_state(g))
     lr = 1e-3
@@ -145,7 +151,11 @@ def test_train_steps_vs_reference_golden(model, d, cfg, path, monkeypatch):
         got = [log.get("regularization", 0.0), log["positive_sample_loss"], log["negative_sample_loss"], log["loss"]]
         np.testing.assert_allclose(got, ref, rtol=TOL, atol=1e-7)
         if step == 0:
-            assert relinf(m.entity_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gE0"]) < TOL
+            if m.entity_embedding.grad is None:       # fused entity optimizer (needs rows that are 16-byte multiples)
+                assert path == "single_read_fused_adam" and d % 4 == 0
+            else:
+                assert path != "single_read_fused_adam" or d % 4 != 0
+                assert relinf(m.entity_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gE0"]) < TOL
             assert relinf(m.relation_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gR0"]) < TOL
             if model == "pRotatE":
                 assert relinf(m.modulus.grad.cpu().numpy(), g[f"train_{cfg}_gM0"]) < TOL
@@ -163,6 +173,7 @@ def test_train_steps_vs_reference_golden(model, d, cfg, path, monkeypatch):
 def test_train_step_matches_autograd_path_full_width(path, monkeypatch):
     if path == "single_read":
         monkeypatch.setenv("KGE_FORCE_SPLIT", "1")
+    monkeypatch.setenv("KGE_KEEP_GRADS", "1")
     _full_width_case()
 
 
@@ -266,8 +277,10 @@ def test_countries_s1_end_to_end():
     """Real dataset, reference-sampled batches: 4 train steps, AUC-PR (model.py:322-344) and filtered ranks."""
     g = np.load(os.path.join(GOLDEN, "countries_S1.npz"))
     d, gamma, nentity, nrel = int(g["d"]), float(g["gamma"]), int(g["nentity"]), int(g["nrelation"])
-    m = make_model("RotatE", nentity, nrel, d, gamma, {"entity_embedding": g["init_E"], "relation_embedding": g["init_R"]})
-    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+    from test_oracle_golden import countries_init
+    assert (d, g["pos0"].shape[0], g["neg0"].shape[1]) == (500, 512, 64)     # BASELINE configs[0] at its stated shape
+    m = make_model("RotatE", nentity, nrel, d, gamma, countries_init(g))
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=float(g["lr"]))
     regions = [int(r) for r in g["regions"]]
     args = ns(negative_adversarial_sampling=True, countries=True, regions=regions, nentity=nentity, nrelation=nrel)
     for step in range(4):
@@ -469,6 +482,7 @@ def test_single_read_path_matches_two_sweep_kernel(model, mode, monkeypatch):
     oracle on a medium shape, adversarial and uniform losses."""
     nentity, nrel, d, gamma, B, N = 3000, 7, 128, 6.0, 37, 50
     de, dr = FLAGS[model]
+    monkeypatch.setenv("KGE_KEEP_GRADS", "1")
     st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=5)
     rng = np.random.RandomState(6)
     pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
@@ -601,9 +615,10 @@ def test_two_stage_rotate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d,
 
 
 def test_train_step_input_prefetch_semantics():
-    """One batch is pulled ahead per iterator (copied on a side stream under the current step); a finite iterator of
-    K batches still yields exactly K steps and raises StopIteration at call K+1, like the reference's next() at
-    model.py:261; results do not depend on the prefetch."""
+    """Default = the reference's contract (model.py:261): exactly one next() per call.  With KGE_PREFETCH=1 one batch
+    is pulled ahead per iterator (copied on a side stream under the current step); a finite iterator of K batches
+    still yields exactly K steps and raises StopIteration at call K+1; two alternating iterators lose no batch;
+    results do not depend on the prefetch."""
     torch.manual_seed(0)
     st = O.init_tables("RotatE", 500, 5, 16, 6.0, True, False, seed=2)
     args = ns(negative_adversarial_sampling=True)
@@ -613,52 +628,119 @@ def test_train_step_input_prefetch_semantics():
         batches.append((pos.pin_memory(), torch.randint(500, (32, 16)).pin_memory(), (torch.rand(32) + 0.1).pin_memory(),
                         "tail-batch" if i % 2 == 0 else "head-batch"))
     results = {}
+    class Counting:
+        def __init__(self, items):
+            self.items, self.pulled = list(items), 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            if self.pulled >= len(self.items):
+                raise StopIteration
+            self.pulled += 1
+            return self.items[self.pulled - 1]
+
     for tag in ("prefetch", "strict"):
-        if tag == "strict":
-            os.environ["KGE_NO_PREFETCH"] = "1"
+        if tag == "prefetch":
+            os.environ["KGE_PREFETCH"] = "1"
         try:
             m = make_model("RotatE", 500, 5, 16, 6.0, st)
             opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
-            it = iter(batches)
-            logs = [KGE().train_step(m, opt, it, args) for _ in range(3)]
+            it = Counting(batches)
+            logs = []
+            for k in range(3):
+                logs.append(KGE().train_step(m, opt, it, args))
+                assert it.pulled == (min(k + 2, 3) if tag == "prefetch" else k + 1)
             with pytest.raises(StopIteration):
                 KGE().train_step(m, opt, it, args)
             results[tag] = (logs, m.entity_embedding.detach().cpu().numpy().copy())
+            # two iterators used alternately (e.g. separate head / tail loaders): every batch of both is consumed
+            a, b = Counting(batches[:2]), Counting(batches[1:])
+            m2 = make_model("RotatE", 500, 5, 16, 6.0, st)
+            opt2 = torch.optim.Adam(filter(lambda p: p.requires_grad, m2.parameters()), lr=1e-3)
+            seq = [KGE().train_step(m2, opt2, x, args)["loss"] for x in (a, b, a, b)]
+            ref2 = make_model("RotatE", 500, 5, 16, 6.0, st)
+            opt3 = torch.optim.Adam(filter(lambda p: p.requires_grad, ref2.parameters()), lr=1e-3)
+            want = [KGE().train_step(ref2, opt3, iter([x]), args)["loss"]
+                    for x in (batches[0], batches[1], batches[1], batches[2])]
+            np.testing.assert_allclose(seq, want, rtol=1e-6)
         finally:
-            os.environ.pop("KGE_NO_PREFETCH", None)
+            os.environ.pop("KGE_PREFETCH", None)
     for a, b in zip(results["prefetch"][0], results["strict"][0]):
         assert a.keys() == b.keys() and all(abs(a[k] - b[k]) <= 1e-6 * abs(b[k]) for k in a)
     assert relinf(results["prefetch"][1], results["strict"][1]) < 1e-6
 
 
-def test_sliced_entity_pass_matches_single_launch(monkeypatch):
-    """The multi-GPU flow (kge_train_rows_begin + kge_train_entity_pass per entity slice + Adam per slice) gives the
-    same losses, gradients and updated tables as the single-call flow."""
+@pytest.mark.parametrize("model,reg", [("RotatE", 0.0), ("ComplEx", 1e-3), ("pRotatE", 0.0), ("TransE", 0.0),
+                                       ("DistMult", 1e-3)])
+def test_fused_entity_optimizer_matches_dense_adam(model, reg, monkeypatch):
+    """kge_train_rows_adam (Adam for the entity table inside the entity-major pass, no dense entity gradient) against
+    the same step with dense gradients + kge_adam_step (KGE_KEEP_GRADS=1): losses, tables and moments over 3 steps;
+    entities that no pair touches are still updated (dense Adam semantics); with -r the L3 term is included."""
     nentity, nrel, d, gamma, B, N = 3001, 7, 64, 6.0, 64, 300
-    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=5)
+    de, dr = FLAGS[model]
+    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=5)
     rng = np.random.RandomState(6)
     batches = []
     for i in range(3):
         pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
-        batches.append((torch.from_numpy(pos), torch.from_numpy(rng.randint(nentity, size=(B, N))),
+        batches.append((torch.from_numpy(pos), torch.from_numpy(rng.randint(nentity // 2, size=(B, N))),
                         torch.from_numpy(np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)),
                         "tail-batch" if i % 2 == 0 else "head-batch"))
-    args = ns(negative_adversarial_sampling=True)
+    args = ns(negative_adversarial_sampling=True, regularization=reg)
     out = {}
-    for tag in ("single", "sliced"):
-        if tag == "sliced":
-            monkeypatch.setenv("KGE_SLICED_TRAIN", "1")
-        m = make_model("RotatE", nentity, nrel, d, gamma, st)
+    for tag in ("dense", "fused"):
+        if tag == "dense":
+            monkeypatch.setenv("KGE_KEEP_GRADS", "1")
+        else:
+            monkeypatch.delenv("KGE_KEEP_GRADS")
+        m = make_model(model, nentity, nrel, d, gamma, st)
         opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
         it = iter(batches)
         logs = [KGE().train_step(m, opt, it, args) for _ in range(3)]
+        assert (m.entity_embedding.grad is None) == (tag == "fused"), "fused entity optimizer was (not) taken"
+        mom = opt.state[m.entity_embedding]
         out[tag] = (logs, m.entity_embedding.detach().cpu().numpy().copy(), m.relation_embedding.detach().cpu().numpy().copy(),
-                    m.entity_embedding.grad.cpu().numpy().copy())
-    monkeypatch.delenv("KGE_SLICED_TRAIN")
-    for a, b in zip(out["single"][0], out["sliced"][0]):
-        assert all(abs(a[k] - b[k]) <= 1e-6 * abs(a[k]) for k in a)
-    assert relinf(out["sliced"][3], out["single"][3]) < 1e-6
-    assert outlier_fraction(out["sliced"][1], out["single"][1]) < 1e-4 and relinf(out["sliced"][2], out["single"][2]) < 1e-5
+                    mom["exp_avg"].cpu().numpy().copy(), mom["exp_avg_sq"].cpu().numpy().copy(), float(mom["step"]))
+    for a, b in zip(out["dense"][0], out["fused"][0]):
+        assert list(a) == list(b) and all(abs(a[k] - b[k]) <= 1e-6 * abs(a[k]) for k in a)
+    assert outlier_fraction(out["fused"][1], out["dense"][1]) < 1e-4 and relinf(out["fused"][2], out["dense"][2]) < 1e-5
+    assert relinf(out["fused"][3], out["dense"][3]) < 1e-5 and relinf(out["fused"][4], out["dense"][4]) < 1e-5
+    assert out["fused"][5] == out["dense"][5] == 3.0
+    # the upper half of the entity ids never appears as a negative: those rows still move (m decays, v stays 0 ...)
+    untouched = np.setdiff1d(np.arange(nentity // 2, nentity), np.concatenate([b[0][:, [0, 2]].numpy().ravel() for b in batches]))
+    assert untouched.size > 100
+    np.testing.assert_array_equal(out["fused"][1][untouched], out["dense"][1][untouched])
+
+
+def test_bad_index_leaves_model_and_optimizer_untouched():
+    """An out-of-range id raises IndexError like the reference's index_select -- and, as there, before any state
+    changed: the optimizer kernels see the error flag and skip the update, the step counters are rolled back."""
+    for B, N, nentity in ((64, 300, 3001), (8, 16, 500)):          # single-read (fused optimizer) and two-sweep paths
+        st = O.init_tables("RotatE", nentity, 7, 64, 6.0, True, False, seed=5)
+        m = make_model("RotatE", nentity, 7, 64, 6.0, st)
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+        args = ns(negative_adversarial_sampling=True)
+        rng = np.random.RandomState(1)
+
+        def batch(bad):
+            pos = np.stack([rng.randint(nentity, size=B), rng.randint(7, size=B), rng.randint(nentity, size=B)], 1)
+            neg = rng.randint(nentity, size=(B, N))
+            if bad:
+                neg[B // 2, N // 2] = nentity
+            return (torch.from_numpy(pos), torch.from_numpy(neg), torch.rand(B) + 0.1, "tail-batch")
+
+        KGE().train_step(m, opt, iter([batch(False)]), args)
+        before = (m.entity_embedding.detach().clone(), m.relation_embedding.detach().clone(),
+                  opt.state[m.entity_embedding]["exp_avg"].clone(), float(opt.state[m.entity_embedding]["step"]))
+        with pytest.raises(IndexError):
+            KGE().train_step(m, opt, iter([batch(True)]), args)
+        assert torch.equal(m.entity_embedding.detach(), before[0]) and torch.equal(m.relation_embedding.detach(), before[1])
+        assert torch.equal(opt.state[m.entity_embedding]["exp_avg"], before[2])
+        assert float(opt.state[m.entity_embedding]["step"]) == before[3] == 1.0
+        log = KGE().train_step(m, opt, iter([batch(False)]), args)     # and the model keeps training afterwards
+        assert np.isfinite(log["loss"]) and float(opt.state[m.entity_embedding]["step"]) == 2.0
 
 
 @pytest.mark.parametrize("model", ["RotatE", "ComplEx"])

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.kge_abi_version() == 1
+    assert lib.kge_abi_version() == 2
 
 
 def test_abi_argument_errors_without_a_gpu():
