@@ -115,7 +115,8 @@ typedef struct kge_entity_adam {
 } kge_entity_adam_t;
 
 enum { KGE_PLAN_SINGLE_READ = 1, KGE_PLAN_ENTITY_ADAM = 2 };
-/* which path kge_train_rows takes for `rows` local positive rows x N candidates (bit mask of KGE_PLAN_*)        */
+/* for `rows` local positive rows x N candidates: SINGLE_READ = kge_train_rows takes the single-read path (a shape AND
+ * pair-density decision), ENTITY_ADAM = kge_train_rows_adam is available (shape only; bit mask of KGE_PLAN_*)      */
 int kge_train_plan(const kge_model_t *m, int64_t rows, int64_t N);
 
 int kge_train_rows_adam(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
@@ -171,6 +172,10 @@ typedef struct kge_adam_tensor {
 int kge_adam_step(const kge_adam_tensor_t *host_tensors, int n_tensors, double lr, double beta1,
                   double beta2, double eps, double l3_coefficient, double *reg_partials,
                   int64_t n_reg_partials, const int32_t *skip_flag, void *stream);
+/* sum |x|^3 of the tensors flagged l3 into reg_partials (block sums, doubles): the VALUE of the L3 regulariser when the
+ * update runs through kge_peer_reduce_adam, which applies the L3 gradient itself (only `param`, `numel`, `l3` are read) */
+int kge_l3_partials(const kge_adam_tensor_t *host_tensors, int n_tensors, double *reg_partials,
+                    int64_t n_reg_partials, void *stream);
 
 /* ---- filtered ranking: KGEModel.test_step (model.py:346-427) with dataloader.py:134-154's filter ----
  * Step 1: per query the fixed side is folded into a query vector (model.py:214-223 etc.)
@@ -258,7 +263,9 @@ int kge_sample_negatives(const int64_t *triple_index, const int32_t *key_start, 
  *   - one call exchanges the region [region_begin4, region_end4) of the parameter part of the workspace (float4 units; a
  *     step may be cut into several regions so that the exchange of a finished gradient slice overlaps the computation
  *     of the next one); for the groups [slice_begin4, slice_end4) of the region it owns the rank sums the G workspaces
- *     (in rank order, or inside the NVSwitch with multimem.ld_reduce when a multicast mapping is given), applies the Adam update (same arithmetic as kge_adam_step) to the local param / exp_avg / exp_avg_sq and
+ *     (in rank order, or inside the NVSwitch with multimem.ld_reduce when a multicast mapping is given), adds the L3
+ *     gradient 3*l3*x*|x| for the tensors flagged l3 (l3_coefficient != 0; model.py:290-297), applies the Adam update
+ *     (same arithmetic as kge_adam_step) to the local param / exp_avg / exp_avg_sq and
  *     pushes the new parameter values to every other rank,
  *   - sums the row-loss region of all ranks into rows_out (local, row_floats floats),
  *   - waits until every rank has pushed, then copies the rest of the region (received slices) into the local parameters.
@@ -282,8 +289,8 @@ int kge_peer_close(void *peer_ptr);
 int kge_peer_reduce_adam(const kge_peer_group_t *host_group, uint32_t epoch, const kge_adam_tensor_t *host_tensors,
                          int n_tensors, int64_t param_floats, int64_t region_begin4, int64_t region_end4,
                          int64_t slice_begin4, int64_t slice_end4, int64_t row_offset, int64_t row_floats,
-                         float *rows_out, double lr, double beta1, double beta2, double eps, int32_t *err_flag,
-                         void *stream);
+                         float *rows_out, double lr, double beta1, double beta2, double eps, double l3_coefficient,
+                         int32_t *err_flag, void *stream);
 
 #ifdef __cplusplus
 }

@@ -93,7 +93,8 @@ PROTOTYPES = {
     "kge_peer_close": (c_int, [c_void_p]),
     "kge_peer_reduce_adam": (c_int, [POINTER(KgePeerGroup), ctypes.c_uint32, POINTER(KgeAdamTensor), c_int, c_int64,
                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_double,
-                                     c_double, c_double, c_void_p, c_void_p]),
+                                     c_double, c_double, c_double, c_void_p, c_void_p]),
+    "kge_l3_partials": (c_int, [POINTER(KgeAdamTensor), c_int, c_void_p, c_int64, c_void_p]),
     "kge_eval_filter_bits_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                                             c_int64, c_void_p, c_void_p]),
 }

@@ -221,6 +221,14 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+    constexpr bool PACKED = FAST && OP == OP_CDIST;        // FADD2 / FMUL2 / FFMA2: 3.5 issue slots per term, not 6
+    f2 part2[PACKED ? 4 : 1][PACKED ? 4 : 1];
+    if constexpr (PACKED) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part2[i][j] = pack2(0.f, 0.f);
+    }
 #pragma unroll 2
     for (int kk = 0; kk < KC; kk += 4) {
       float4 qa[4], qb[4], xa[4], xb[4];
@@ -240,7 +248,23 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {       // k ascending inside the group => index-order accumulation
-          if constexpr (FAST) {
+          if constexpr (PACKED) {
+            // |q - x| for four k at once: differences, squares and the partial sums run on packed pairs; only the four
+            // square roots (MUFU) are scalar.  The approximate scores stay inside the band of the two-stage scheme
+            // (same per-term error; the block sum is formed as (even k) + (odd k), still at most KC terms deep).
+            const f2 a01 = sub2(pack2(qa[i].x, qa[i].y), pack2(xa[j].x, xa[j].y));
+            const f2 a23 = sub2(pack2(qa[i].z, qa[i].w), pack2(xa[j].z, xa[j].w));
+            const f2 b01 = sub2(pack2(qb[i].x, qb[i].y), pack2(xb[j].x, xb[j].y));
+            const f2 b23 = sub2(pack2(qb[i].z, qb[i].w), pack2(xb[j].z, xb[j].w));
+            const f2 m01 = fma2(b01, b01, mul2(a01, a01));
+            const f2 m23 = fma2(b23, b23, mul2(a23, a23));
+            float s0, s1, s2, s3;
+            unpack2(m01, s0, s1);
+            unpack2(m23, s2, s3);
+            const f2 r01 = pack2(sqrt_approx(s0), sqrt_approx(s1));
+            const f2 r23 = pack2(sqrt_approx(s2), sqrt_approx(s3));
+            part2[i][j] = add2(part2[i][j], add2(r01, r23));
+          } else if constexpr (FAST) {
             part[i][j] += op_fast<OP>(qa[i].x, qb[i].x, xa[j].x, xb[j].x);
             part[i][j] += op_fast<OP>(qa[i].y, qb[i].y, xa[j].y, xb[j].y);
             part[i][j] += op_fast<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z);
@@ -251,6 +275,16 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
             part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].z, qb[i].z, xa[j].z, xb[j].z));
             part[i][j] = fadd(part[i][j], op_exact<OP>(qa[i].w, qb[i].w, xa[j].w, xb[j].w));
           }
+        }
+    }
+    if constexpr (PACKED) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, hi;
+          unpack2(part2[i][j], lo, hi);
+          part[i][j] = lo + hi;
         }
     }
 #pragma unroll

@@ -154,6 +154,31 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   }
 }
 
+// sum |x|^3 over up to 4 tensors -> per-block double partials (the value of the L3 regulariser, model.py:292-295, when
+// the update itself runs elsewhere: the NVLink peer exchange applies the L3 gradient per owned slice)
+__global__ void __launch_bounds__(256) l3_partials_kernel(const AdamArgs a) {
+  double racc = 0.0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int ti = 0; ti < a.nt; ++ti) {
+    const AdamTensor t = a.t[ti];
+    if (!t.l3) continue;
+    for (int64_t i = tid; i < t.n; i += nth) {
+      const float ax = fabsf(t.p[i]);
+      racc += (double)(ax * ax * ax);
+    }
+  }
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = racc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += sh[i];
+    a.reg_partials[blockIdx.x] = s;
+  }
+}
+
 }  // namespace kge
 
 using namespace kge;
@@ -222,6 +247,28 @@ extern "C" int kge_adam_step(const kge_adam_tensor_t *ts, int nt, double lr, dou
     a.reg_partials = reg_partials;
   }
   adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_l3_partials(const kge_adam_tensor_t *ts, int nt, double *reg_partials, int64_t n_reg_partials,
+                               void *stream) {
+  KGE_REQUIRE(ts && nt >= 1 && nt <= 4 && reg_partials && n_reg_partials >= 1, "bad arguments");
+  AdamArgs a{};
+  a.nt = nt;
+  int64_t total = 0;
+  for (int i = 0; i < nt; ++i) {
+    KGE_REQUIRE(ts[i].param && ts[i].numel > 0, "bad tensor %d", i);
+    a.t[i] = AdamTensor{ts[i].param, nullptr, nullptr, nullptr, ts[i].numel, AdamScalars{}, ts[i].l3};
+    total += ts[i].numel;
+  }
+  int grid = (int)((total + 1023) / 1024);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > n_reg_partials) grid = (int)n_reg_partials;
+  if (grid < 1) grid = 1;
+  KGE_CUDA_OK(cudaMemsetAsync(reg_partials, 0, sizeof(double) * n_reg_partials, (cudaStream_t)stream));
+  a.reg_partials = reg_partials;
+  l3_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   KGE_CUDA_OK(cudaGetLastError());
   return KGE_OK;
 }

@@ -31,6 +31,7 @@ struct PeerTensor {
   float *p, *m, *v;
   int64_t off, n;                // position of the tensor's gradient inside the workspace (floats), element count
   float step_size, bc2_sqrt;
+  int l3;                        // this tensor takes part in the L3 regulariser (model.py:290-297)
 };
 struct PeerArgs {
   float *grad[PEER_MAX];         // workspace base of every rank (peer-mapped); grad[rank] is local
@@ -44,7 +45,7 @@ struct PeerArgs {
   int64_t lo4, hi4;              // slice of the region this rank owns, in float4 units
   int64_t row_off, row_n;        // loss rows inside the workspace (floats); summed over ranks into rows_out
   float *rows_out;
-  float w1, b2, w2, eps;
+  float w1, b2, w2, eps, l3x3;   // l3x3 = 3 * regularization (0: no L3 term)
   int32_t *err;
   unsigned long long timeout_ns; // bound on a barrier wait
 };
@@ -116,7 +117,8 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs &a, int channel) {
 }
 
 __device__ __forceinline__ void peer_adam(float &p, float g, float &m, float &v, const PeerArgs &a, const PeerTensor &t) {
-  m = m + (g - m) * a.w1;                                  // same operation order as adam_elem (kge_optim.cu)
+  if (t.l3) g = g + a.l3x3 * p * fabsf(p);                 // dense L3 gradient on the (replicated) parameter, added once
+  m = m + (g - m) * a.w1;                                  // same operation order as adam_elem (kge_adam.cuh)
   v = v * a.b2;
   v = v + a.w2 * g * g;
   const float denom = sqrtf(v) / t.bc2_sqrt + a.eps;
@@ -298,7 +300,7 @@ extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch,
                                     int nt, int64_t param_floats, int64_t region_begin4, int64_t region_end4,
                                     int64_t slice_begin4, int64_t slice_end4, int64_t row_offset, int64_t row_floats,
                                     float *rows_out, double lr, double beta1, double beta2, double eps,
-                                    int32_t *err_flag, void *stream) {
+                                    double l3_coefficient, int32_t *err_flag, void *stream) {
   KGE_REQUIRE(grp && ts && nt >= 1 && nt <= 3, "kge_peer_reduce_adam takes 1..3 tensors");
   KGE_REQUIRE(grp->world >= 2 && grp->world <= PEER_MAX && grp->rank >= 0 && grp->rank < grp->world,
               "peer group of %d ranks not supported (2..%d)", grp->world, PEER_MAX);
@@ -326,11 +328,12 @@ extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch,
     const double bc1 = 1.0 - pow(beta1, (double)ts[i].step);
     const double bc2 = 1.0 - pow(beta2, (double)ts[i].step);
     a.t[i] = PeerTensor{ts[i].param, ts[i].exp_avg, ts[i].exp_avg_sq, off, ts[i].numel, (float)(-(lr / bc1)),
-                        (float)sqrt(bc2)};
+                        (float)sqrt(bc2), (ts[i].l3 && l3_coefficient != 0.0) ? 1 : 0};
   }
   a.rlo4 = region_begin4; a.rhi4 = region_end4; a.lo4 = slice_begin4; a.hi4 = slice_end4;
   a.row_off = row_offset; a.row_n = row_floats; a.rows_out = rows_out;
   a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
+  a.l3x3 = (float)(3.0 * l3_coefficient);
   a.err = err_flag;
   {
     const char *t = getenv("KGE_PEER_TIMEOUT_S");          // a rank that is later than this aborts the step (err_flag 2)

@@ -125,14 +125,17 @@ SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int
   return ws;
 }
 
-// The single-read path needs 16-byte rows that fit one k-tile, >= 8 candidates and 32-bit pair counts; it pays a fixed
-// cost per touched entity, so it wins when an entity collects several pairs (17 at FB15k shapes: 0.73 vs 0.96 ms) and
-// loses when pairs are sparse (3.3 at YAGO3-10 shapes: 1.59 vs 0.99 ms).  KGE_FORCE_SPLIT / KGE_NO_SPLIT override.
-bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity) {
+// The single-read path needs 16-byte rows that fit one k-tile, >= 8 candidates and 32-bit pair counts.  With dense
+// gradients it pays a fixed cost per touched entity, so it wins when an entity collects several pairs (17 at FB15k
+// shapes: 0.73 vs 0.96 ms) and loses when pairs are sparse (3.3 at YAGO3-10 shapes: 1.59 vs 0.99 ms).  With the entity
+// table's Adam update fused into the entity pass every entity is visited anyway (dense Adam) and the pass replaces the
+// zero-fill, the atomic scatter and the optimizer's 7 table streams: it wins at every density (YAGO3-10 shapes: 1.06 vs
+// 1.63 ms per step).  KGE_FORCE_SPLIT / KGE_NO_SPLIT override.
+bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity, bool fused_adam) {
   if (getenv("KGE_NO_SPLIT") || getenv("KGE_NO_TMA")) return false;
   if (d % 4 || De % 4 || d / 4 > 32 * (cplx ? 8 : 16)) return false;
   if (N < 8 || nentity >= (1ll << 31) || rows * (N + 3) >= (1ll << 31)) return false;
-  return rows * N >= 6 * nentity || getenv("KGE_FORCE_SPLIT");
+  return fused_adam || rows * N >= 6 * nentity || getenv("KGE_FORCE_SPLIT");
 }
 
 static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t st, void *workspace = nullptr,
@@ -274,18 +277,18 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
                          score_out, workspace, workspace_bytes, err_flag, nullptr, stream);
 }
 
-static bool plan_split(const kge_model_t *m, int64_t rows, int64_t N) {
+static bool plan_split(const kge_model_t *m, int64_t rows, int64_t N, bool fused_adam) {
   const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
   const int64_t d = cplx ? m->entity_dim / 2 : m->entity_dim;
-  return ((uintptr_t)m->entity & 15) == 0 && split_path_shape_ok(rows, N, m->entity_dim, d, cplx, m->nentity);
+  return ((uintptr_t)m->entity & 15) == 0 && N <= 8192 &&
+         split_path_shape_ok(rows, N, m->entity_dim, d, cplx, m->nentity, fused_adam);
 }
 
 extern "C" int kge_train_plan(const kge_model_t *m, int64_t rows, int64_t N) {
   if (check_model(m) || rows <= 0 || N <= 0) return 0;
   // the fit of the kernel's shared-memory carve-up (>= 4 warps next to q, dq, 2N scores) holds for every N that passes
   // launch_rows' own limit when rows fit one k-tile, except absurdly long candidate lists
-  const bool split = plan_split(m, rows, N) && N <= 8192;
-  return split ? (KGE_PLAN_SINGLE_READ | KGE_PLAN_ENTITY_ADAM) : 0;
+  return (plan_split(m, rows, N, false) ? KGE_PLAN_SINGLE_READ : 0) | (plan_split(m, rows, N, true) ? KGE_PLAN_ENTITY_ADAM : 0);
 }
 
 extern "C" int kge_train_rows_adam(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,

@@ -61,7 +61,7 @@ struct SplitWs {             // carved from the caller's workspace
 size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity);
 SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity);
 // does the launcher take the single-read path for this shape (same predicate in kge_train_plan and launch_rows_model)?
-bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity);
+bool split_path_shape_ok(int64_t rows, int64_t N, int64_t De, int64_t d, bool cplx, int64_t nentity, bool fused_adam);
 
 // per-model entry points (explicitly instantiated in kge_train_inst.cu)
 template <int MODEL>

@@ -58,10 +58,10 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   return KGE_OK;
 }
 
-// which register / shared-memory variant of row_kernel_split runs (KGE_SPLIT_VARIANT=0|1|2 overrides; see split_warps)
+// which register / shared-memory variant of row_kernel_split runs (KGE_SPLIT_VARIANT=0..4 overrides; see split_warps)
 static int split_variant() {
   const char *v = getenv("KGE_SPLIT_VARIANT");
-  if (v && v[0] >= '0' && v[0] <= '2' && !v[1]) return v[0] - '0';
+  if (v && v[0] >= '0' && v[0] <= '4' && !v[1]) return v[0] - '0';
   return 2;
 }
 
@@ -77,7 +77,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
     const size_t rowbytes = (size_t)a.De * 4;
     const bool split = workspace && (a.gE || want_adam) && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
                        workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
-                       split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity);
+                       split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity,
+                                           want_adam && a.pos_row_loss && !a.defer_entity);
     // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
     if (split) {
       constexpr int Hs = CPLX ? 2 : 1;
@@ -86,13 +87,16 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       const int var = split_variant();
       const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
       const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
-      const size_t per_warp = 2 * hs * sizeof(float) + 16;
+      // Ws = row groups per CTA (one warp each, or a pair of warps: variants 3 / 4); a group owns two slots, two
+      // mbarriers and the pair's exchange words
+      const int wpr = split_warps_per_row(var);
+      const size_t per_warp = 2 * hs * sizeof(float) + 16 + 16;
       int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
-      const int wcap = split_warps(CPLX, nch, var);
+      const int wcap = split_warps(CPLX, nch, var) / wpr;
       if (Ws > wcap) Ws = wcap;
       if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
       if (Ws > wcap) Ws = wcap;
-      if (Ws >= 4 && fixed_s + Ws * per_warp <= 227 * 1024) {
+      if (Ws >= (wpr == 2 ? 2 : 4) && fixed_s + Ws * per_warp <= 227 * 1024) {
         const size_t total = fixed_s + Ws * per_warp;
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
         // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
@@ -109,12 +113,14 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
   do {                                                                                                 \
     auto k = row_kernel_split<MODEL, HEAD, NCH, VAR>;                                                  \
     KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
-    k<<<sgrid, Ws * 32, total, st>>>(a, ws);                                                           \
+    k<<<sgrid, Ws * wpr * 32, total, st>>>(a, ws);                                                     \
   } while (0)
 #define KGE_SPLIT_LAUNCH(NCH)                                                                          \
   do {                                                                                                 \
     if (var == 0) KGE_SPLIT_LAUNCH2(NCH, 0);                                                           \
     else if (var == 1) KGE_SPLIT_LAUNCH2(NCH, 1);                                                      \
+    else if (var == 3) KGE_SPLIT_LAUNCH2(NCH, 3);                                                      \
+    else if (var == 4) KGE_SPLIT_LAUNCH2(NCH, 4);                                                      \
     else KGE_SPLIT_LAUNCH2(NCH, 2);                                                                    \
   } while (0)
         if (nch == 4) KGE_SPLIT_LAUNCH(4);

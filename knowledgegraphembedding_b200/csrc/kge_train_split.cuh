@@ -34,6 +34,11 @@ namespace kge {
 //   0  u parked in the slot (STS + second LDS pass + a proxy fence per candidate), q in shared memory   [round 1]
 //   1  u in registers, q in shared memory
 //   2  u and q in registers: per candidate the only shared-memory traffic is one read of the row
+//   3  like 2, but TWO warps share a candidate row (each covers half of the 128-float chunks): a third of the
+//      registers per thread less, so 12 warps (6 pairs) instead of 8 are resident to cover the fixed-latency stalls that
+//      ncu r2a shows for variant 2 (36 % issue-slot use with 2 warps per scheduler); the halves of the score meet through
+//      one shared-memory word per warp and one 64-thread named barrier per candidate
+//   4  like 3 with 16 warps (8 pairs) at 128 registers
 // ncu r1l showed variant 0 bound by shared-memory bandwidth (40 KB moved per 8 KB candidate row: TMA write, x, q,
 // u out, u back); variants 1 / 2 move 24 / 16 KB.  The register footprint (acc + u [+ q] = 2-3 x the lane's share of the
 // row) sets the warp count: f = chunks per lane (H * NCH).
@@ -41,8 +46,11 @@ __host__ __device__ constexpr int split_warps(bool cplx, int nch, int var) {
   const int f = (cplx ? 2 : 1) * nch;
   if (var == 0) return f >= 16 ? 13 : 16;                 // 13 x 32 x 128 registers; 8 KB slots
   if (var == 1) return f >= 16 ? 12 : 16;                 // 128 + ~45 registers -> 168 at 12 warps (3 per sub-partition)
-  return f >= 16 ? 8 : (f >= 8 ? 12 : 16);                // 192 + ~45 -> 255 at 8 warps; 96 + 45 -> 168 at 12
+  if (var == 2) return f >= 16 ? 8 : (f >= 8 ? 12 : 16);  // 192 + ~45 -> 255 at 8 warps; 96 + 45 -> 168 at 12
+  if (var == 3) return f >= 16 ? 12 : 16;                 // warp pairs: 96 + ~45 registers
+  return 16;
 }
+__host__ __device__ constexpr int split_warps_per_row(int var) { return var >= 3 ? 2 : 1; }
 
 // element value and u for one 4-float group (both halves); OP_CDIST runs on packed pairs (FADD2 / FMUL2 / FFMA2)
 template <int OP>
@@ -82,10 +90,15 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   constexpr int DP = 128 * NCH;                 // padded half length (floats)
   constexpr int HS = H * DP;                    // slot size (floats)
   constexpr bool UREG = VAR >= 1, QREG = VAR >= 2;
+  constexpr int WPR = split_warps_per_row(VAR);  // warps sharing one candidate row
+  constexpr int NCL = NCH / WPR;                 // 128-float chunks (per half) this lane's warp covers
   extern __shared__ __align__(128) float smem[];
   const int Dq4 = (a.De + 3) & ~3;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  // layout: [slots: nwarps x 2 x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers], all derived from `smem`
+  const int tid = threadIdx.x, lane = tid & 31;
+  // `warp` / `nwarps` index the row groups (one warp, or a pair of warps: hw = which half of the chunks this warp covers)
+  const int warp = (tid >> 5) / WPR, nwarps = (blockDim.x >> 5) / WPR, hw = (tid >> 5) % WPR;
+  const int c0 = hw * NCL;                        // first chunk of this warp
+  // layout: [slots: nwarps x 2 x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers | pair exchange], from `smem`
   float *slot0 = smem + (size_t)(2 * warp) * HS, *slot1 = slot0 + HS;
   float *q = smem + (size_t)(2 * nwarps) * HS;
   float *dq = q + HS;                           // compact [d | d]
@@ -96,6 +109,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   const uint32_t halfbytes = (uint32_t)a.d * 4u;
   uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
   uint32_t par0 = 0, par1 = 0;
+  float *xch = reinterpret_cast<float *>(bars + 2 * nwarps) + 4 * warp;      // [2 parities][2 halves] partial scores
 
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const bool adversarial = a.do_loss && a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL;
@@ -107,7 +121,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       smem[(size_t)sl * HS + (r / padn) * DP + a.d + (r % padn)] = 0.f;
     }
   }
-  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  if (lane == 0 && hw == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       }
       int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
-      if (lane == 0) {
+      if (lane == 0 && hw == 0) {
         atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
         uint64_t *bar = s ? bar1 : bar0;
         float *dst = s ? slot1 : slot0;
@@ -169,17 +183,17 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     __syncthreads();
 
     // ---- phase 1: per candidate, score (sweep 1) and deferred-normalised dL/dq (sweep 2) ------------------
-    f2 acc[NCH][H][2];
+    f2 acc[NCL][H][2];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i = 0; i < NCL; ++i)
 #pragma unroll
       for (int h = 0; h < H; ++h) { acc[i][h][0] = pack2(0.f, 0.f); acc[i][h][1] = pack2(0.f, 0.f); }
     float Mw = -INFINITY;                                  // running max of alpha * s over this warp's rows
-    const float *ql = q + lane * V;
-    float qr[QREG ? NCH : 1][H][V];
+    const float *ql = q + c0 * 128 + lane * V;
+    float qr[QREG ? NCL : 1][H][V];
     if constexpr (QREG) {
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
+      for (int i = 0; i < NCL; ++i) {
         load_shared<V>(qr[i][0], ql + i * 128);
         if constexpr (CPLX) load_shared<V>(qr[i][1], ql + DP + i * 128);
       }
@@ -189,13 +203,13 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       for (int n = warp; n < a.N; n += nwarps, ++it) {
         const int s = (it + fs) & 1;
         if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-        float *xl = (s ? slot1 : slot0) + lane * V;
+        float *xl = (s ? slot1 : slot0) + c0 * 128 + lane * V;
         // sweep 1: element values -> score; u = d(value)/dq stays in registers (VAR >= 1) or is parked in the slot
         float part = 0.f;
         f2 part2 = pack2(0.f, 0.f);
-        f2 u[UREG ? NCH : 1][H][2];
+        f2 u[UREG ? NCL : 1][H][2];
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
+        for (int i = 0; i < NCL; ++i) {
           float x0[V], x1[V], q0[V], q1[V];
           load_shared<V>(x0, xl + i * 128);
           if constexpr (CPLX) load_shared<V>(x1, xl + DP + i * 128);
@@ -231,8 +245,17 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
           part = pa + pb;
         }
         float coef;
-        if (a.do_loss) {
+        if constexpr (WPR == 2) {
+          // the two halves of the score meet here: one word per warp (double-buffered by candidate parity), one named
+          // barrier of the pair; both warps then hold the same sum and run the same softmax bookkeeping
           part = warp_sum(part);
+          float *xc = xch + 2 * (it & 1);
+          if (lane == 0) xc[hw] = part;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory");
+          part = xc[0] + xc[1];
+        }
+        if (a.do_loss) {
+          if constexpr (WPR == 1) part = warp_sum(part);
           if constexpr (UREG) {
             // every lane's reads of the slot fed the reduction above: the slot can take the next row already, while
             // the softmax bookkeeping and the accumulate step run from registers
@@ -240,7 +263,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
             if (n + 2 * nwarps < a.N) issue(s, it + 2);
           }
           const float sv = finish_score<MODEL>(part, a.gamma, modulus);
-          if (lane == 0) {
+          if (lane == 0 && hw == 0) {
             sc[n] = sv;
             if (a.score_out) a.score_out[(int64_t)rl * a.N + n] = sv;
           }
@@ -250,7 +273,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
               const float r = expf(Mw - z);                // 0 on the first row (Mw = -inf)
               const f2 r2 = pack2(r, r);
 #pragma unroll
-              for (int i = 0; i < NCH; ++i)
+              for (int i = 0; i < NCL; ++i)
 #pragma unroll
                 for (int h = 0; h < H; ++h) { acc[i][h][0] = mul2(acc[i][h][0], r2); acc[i][h][1] = mul2(acc[i][h][1], r2); }
               Mw = z;
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         const f2 c2 = pack2(coef, coef);
         if constexpr (UREG) {
 #pragma unroll
-          for (int i = 0; i < NCH; ++i)
+          for (int i = 0; i < NCL; ++i)
 #pragma unroll
             for (int h = 0; h < H; ++h) {
               acc[i][h][0] = fma2(c2, u[i][h][0], acc[i][h][0]);
@@ -278,7 +301,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
             }
         } else {
 #pragma unroll
-          for (int i = 0; i < NCH; ++i) {                  // each lane re-reads exactly the slot words it wrote
+          for (int i = 0; i < NCL; ++i) {                  // each lane re-reads exactly the slot words it wrote
             float u0[V], u1[V];
             load_shared<V>(u0, xl + i * 128);
             if constexpr (CPLX) load_shared<V>(u1, xl + DP + i * 128);
@@ -352,10 +375,10 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     // ---- phase 4: fold the per-warp partial dL/dq.  Each warp parks its (scaled) accumulators in its own idle
     // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
     {
-      float *pl = slot0 + lane * V;
+      float *pl = slot0 + c0 * 128 + lane * V;
       const f2 f2v = pack2(factor, factor);
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
+      for (int i = 0; i < NCL; ++i) {
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           float t0, t1, t2, t3;
@@ -692,17 +715,19 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
         for (int c = 0; c < CH; ++c) {
           const int u = lane + 32 * c;
           if (u < ucnt) {
-            float p[V], g[V];
-            unpack2(acc[c][h][0], g[0], g[1]);
-            unpack2(acc[c][h][1], g[2], g[3]);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              p[j] = h == 0 ? x0[c][j] : x1[CPLX ? c : 0][j];
-              adam_elem(p[j], g[j], mm[c][j], vv[c][j], a.adam, l3, racc);
-            }
-            *reinterpret_cast<float4 *>(a.E + hb + u * V) = make_float4(p[0], p[1], p[2], p[3]);
-            *reinterpret_cast<float4 *>(a.exp_avg + hb + u * V) = make_float4(mm[c][0], mm[c][1], mm[c][2], mm[c][3]);
-            *reinterpret_cast<float4 *>(a.exp_avg_sq + hb + u * V) = make_float4(vv[c][0], vv[c][1], vv[c][2], vv[c][3]);
+            const float *px = h == 0 ? x0[c] : x1[CPLX ? c : 0];
+            f2 p01 = pack2(px[0], px[1]), p23 = pack2(px[2], px[3]);
+            f2 m01 = pack2(mm[c][0], mm[c][1]), m23 = pack2(mm[c][2], mm[c][3]);
+            f2 v01 = pack2(vv[c][0], vv[c][1]), v23 = pack2(vv[c][2], vv[c][3]);
+            adam_pair_fast(p01, acc[c][h][0], m01, v01, a.adam, l3, racc);
+            adam_pair_fast(p23, acc[c][h][1], m23, v23, a.adam, l3, racc);
+            float t0, t1, t2, t3;
+            unpack2(p01, t0, t1); unpack2(p23, t2, t3);
+            *reinterpret_cast<float4 *>(a.E + hb + u * V) = make_float4(t0, t1, t2, t3);
+            unpack2(m01, t0, t1); unpack2(m23, t2, t3);
+            *reinterpret_cast<float4 *>(a.exp_avg + hb + u * V) = make_float4(t0, t1, t2, t3);
+            unpack2(v01, t0, t1); unpack2(v23, t2, t3);
+            *reinterpret_cast<float4 *>(a.exp_avg_sq + hb + u * V) = make_float4(t0, t1, t2, t3);
           }
         }
       }

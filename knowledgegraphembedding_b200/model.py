@@ -547,7 +547,7 @@ class KGEModel(nn.Module):
 
         # ---- multi-GPU plan: NVLink peer-memory exchange (csrc/kge_peer.cu) when it is set up and Adam is fused,
         # otherwise one NCCL all-reduce of the workspace followed by the replicated optimizer
-        peer = ws['peer'] if (world > 1 and fused_adam and reg == 0.0) else None
+        peer = ws['peer'] if (world > 1 and fused_adam) else None
         regions = entity_slices = None
         if peer is not None:
             from .peer import exchange_regions
@@ -612,8 +612,11 @@ class KGEModel(nn.Module):
             if fused_adam:
                 entries, hyper = adam_entries()
             if peer is not None:
+                if reg != 0.0:                       # value of the L3 term from the replicated pre-update tables
+                    tensors = (_lib.KgeAdamTensor * len(entries))(*[_lib.KgeAdamTensor(*c) for c in entries])
+                    _lib.call("kge_l3_partials", tensors, len(entries), _ptr(ws['reg']), ws['reg'].numel(), st)
                 peer.reduce_adam(entries, hyper, ws['param_floats'], regions[0], ws['param_floats'], 2 * B,
-                                 ws['rows_sum'], err, st)
+                                 ws['rows_sum'], err, st, l3=reg)
             elif world > 1:
                 torch.distributed.all_reduce(ws['flat'])     # [dE|dR|dM|row losses] in one piece
         else:
@@ -626,6 +629,9 @@ class KGEModel(nn.Module):
                           _ptr(neg_row), _ptr(pos_row), _ptr(ws['gE']), _ptr(ws['gR']), _ptr(gM), _ptr(wsp),
                           wbytes, _ptr(err), ctypes.byref(pending), st)
             entries, hyper = adam_entries()
+            if reg != 0.0:
+                tensors = (_lib.KgeAdamTensor * len(entries))(*[_lib.KgeAdamTensor(*c) for c in entries])
+                _lib.call("kge_l3_partials", tensors, len(entries), _ptr(ws['reg']), ws['reg'].numel(), st)
             main = torch.cuda.current_stream(dev)
             side = model._ws.get('exchange_stream')
             if side is None:
@@ -645,7 +651,7 @@ class KGEModel(nn.Module):
                         xev0.record()
                 side.wait_stream(main)
                 peer.reduce_adam(entries, hyper, ws['param_floats'], region, ws['param_floats'],
-                                 2 * B if k == last else 0, ws['rows_sum'], err, side_ptr)
+                                 2 * B if k == last else 0, ws['rows_sum'], err, side_ptr, l3=reg)
             main.wait_stream(side)
         if peer is not None:
             pos_rows, neg_rows = ws['rows_sum'][:B], ws['rows_sum'][B:]

@@ -175,7 +175,7 @@ class PeerExchange:
         self.workspace = block[FLAG_BYTES:].view(torch.float32)        # [capacity] fp32, zero-initialised
         return ptrs, []
 
-    def reduce_adam(self, entries, hyper, param_floats, region, row_offset, row_floats, rows_out, err, stream):
+    def reduce_adam(self, entries, hyper, param_floats, region, row_offset, row_floats, rows_out, err, stream, l3=0.0):
         """Exchange one region (begin4, end4) of the parameter part.  entries: [(param_ptr, grad_ptr, exp_avg_ptr,
         exp_avg_sq_ptr, numel, step, 0)], as for kge_adam_step; row_floats > 0 also sums the loss rows."""
         self.epoch += 1
@@ -183,7 +183,7 @@ class PeerExchange:
         tensors = (_lib.KgeAdamTensor * len(entries))(*[_lib.KgeAdamTensor(*c) for c in entries])
         _lib.call("kge_peer_reduce_adam", ctypes.byref(self.struct), self.epoch, tensors, len(entries), param_floats,
                   region[0], region[1], lo4, hi4, row_offset, row_floats,
-                  ctypes.c_void_p(rows_out.data_ptr()) if row_floats else None, *hyper,
+                  ctypes.c_void_p(rows_out.data_ptr()) if row_floats else None, *hyper, float(l3),
                   ctypes.c_void_p(err.data_ptr()), stream)
 
     def close(self):

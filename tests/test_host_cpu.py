@@ -235,14 +235,14 @@ def test_peer_abi_argument_errors_without_a_gpu():
     lib = _lib.load()
     grp = _lib.KgePeerGroup(world=1, rank=0)
     t = (_lib.KgeAdamTensor * 1)(_lib.KgeAdamTensor(16, 16, 16, 16, 4, 1, 0))
-    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None)
     assert rc == _lib.ERR_INVALID and b"peer group of 1 ranks not supported" in lib.kge_last_error()
     grp = _lib.KgePeerGroup(world=2, rank=0)
-    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 6, 0, 1, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 6, 0, 1, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None)
     assert rc == _lib.ERR_INVALID and b"multiple of 4" in lib.kge_last_error()
-    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 1, 3, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 1, 3, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None)
     assert rc == _lib.ERR_INVALID and b"bad region / slice" in lib.kge_last_error()
-    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, None, None)
+    rc = lib.kge_peer_reduce_adam(ctypes.byref(grp), 1, t, 1, 8, 0, 2, 0, 1, 8, 0, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None)
     assert rc == _lib.ERR_INVALID and b"peer 0 is not mapped" in lib.kge_last_error()
 
 

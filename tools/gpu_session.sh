@@ -1,0 +1,35 @@
+#!/bin/bash
+# One gpurun session: tests, microbenchmark, bench variants, ncu captures.  Usage: tools/gpu_session.sh <tag> [steps...]
+# Everything lands under gpurun_out/<tag>/ ; each step has its own timeout so that a hang cannot eat the box.
+TAG=${1:-s}; shift
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+STEPS=${@:-"tests l2 variants bench ref ncu"}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/smi.txt 2>&1
+for S in $STEPS; do
+  case $S in
+    tests)  timeout 1500 python -m pytest tests -m gpu -q -x --timeout=600 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/rc.txt ;;
+    tests_all) timeout 1800 python -m pytest tests -m gpu -q --timeout=600 > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/rc.txt ;;
+    smoke)  timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/rc.txt ;;
+    l2)     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o /tmp/l2_gather_bench tools/l2_gather_bench.cu 2> $OUT/l2_gather.err \
+              && timeout 120 /tmp/l2_gather_bench > $OUT/l2_gather.json 2>> $OUT/l2_gather.err; echo "l2 rc=$?" >> $OUT/rc.txt ;;
+    variants)
+      for V in 2 3 4; do
+        KGE_SPLIT_VARIANT=$V timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_var$V.json 2> $OUT/bench_var$V.err
+        echo "variant $V rc=$?" >> $OUT/rc.txt
+      done
+      KGE_KEEP_GRADS=1 timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_keepgrads.json 2> $OUT/bench_keepgrads.err
+      echo "keepgrads rc=$?" >> $OUT/rc.txt ;;
+    bench)  timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/rc.txt ;;
+    hostprof) timeout 300 python tools/profile_host.py > $OUT/hostprof.txt 2>&1; echo "hostprof rc=$?" >> $OUT/rc.txt ;;
+    yago)   KGE_FORCE_SPLIT=1 timeout 300 python bench.py --workload rotate_yago310 --no-extras --no-cpu-baseline --no-parity --eval-queries 1024 > $OUT/bench_yago_split.json 2> $OUT/bench_yago_split.err; echo "yago rc=$?" >> $OUT/rc.txt ;;
+    ref)    timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?" >> $OUT/rc.txt ;;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 512 > $OUT/ncu_launch.log 2>&1
+      echo "ncu launches rc=$?" >> $OUT/rc.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"row_kernel_split|entity_kernel" -c 4 -o $OUT/prof_train \
+        python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 512 > $OUT/ncu_full.log 2>&1
+      echo "ncu full rc=$?" >> $OUT/rc.txt ;;
+  esac
+done
+cat $OUT/rc.txt

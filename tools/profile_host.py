@@ -1,51 +1,73 @@
-"""Host-side profile of KGEModel.train_step (cProfile) on one GPU: where the Python time of a step goes."""
+#!/usr/bin/env python
+"""Where does the host time of one KGEModel.train_step go?  (the `e2e` number pays it on every step: the log dict is
+read back, so host work and GPU work do not overlap across steps)
+
+  python tools/profile_host.py            # cfg-3 shape, pinned host batches; prints phase timings + cProfile top entries
+"""
 import cProfile
 import os
 import pstats
 import sys
+import time
 import types
 
+import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench                                             # noqa: E402
-from knowledgegraphembedding_b200 import KGEModel        # noqa: E402
-from oracle import kge_oracle as O                       # noqa: E402
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from knowledgegraphembedding_b200 import KGEModel  # noqa: E402
 
 
 def main():
-    model, nentity, nrel, d, gamma, B, N, lr, de, dr = bench.WORKLOADS["rotate_fb15k"]
-    dev = torch.device("cuda", 0)
-    st = O.init_tables(model, nentity, nrel, d, gamma, de, dr, seed=0)
-    m = KGEModel(model, nentity, nrel, d, gamma, double_entity_embedding=de, double_relation_embedding=dr)
-    with torch.no_grad():
-        m.entity_embedding.copy_(torch.from_numpy(st["entity_embedding"]))
-        m.relation_embedding.copy_(torch.from_numpy(st["relation_embedding"]))
-    m = m.to(dev)
-    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
-    args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=True, adversarial_temperature=1.0,
-                                 uni_weight=False, regularization=0.0)
-    pool = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(w).pin_memory(), md)
-            for p, n, w, md in bench.make_batches(nentity, nrel, B, N, 8, seed=1)]
-
-    class It:
-        i = 0
-
-        def __next__(self):
-            It.i += 1
-            return pool[It.i % len(pool)]
-
-    it = It()
-    for _ in range(20):
-        KGEModel.train_step(m, opt, it, args)
+    wl = "rotate_fb15k"
+    model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = bench.WORKLOADS[wl]
+    b = bench.Bench(types.SimpleNamespace())
+    m, opt, targs, _ = b.build_model(wl)
+    pool = bench.make_batches(nentity, nrel, B, N, 8, seed=1)
+    pin = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(w).pin_memory(), md)
+           for p, n, w, md in pool]
+    dev = [(p.cuda(), n.cuda(), w.cuda(), md) for p, n, w, md in pin]
+    for i in range(10):
+        KGEModel.train_step(m, opt, iter([pin[i % 8]]), targs)
     torch.cuda.synchronize()
+    # (1) host-only cost of launching one step (device-resident inputs, no sync between steps)
+    steps = 300
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.train_step_async(opt, dev[i % 8], targs)
+    host_launch = (time.perf_counter() - t0) / steps
+    torch.cuda.synchronize()
+    # (2) full e2e step
+    t0 = time.perf_counter()
+    for i in range(steps):
+        KGEModel.train_step(m, opt, iter([pin[i % 8]]), targs)
+    e2e = (time.perf_counter() - t0) / steps
+    # (3) the pure H2D of one batch + a sync
+    t0 = time.perf_counter()
+    for i in range(steps):
+        p, n, w, _ = pin[i % 8]
+        p.cuda(non_blocking=True); n.cuda(non_blocking=True); w.cuda(non_blocking=True)
+        torch.cuda.synchronize()
+    h2d = (time.perf_counter() - t0) / steps
+    # (4) an empty round trip: tiny kernel + .cpu()
+    z = torch.zeros(8, device="cuda")
+    t0 = time.perf_counter()
+    for i in range(steps):
+        z.cpu()
+    rt = (time.perf_counter() - t0) / steps
+    print(f"host time to enqueue one step (no sync): {host_launch * 1e6:.1f} us   [GPU-bound loop if > kernel time]")
+    print(f"e2e step (pinned batch, log read back):     {e2e * 1e6:.1f} us")
+    print(f"H2D of one batch + sync:                    {h2d * 1e6:.1f} us")
+    print(f"device->host read of 32 B (idle GPU):       {rt * 1e6:.1f} us")
     pr = cProfile.Profile()
     pr.enable()
-    for _ in range(300):
-        KGEModel.train_step(m, opt, it, args)
+    for i in range(steps):
+        KGEModel.train_step(m, opt, iter([pin[i % 8]]), targs)
     pr.disable()
-    torch.cuda.synchronize()
-    pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+    st = pstats.Stats(pr)
+    st.sort_stats("tottime").print_stats(22)
 
 
 if __name__ == "__main__":
