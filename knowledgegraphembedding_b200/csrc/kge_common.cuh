@@ -110,6 +110,30 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 }
 constexpr float kFltMin = 1.17549435e-38f;
 
+// ---- L2 residency hints (createpolicy + .L2::cache_hint) -------------------------------------------------------
+// The 120 MB entity table of FB15k-sized models almost fits the 126 MB L2, but every train step also streams the two
+// Adam moment tables (240 MB read + 240 MB written) through it.  Tagging the moment traffic evict_first and the entity
+// rows evict_last keeps the table that the NEXT step gathers at random resident.  kind: 0 normal, 1 evict_first, 2 evict_last.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld4_hint(const float *p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st4_hint(float *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+
 // ---- packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two IEEE-rn operations ------------
 struct f2 { unsigned long long v; };
 __device__ __forceinline__ f2 pack2(float lo, float hi) {

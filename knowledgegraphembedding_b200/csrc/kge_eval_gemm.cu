@@ -14,10 +14,13 @@
 // ranks) are therefore identical to the exact SIMT kernel's, whatever the tensor core's internal rounding is.
 //
 // Kernel anatomy (one CTA per 128-query tile, looping over 128-entity tiles):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128 rows x 32 fp32, SWIZZLE_128B) of the query and
-//            entity pieces into a 6-stage shared-memory ring, mbarrier complete_tx
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) on
-//            shared-memory descriptors, accumulating in TMEM; tcgen05.commit frees ring slots / publishes tiles
+//   warp 0   TMA producer: per 32-wide k-block FOUR cp.async.bulk.tensor 2-D tiles (128 rows x 32 fp32, SWIZZLE_128B:
+//            Q_hi, Q_lo, E_hi, E_lo) into one stage of a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) per stage
+//            -- hi*hi, hi*lo, lo*hi on the same four tiles -- accumulating in TMEM; tcgen05.commit frees ring slots /
+//            publishes tiles.  (Round 1 streamed the three products as separate passes over two-tile stages: 32 KB of
+//            operands per 4 MMAs = 120 B/clk per SM, more than L2 delivers; ncu r1g: tensor pipe 52 % active.  Four
+//            tiles feed 12 MMAs: 80 B/clk.)
 //   warp 2   TMEM allocator (256 columns = two accumulator buffers)
 //   warps 4-7  epilogue: tcgen05.ld 32x32b (lane = query row), band test, filter bitmap, counts, ambiguous list
 #include <cuda.h>
@@ -26,7 +29,7 @@
 
 namespace kge {
 
-constexpr int GM = 128, GN = 128, GK = 32, GSTAGES = 6, GTHREADS = 256;
+constexpr int GM = 128, GN = 128, GK = 32, GSTAGES = 3, GTHREADS = 256;
 constexpr uint32_t kTileBytes = GM * GK * 4;                  // 16 KB per operand tile
 // eps = band * |q| * |e| with band = kBandSplit + kBandPerKBlock * (number of 32-wide k-blocks issued):
 //   kBandSplit      operand residuals (3 * 2^-20), the dropped lo*lo term, and the rounding of the canonical fp32 sum
@@ -118,9 +121,8 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
                   const GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
   uint8_t *gsm = gsm_raw + ((1024u - (s32(gsm_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles need 1024-B alignment
-  uint8_t *tilesA = gsm;                                        // [GSTAGES][16 KB]
-  uint8_t *tilesB = gsm + GSTAGES * kTileBytes;                 // [GSTAGES][16 KB]
-  uint64_t *full = reinterpret_cast<uint64_t *>(gsm + 2 * GSTAGES * kTileBytes);
+  uint8_t *tiles = gsm;                                         // [GSTAGES][Q_hi | Q_lo | E_hi | E_lo][16 KB]
+  uint64_t *full = reinterpret_cast<uint64_t *>(gsm + 4 * GSTAGES * kTileBytes);
   uint64_t *empty = full + GSTAGES;
   uint64_t *tfull = empty + GSTAGES;                            // [2] accumulator ready
   uint64_t *tempty = tfull + 2;                                 // [2] accumulator drained
@@ -130,8 +132,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * GM;
   const int64_t ntiles_all = (a.ent_end - a.ent_begin + GN - 1) / GN;
-  const int kpb = (a.K + GK - 1) / GK;                          // k-blocks per operand pair
-  const int nkb = 3 * kpb;                                      // hi*hi, hi*lo, lo*hi
+  const int nkb = (a.K + GK - 1) / GK;                          // k-blocks; each carries hi*hi, hi*lo, lo*hi
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < GSTAGES; ++i) { mb_init(full + i, 1); mb_init(empty + i, 1); }
@@ -159,11 +160,14 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
       for (int64_t jt = blockIdx.y; jt < ntiles_all; jt += gridDim.y) {
         const int j0 = (int)(a.ent_begin + jt * GN);
         for (int kb = 0; kb < nkb; ++kb) {
-          const int seg = kb / kpb, kk = (kb % kpb) * GK;
+          const int kk = kb * GK;
+          uint8_t *t = tiles + (size_t)stage * 4 * kTileBytes;
           mb_wait(empty + stage, phase ^ 1);
-          mb_expect(full + stage, 2 * kTileBytes);
-          tma_2d(tilesA + stage * kTileBytes, seg == 2 ? &tmQlo : &tmQhi, kk, q0, full + stage);
-          tma_2d(tilesB + stage * kTileBytes, seg == 1 ? &tmElo : &tmEhi, kk, j0, full + stage);
+          mb_expect(full + stage, 4 * kTileBytes);
+          tma_2d(t, &tmQhi, kk, q0, full + stage);
+          tma_2d(t + kTileBytes, &tmQlo, kk, q0, full + stage);
+          tma_2d(t + 2 * kTileBytes, &tmEhi, kk, j0, full + stage);
+          tma_2d(t + 3 * kTileBytes, &tmElo, kk, j0, full + stage);
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -183,11 +187,16 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mb_wait(full + stage, phase);
           tc_fence_after();
-          const uint64_t ad = smem_desc(tilesA + stage * kTileBytes);
-          const uint64_t bd = smem_desc(tilesB + stage * kTileBytes);
+          const uint8_t *t = tiles + (size_t)stage * 4 * kTileBytes;
+          const uint64_t qhi = smem_desc(t), qlo = smem_desc(t + kTileBytes);
+          const uint64_t ehi = smem_desc(t + 2 * kTileBytes), elo = smem_desc(t + 3 * kTileBytes);
 #pragma unroll
-          for (int k = 0; k < GK / 8; ++k)                      // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
-            umma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < GK / 8; ++k) {                    // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32(d_tmem, qhi + o, ehi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(d_tmem, qhi + o, elo + o, idesc, 1u);
+            umma_tf32(d_tmem, qlo + o, ehi + o, idesc, 1u);
+          }
           umma_commit(empty + stage);                           // slot free once these MMAs have read it
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -404,7 +413,7 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   a.band = kge_eval_gemm_band(K);
   a.approx_out = approx_scores_out;
   KGE_CUDA_OK(cudaMemsetAsync(amb_count, 0, 2 * sizeof(int), st));
-  const size_t smem = 2 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
+  const size_t smem = 4 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
   KGE_CUDA_OK(cudaFuncSetAttribute(gemm_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int qtiles = (int)((Q + GM - 1) / GM);
   const int64_t jtiles = (ent_end - ent_begin + GN - 1) / GN;

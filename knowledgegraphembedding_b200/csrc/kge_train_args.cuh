@@ -41,6 +41,8 @@ struct RowArgs {
   int *entity_deferred;        // host out flag: the split path ran and its entity pass is still due
   const EntityAdam *entity_adam;   // host: fuse the entity table's Adam update into the entity-major pass (or NULL)
   int *entity_adam_applied;    // host out flag: the update was applied (gE was not written; the caller skips E in Adam)
+  int ring;                    // single-read path: slots per row group in the TMA ring (2..4)
+  int l2_hints;                // single-read path: L2 residency hints on (KGE_L2_HINTS=0 turns them off)
 };
 
 struct SplitWs {             // carved from the caller's workspace

@@ -270,6 +270,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 template <int MODEL, bool HEAD>
 __global__ void __launch_bounds__(512, 1) row_kernel_tma(const RowArgs a) {
   constexpr int OP = op_of(MODEL, HEAD);

@@ -40,10 +40,15 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   e.upp = two ? (nunits + 1) / 2 : nunits;
   // slots have the kernel's compile-time half stride: CH chunks of 32 float4 units, CH = (complex ? 8 : 16) / parts
   const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * ((CPLX ? 8 : 16) / (two ? 2 : 1)) * 32 * 16;
-  int We = (int)((227 * 1024 - 16) / (2 * slotbytes + 16));
-  const int wmax = entity_warps(two ? 2 : 1, fused);
-  if (We > wmax) We = wmax;
-  const size_t esmem = 16 + (size_t)We * (2 * slotbytes + 16);
+  // warps x ring depth: as many slots in flight as the shared memory holds (KGE_ENTITY_WARPS / KGE_ENTITY_DEPTH tune)
+  int We = entity_warps(two ? 2 : 1, fused), depth = 2;
+  if (const char *w = getenv("KGE_ENTITY_WARPS")) { const int v = atoi(w); if (v >= 1 && v <= We) We = v; }
+  while (depth < 4 && 16 + (size_t)We * (depth + 1) * (slotbytes + 16) <= 227 * 1024) ++depth;
+  if (const char *dp = getenv("KGE_ENTITY_DEPTH")) { const int v = atoi(dp); if (v >= 2 && v <= depth) depth = v; }
+  while (We > 1 && 16 + (size_t)We * depth * (slotbytes + 16) > 227 * 1024) --We;
+  e.depth = depth;
+  { const char *h = getenv("KGE_L2_HINTS"); e.l2_hints = !(h && h[0] == '0'); }
+  const size_t esmem = 16 + (size_t)We * depth * (slotbytes + 16);
 #define KGE_ENT_LAUNCH(S, F)                                                                         \
   do {                                                                                               \
     auto k = entity_kernel<MODEL, HEAD, S, F>;                                                       \
@@ -90,14 +95,22 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       // Ws = row groups per CTA (one warp each, or a pair of warps: variants 3 / 4); a group owns two slots, two
       // mbarriers and the pair's exchange words
       const int wpr = split_warps_per_row(var);
-      const size_t per_warp = 2 * hs * sizeof(float) + 16 + 16;
-      int Ws = (int)((227 * 1024 - fixed_s) / per_warp);
       const int wcap = split_warps(CPLX, nch, var) / wpr;
-      if (Ws > wcap) Ws = wcap;
+      int Ws = wcap;
       if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
       if (Ws > wcap) Ws = wcap;
+      // ring depth: as many slots as fit next to q, dq and the score arrays (KGE_SPLIT_RING=2..4 overrides)
+      auto group_bytes = [&](int depth) { return (size_t)depth * (hs * sizeof(float) + 8) + 16 + 4; };
+      int ring = 2;
+      while (ring < 4 && fixed_s + Ws * group_bytes(ring + 1) <= 227 * 1024) ++ring;
+      if (const char *r = getenv("KGE_SPLIT_RING")) { const int v = atoi(r); if (v >= 2 && v <= ring) ring = v; }
+      while (Ws > 1 && fixed_s + Ws * group_bytes(ring) > 227 * 1024) --Ws;
+      const size_t per_warp = group_bytes(ring);
       if (Ws >= (wpr == 2 ? 2 : 4) && fixed_s + Ws * per_warp <= 227 * 1024) {
         const size_t total = fixed_s + Ws * per_warp;
+        RowArgs ar = a;
+        ar.ring = ring;
+        { const char *h = getenv("KGE_L2_HINTS"); ar.l2_hints = !(h && h[0] == '0'); }
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
         // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
         // through ws.Dvec); without it the entity-side rows of the positives go to gE with atomics
@@ -113,7 +126,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
   do {                                                                                                 \
     auto k = row_kernel_split<MODEL, HEAD, NCH, VAR>;                                                  \
     KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));     \
-    k<<<sgrid, Ws * wpr * 32, total, st>>>(a, ws);                                                     \
+    k<<<sgrid, Ws * wpr * 32, total, st>>>(ar, ws);                                                    \
   } while (0)
 #define KGE_SPLIT_LAUNCH(NCH)                                                                          \
   do {                                                                                                 \

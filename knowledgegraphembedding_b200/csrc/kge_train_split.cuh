@@ -98,39 +98,48 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   // `warp` / `nwarps` index the row groups (one warp, or a pair of warps: hw = which half of the chunks this warp covers)
   const int warp = (tid >> 5) / WPR, nwarps = (blockDim.x >> 5) / WPR, hw = (tid >> 5) % WPR;
   const int c0 = hw * NCL;                        // first chunk of this warp
-  // layout: [slots: nwarps x 2 x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers | pair exchange], from `smem`
-  float *slot0 = smem + (size_t)(2 * warp) * HS, *slot1 = slot0 + HS;
-  float *q = smem + (size_t)(2 * nwarps) * HS;
+  // Every row group owns a ring of D = a.ring slots (2..4).  The gather is bound by the bytes in flight per SM against
+  // the L2 / DRAM latency (B200, cfg 3: 16 slots of 8 KB per SM gave the same 0.33 ms with 8 warps at 255 registers and
+  // with 16 warps at 128; 12 slots were slower), so the ring is as deep as the shared memory allows.
+  // layout: [slots: nwarps x D x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers: nwarps x D |
+  //          pair exchange: nwarps x 4 | parking slot of each group: nwarps], all derived from `smem`
+  const int D = a.ring;
+  float *slots = smem + (size_t)(D * warp) * HS;
+  float *q = smem + (size_t)(D * nwarps) * HS;
   float *dq = q + HS;                           // compact [d | d]
   float *sc = dq + Dq4;                         // [N]
   float *gg = sc + a.N;                         // [N]
   float *scratch = gg + a.N;                    // [32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
   const uint32_t halfbytes = (uint32_t)a.d * 4u;
-  uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
-  uint32_t par0 = 0, par1 = 0;
-  float *xch = reinterpret_cast<float *>(bars + 2 * nwarps) + 4 * warp;      // [2 parities][2 halves] partial scores
+  uint64_t *gbars = bars + D * warp;                       // this group's mbarriers
+  uint32_t par = 0;                                         // phase parity of every slot's mbarrier (bit s)
+  float *xch = reinterpret_cast<float *>(bars + D * nwarps) + 4 * warp;      // [2 parities][2 halves] partial scores
+  int *parks = reinterpret_cast<int *>(reinterpret_cast<float *>(bars + D * nwarps) + 4 * nwarps);
 
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const bool adversarial = a.do_loss && a.loss_kind == KGE_LOSS_NEG_ADVERSARIAL;
+  const uint64_t pol_e = l2_policy(a.l2_hints ? 2 : 0);     // entity rows: keep in L2 (see l2_policy)
 
   {                                                        // zero the pads of every slot and of q (once per CTA)
-    const int padn = DP - a.d, nslots = 2 * nwarps + 1;
+    const int padn = DP - a.d, nslots = D * nwarps + 1;
     for (int i = tid; i < nslots * H * padn; i += blockDim.x) {
       const int sl = i / (H * padn), r = i % (H * padn);
       smem[(size_t)sl * HS + (r / padn) * DP + a.d + (r % padn)] = 0.f;
     }
   }
-  if (lane == 0 && hw == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  if (lane == 0 && hw == 0)
+    for (int k = 0; k < D; ++k) mbar_init(gbars + k, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  // The CTA is persistent (one per SM) and walks its rows; the first two candidates of the NEXT row are issued while the
-  // block-wide phases of the current row run (slot 1 right after the candidate loop, slot 0 as soon as the fold has
-  // consumed the parked accumulators), so every row but the first starts with its bulk copies already in flight.
-  int fs = 0;                                              // slot holding candidate 0 of the current row
-  bool primed = false;                                     // candidates 0 and 1 of the current row are already issued
+  // The CTA is persistent (one per SM) and walks its rows; the first D candidates of the NEXT row are issued while the
+  // block-wide phases of the current row run (D - 1 right after the candidate loop, the last one as soon as the fold
+  // has consumed the accumulators parked in the remaining slot), so every row but the first starts with its bulk
+  // copies already in flight.
+  int cons = 0;                                            // ring position of the next candidate to consume
+  bool primed = false;                                     // the first D candidates of the current row are already issued
   int64_t ids = 0;                                         // candidate ids of this warp (see issue())
   int ids_base = -32;
   for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
@@ -158,18 +167,18 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
       if (lane == 0 && hw == 0) {
         atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
-        uint64_t *bar = s ? bar1 : bar0;
-        float *dst = s ? slot1 : slot0;
+        uint64_t *bar = gbars + s;
+        float *dst = slots + (size_t)s * HS;
         const float *src = a.E + id * a.De;
         mbar_expect_tx(bar, halfbytes * H);
-        bulk_g2s(dst, src, halfbytes, bar);
-        if constexpr (CPLX) bulk_g2s(dst + DP, src + a.d, halfbytes, bar);
+        bulk_g2s_hint(dst, src, halfbytes, bar, pol_e);
+        if constexpr (CPLX) bulk_g2s_hint(dst + DP, src + a.d, halfbytes, bar, pol_e);
       }
     };
     if (!primed) {
       ids_base = -32;
-      if (warp < a.N) issue(fs, 0);
-      if (warp + nwarps < a.N) issue(fs ^ 1, 1);
+      for (int k = 0; k < D; ++k)
+        if (warp + k * nwarps < a.N) issue((cons + k) % D, k);
     }
 
     // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
@@ -201,9 +210,11 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     {
       int it = 0;
       for (int n = warp; n < a.N; n += nwarps, ++it) {
-        const int s = (it + fs) & 1;
-        if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-        float *xl = (s ? slot1 : slot0) + c0 * 128 + lane * V;
+        const int s = cons;
+        cons = cons + 1 == D ? 0 : cons + 1;
+        mbar_wait(gbars + s, (par >> s) & 1u);
+        par ^= 1u << s;
+        float *xl = slots + (size_t)s * HS + c0 * 128 + lane * V;
         // sweep 1: element values -> score; u = d(value)/dq stays in registers (VAR >= 1) or is parked in the slot
         float part = 0.f;
         f2 part2 = pack2(0.f, 0.f);
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
             // every lane's reads of the slot fed the reduction above: the slot can take the next row already, while
             // the softmax bookkeeping and the accumulate step run from registers
             __syncwarp();
-            if (n + 2 * nwarps < a.N) issue(s, it + 2);
+            if (n + D * nwarps < a.N) issue(s, it + D);
           }
           const float sv = finish_score<MODEL>(part, a.gamma, modulus);
           if (lane == 0 && hw == 0) {
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
           coef = a.dscore[(int64_t)rl * a.N + n];          // autograd backward: dL/ds is given
           if constexpr (UREG) {
             __syncwarp();
-            if (n + 2 * nwarps < a.N) issue(s, it + 2);
+            if (n + D * nwarps < a.N) issue(s, it + D);
           }
         }
         // sweep 2: acc += coef * u
@@ -315,14 +326,18 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
           // the slot was rewritten with generic stores: order them before the bulk engine's next write to it
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (n + 2 * nwarps < a.N) issue(s, it + 2);
+          if (n + D * nwarps < a.N) issue(s, it + D);
         }
       }
     }
-    if (has_next) {                                        // next row, candidate 0 -> slot 1 (slot 0 parks the fold)
+    // all issued copies are consumed: the ring is empty at position `cons`.  Next row: candidates 0 .. D-2 go out now,
+    // the slot of candidate D-1 parks this row's accumulators for the fold first
+    const int ps = (cons + D - 1) % D;
+    if (has_next) {
       cand = a.cand + (b + gridDim.x) * a.cand_stride;
       ids_base = -32;
-      if (warp < a.N) issue(1, 0);
+      for (int k = 0; k + 1 < D; ++k)
+        if (warp + k * nwarps < a.N) issue((cons + k) % D, k);
     }
 
     // ---- phase 2: loss of this row (model.py:270-288), dL/ds to the workspace ---------------------------------
@@ -375,7 +390,8 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     // ---- phase 4: fold the per-warp partial dL/dq.  Each warp parks its (scaled) accumulators in its own idle
     // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
     {
-      float *pl = slot0 + c0 * 128 + lane * V;
+      float *pl = slots + (size_t)ps * HS + c0 * 128 + lane * V;
+      if (lane == 0 && hw == 0) parks[warp] = ps;
       const f2 f2v = pack2(factor, factor);
 #pragma unroll
       for (int i = 0; i < NCL; ++i) {
@@ -392,12 +408,12 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     for (int k = tid; k < a.De; k += blockDim.x) {
       const int kk = (CPLX && k >= a.d) ? DP + (k - a.d) : k;           // compact index -> padded slot offset
       float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(2 * w) * HS + kk];
+      for (int w = 0; w < nwarps; ++w) t += smem[(size_t)(D * w + parks[w]) * HS + kk];
       dq[k] = t;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // parked / folded slot words vs the next bulk copy
     __syncthreads();
-    if (has_next && warp + nwarps < a.N) issue(0, 1);      // next row, candidate 1 -> slot 0
+    if (has_next && warp + (D - 1) * nwarps < a.N) issue(ps, D - 1);      // next row, candidate D-1 -> the parking slot
     // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
     // With the fused optimizer (ws.Dvec) the entity-side gradient rows are written to the workspace and reach the
     // entity-major pass as "direct" entries of their target entity; otherwise they are added to gE with atomics.
@@ -475,7 +491,6 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       }
     }
     __syncthreads();                                        // q / dq / sc are rewritten by the next row
-    fs = 1;
     primed = has_next;
   }
 }
@@ -500,6 +515,8 @@ struct EntArgs {
   int64_t ent_begin, ent_count;   // entity range of this launch (slices overlap the NCCL all-reduce in multi-GPU runs)
   int N, d, De;
   int upp;                   // units (float4) per part: ceil(nunits / S)
+  int depth;                 // slots per warp in the q-row ring (2..4)
+  int l2_hints;              // tag moment traffic evict_first / entity rows evict_last (see l2_policy)
   float scale;
   int need_gmod;             // backward-only pRotatE: accumulate d/dmodulus here
   // fused optimizer (FUSED instantiations)
@@ -516,8 +533,8 @@ struct EntArgs {
 // row of both moments next to x and the sums: 128 registers) for latency hiding.
 __host__ __device__ constexpr int entity_warps(int parts, bool fused) { return parts == 1 ? 12 : (fused ? 16 : 20); }
 
-__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
 
 template <int MODEL, bool HEAD, int S, bool FUSED>
@@ -533,21 +550,28 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
   // whatever an earlier, longer segment left there -- their x registers are 0 and their accumulators are never stored
   constexpr int HSTR = CH * 32 * V;
   constexpr int slot_floats = H * HSTR;
-  float *slot0 = smem + (size_t)(2 * warp) * slot_floats, *slot1 = slot0 + slot_floats;     // [slots | mbarriers]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * nwarps) * slot_floats);
-  uint64_t *bar0 = bars + 2 * warp, *bar1 = bar0 + 1;
-  uint32_t par0 = 0, par1 = 0;
-  float g0 = 0.f, g1 = 0.f;
-  int r0 = 0, r1 = 0;                                       // perm entries of the two slots (FUSED: < 0 = direct row)
+  // per warp a ring of D slots (D = a.depth, 2..4: the bytes in flight per SM are what hides the L2 latency of the q
+  // rows -- ncu r2b: 45 % of the instructions of the depth-2 kernel were mbarrier polls); layout
+  // [slots: nwarps x D | mbarriers: nwarps x D | (dL/ds, perm entry) of the pair in each slot: nwarps x D]
+  const int D = a.depth;
+  float *slots = smem + (size_t)(D * warp) * slot_floats;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(D * nwarps) * slot_floats) + D * warp;
+  float2 *meta = reinterpret_cast<float2 *>(reinterpret_cast<uint64_t *>(smem + (size_t)(D * nwarps) * slot_floats) +
+                                            D * nwarps) + D * warp;      // FUSED: perm entry < 0 = direct gradient row
+  uint32_t par = 0;                                         // phase parity of every slot's mbarrier (bit s)
   const int nunits = a.d / V;
   const float modulus = MODEL == KGE_PROTATE ? __ldg(a.modulus) : 1.f;
   const int64_t ntasks = a.ent_count * S;
   if constexpr (FUSED) {
     if (a.err && *a.err) return;
   }
+  // fused optimizer: the moments stream through L2 once per step (evict_first), the entity rows are what the next step's
+  // row kernel gathers at random (evict_last)
+  const uint64_t pol_mv = l2_policy(a.l2_hints ? 1 : 0), pol_e = l2_policy(a.l2_hints ? 2 : 0);
 
-  for (int i = tid; i < 2 * nwarps * slot_floats; i += blockDim.x) smem[i] = 0.f;     // finite pads from the start
-  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  for (int i = tid; i < D * nwarps * slot_floats; i += blockDim.x) smem[i] = 0.f;     // finite pads from the start
+  if (lane == 0)
+    for (int k = 0; k < D; ++k) mbar_init(bars + k, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -581,25 +605,25 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
       if (i >= pbase + 32) refill(i);
       const int row = __shfl_sync(0xffffffffu, prow, i - pbase);
       const float g = __shfl_sync(0xffffffffu, pg, i - pbase);
-      if (s) { g1 = g; r1 = row; } else { g0 = g; r0 = row; }
       if (lane == 0) {
-        uint64_t *bar = s ? bar1 : bar0;
-        float *dst = s ? slot1 : slot0;
+        meta[s] = make_float2(g, __int_as_float(row));
+        uint64_t *bar = bars + s;
+        float *dst = slots + (size_t)s * slot_floats;
         const float *src = (FUSED && row < 0 ? a.Dvec + (size_t)(-row - 1) * a.De : a.Qtab + (size_t)row * a.De) + ubeg * V;
         mbar_expect_tx(bar, segbytes * H);
         bulk_g2s(dst, src, segbytes, bar);
         if constexpr (CPLX) bulk_g2s(dst + HSTR, src + a.d, segbytes, bar);
       }
     };
-    if (beg < end) issue(0, beg);
-    if (beg + 1 < end) issue(1, beg + 1);
+    for (int k = 0; k < D; ++k)
+      if (beg + k < end) issue(k, beg + k);
     if constexpr (FUSED) {
       if (lane == 0) {                                      // the moments of this slice are needed at the end of the task
         const size_t mb = (size_t)e * a.De + ubeg * V;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          prefetch_l2(a.exp_avg + mb + (size_t)h * a.d, segbytes);
-          prefetch_l2(a.exp_avg_sq + mb + (size_t)h * a.d, segbytes);
+          prefetch_l2(a.exp_avg + mb + (size_t)h * a.d, segbytes, pol_mv);
+          prefetch_l2(a.exp_avg_sq + mb + (size_t)h * a.d, segbytes, pol_mv);
         }
       }
     }
@@ -621,13 +645,14 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
     }
 
     const int nact = (ucnt + 31) >> 5;                    // chunks holding at least one unit: the same for every lane
-    int it = 0;
-    for (int i = beg; i < end; ++i, ++it) {
-      const int s = it & 1;
-      if (s) { mbar_wait(bar1, par1); par1 ^= 1; } else { mbar_wait(bar0, par0); par0 ^= 1; }
-      const float *ql = (s ? slot1 : slot0) + lane * V;
-      const float g = s ? g1 : g0;
-      const int row = s ? r1 : r0;
+    int s = 0;
+    for (int i = beg; i < end; ++i) {
+      mbar_wait(bars + s, (par >> s) & 1u);
+      par ^= 1u << s;
+      const float *ql = slots + (size_t)s * slot_floats + lane * V;
+      const float2 mt = meta[s];
+      const float g = mt.x;
+      const int row = __float_as_int(mt.y);
       const float go = dsum_of<MODEL>(g, modulus);
       float vsum = 0.f;
       if (FUSED && row < 0) {
@@ -690,7 +715,8 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
         }
       }
       __syncwarp();
-      if (i + 2 < end) issue(s, i + 2);
+      if (i + D < end) issue(s, i + D);
+      s = s + 1 == D ? 0 : s + 1;
       if constexpr (MODEL == KGE_PROTATE) {
         if (a.need_gmod) gmod += -g * warp_sum(vsum);
       }
@@ -707,8 +733,9 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
         for (int c = 0; c < CH; ++c) {
           const int u = lane + 32 * c;
           if (u < ucnt) {
-            load_global<V>(mm[c], a.exp_avg + hb + u * V);
-            load_global<V>(vv[c], a.exp_avg_sq + hb + u * V);
+            const float4 m4 = ld4_hint(a.exp_avg + hb + u * V, pol_mv), v4 = ld4_hint(a.exp_avg_sq + hb + u * V, pol_mv);
+            mm[c][0] = m4.x; mm[c][1] = m4.y; mm[c][2] = m4.z; mm[c][3] = m4.w;
+            vv[c][0] = v4.x; vv[c][1] = v4.y; vv[c][2] = v4.z; vv[c][3] = v4.w;
           }
         }
 #pragma unroll
@@ -723,11 +750,11 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
             adam_pair_fast(p23, acc[c][h][1], m23, v23, a.adam, l3, racc);
             float t0, t1, t2, t3;
             unpack2(p01, t0, t1); unpack2(p23, t2, t3);
-            *reinterpret_cast<float4 *>(a.E + hb + u * V) = make_float4(t0, t1, t2, t3);
+            st4_hint(a.E + hb + u * V, make_float4(t0, t1, t2, t3), pol_e);
             unpack2(m01, t0, t1); unpack2(m23, t2, t3);
-            *reinterpret_cast<float4 *>(a.exp_avg + hb + u * V) = make_float4(t0, t1, t2, t3);
+            st4_hint(a.exp_avg + hb + u * V, make_float4(t0, t1, t2, t3), pol_mv);
             unpack2(v01, t0, t1); unpack2(v23, t2, t3);
-            *reinterpret_cast<float4 *>(a.exp_avg_sq + hb + u * V) = make_float4(t0, t1, t2, t3);
+            st4_hint(a.exp_avg_sq + hb + u * V, make_float4(t0, t1, t2, t3), pol_mv);
           }
         }
       }

@@ -155,7 +155,7 @@ def test_train_steps_vs_reference_golden(model, d, cfg, path, monkeypatch):
             if m.entity_embedding.grad is None:       # fused entity optimizer (needs rows that are 16-byte multiples)
                 assert path != "single_read" and d % 4 == 0
             else:
-                assert path == "single_read" or d % 4 != 0
+                assert path in ("single_read", "two_sweep") or d % 4 != 0
                 assert relinf(m.entity_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gE0"]) < TOL
             assert relinf(m.relation_embedding.grad.cpu().numpy(), g[f"train_{cfg}_gR0"]) < TOL
             if model == "pRotatE":

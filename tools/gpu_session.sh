@@ -13,12 +13,15 @@ for S in $STEPS; do
     l2)     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o /tmp/l2_gather_bench tools/l2_gather_bench.cu 2> $OUT/l2_gather.err \
               && timeout 120 /tmp/l2_gather_bench > $OUT/l2_gather.json 2>> $OUT/l2_gather.err; echo "l2 rc=$?" >> $OUT/rc.txt ;;
     variants)
-      for V in 2 3 4; do
-        KGE_SPLIT_VARIANT=$V timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_var$V.json 2> $OUT/bench_var$V.err
-        echo "variant $V rc=$?" >> $OUT/rc.txt
-      done
-      KGE_KEEP_GRADS=1 timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_keepgrads.json 2> $OUT/bench_keepgrads.err
-      echo "keepgrads rc=$?" >> $OUT/rc.txt ;;
+      # A/B of kernel variants through environment switches (bench.py --no-extras: cfg 3 only)
+      i=0
+      for CFG in "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=2 KGE_ENTITY_DEPTH=2" "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=2" \
+                 "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=3" "KGE_SPLIT_VARIANT=4 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=3" \
+                 "KGE_SPLIT_VARIANT=2 KGE_ENTITY_WARPS=12 KGE_ENTITY_DEPTH=4" "KGE_KEEP_GRADS=1"; do
+        i=$((i+1))
+        env $CFG timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_ab$i.json 2> $OUT/bench_ab$i.err
+        echo "ab$i [$CFG] rc=$?" >> $OUT/rc.txt
+      done ;;
     bench)  timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/rc.txt ;;
     hostprof) timeout 300 python tools/profile_host.py > $OUT/hostprof.txt 2>&1; echo "hostprof rc=$?" >> $OUT/rc.txt ;;
     yago)   KGE_FORCE_SPLIT=1 timeout 300 python bench.py --workload rotate_yago310 --no-extras --no-cpu-baseline --no-parity --eval-queries 1024 > $OUT/bench_yago_split.json 2> $OUT/bench_yago_split.err; echo "yago rc=$?" >> $OUT/rc.txt ;;
