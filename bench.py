@@ -655,7 +655,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--negatives", type=int, default=0, help="experiments: override the workload's negative_sample_size")
+    ap.add_argument("--batch", type=int, default=0, help="experiments: override the workload's batch size per GPU")
     args = ap.parse_args()
+    if args.negatives or args.batch:                 # (shows up in `config`: not the BASELINE workload any more)
+        w = list(WORKLOADS[args.workload])
+        w[5], w[6] = args.batch or w[5], args.negatives or w[6]
+        WORKLOADS[args.workload] = tuple(w)
     if args.impl == "reference":
         # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly
         os.environ["OMP_NUM_THREADS"] = str(host_cores())

@@ -54,6 +54,36 @@ __device__ __forceinline__ void build_q(const float *__restrict__ F, const float
   build_q<MODEL, HEAD>(F, Rr, k, d, scale, q, d);
 }
 
+// RotatE with the rotation (cos, sin of the relation phase) given: the persistent train kernel evaluates the phases of
+// a row's relation once and reuses them for q, the chain rule and the positive triple (same values as build_q /
+// chain_q, which call sincos_rep themselves).
+template <bool HEAD>
+__device__ __forceinline__ void build_q_rot(const float *__restrict__ F, float c, float s, int k, int d,
+                                            float *__restrict__ q, int qd) {
+  const float fr = F[k], fi = F[d + k];
+  if (HEAD) {                                              // model.py:215-216
+    q[k] = fadd(fmul(c, fr), fmul(s, fi));
+    q[qd + k] = fsub(fmul(c, fi), fmul(s, fr));
+  } else {                                                 // model.py:220-221
+    q[k] = fsub(fmul(fr, c), fmul(fi, s));
+    q[qd + k] = fadd(fmul(fr, s), fmul(fi, c));
+  }
+}
+template <bool HEAD>
+__device__ __forceinline__ void chain_q_rot(const float *__restrict__ F, float c, float s, const float *__restrict__ dq,
+                                            int k, int d, float scale, float &dF0, float &dF1, float &dR0) {
+  const float fr = F[k], fi = F[d + k], a = dq[k], b = dq[d + k];
+  float dc, ds;
+  if (HEAD) {      // q = conj(e^{i th}) * t
+    dF0 = a * c - b * s;  dF1 = a * s + b * c;
+    dc = a * fr + b * fi; ds = a * fi - b * fr;
+  } else {         // q = h * e^{i th}
+    dF0 = a * c + b * s;  dF1 = -a * s + b * c;
+    dc = a * fr + b * fi; ds = -a * fi + b * fr;
+  }
+  dR0 = (-dc * s + ds * c) / scale;
+}
+
 // ---- forward element op (train path: compiler may contract, approximate sqrt allowed) ------------------
 template <int OP>
 __device__ __forceinline__ float op_forward(float q0, float q1, float x0, float x1, float scale) {

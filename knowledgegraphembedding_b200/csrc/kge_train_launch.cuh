@@ -36,7 +36,8 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
       e.reg_partials = o.reg_partials;
     }
   }
-  const bool two = nunits >= 64;                     // enough work per lane to split the row in two parts
+  bool two = nunits >= 64;                           // enough work per lane to split the row in two parts
+  if (const char *pe = getenv("KGE_ENTITY_PARTS")) two = two && pe[0] != '1';   // (tuning: one warp per whole row)
   e.upp = two ? (nunits + 1) / 2 : nunits;
   // slots have the kernel's compile-time half stride: CH chunks of 32 float4 units, CH = (complex ? 8 : 16) / parts
   const size_t slotbytes = (size_t)(CPLX ? 2 : 1) * ((CPLX ? 8 : 16) / (two ? 2 : 1)) * 32 * 16;
@@ -91,7 +92,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       const int nch = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16);
       const int var = split_variant();
       const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
-      const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)a.N + 32) + 16;
+      const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)((a.d + 3) & ~3) +
+                                              2 * (size_t)a.N + 32) + 16;
       // Ws = row groups per CTA (one warp each, or a pair of warps: variants 3 / 4); a group owns two slots, two
       // mbarriers and the pair's exchange words
       const int wpr = split_warps_per_row(var);
@@ -99,11 +101,13 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       int Ws = wcap;
       if (a.N < 4 * Ws) Ws = a.N >= 16 ? (a.N + 3) / 4 : 4;              // short candidate lists: fewer, busier warps
       if (Ws > wcap) Ws = wcap;
-      // ring depth: as many slots as fit next to q, dq and the score arrays (KGE_SPLIT_RING=2..4 overrides)
+      // ring depth (KGE_SPLIT_RING=2..4, bounded by what fits next to q, dq and the score arrays)
       auto group_bytes = [&](int depth) { return (size_t)depth * (hs * sizeof(float) + 8) + 16 + 4; };
-      int ring = 2;
-      while (ring < 4 && fixed_s + Ws * group_bytes(ring + 1) <= 227 * 1024) ++ring;
-      if (const char *r = getenv("KGE_SPLIT_RING")) { const int v = atoi(r); if (v >= 2 && v <= ring) ring = v; }
+      // (measured on B200 at cfg 3: a third slot per group does not help -- 0.673 vs 0.650 ms per step -- the gather is
+      // not short of bytes in flight; the ring stays at 2 unless KGE_SPLIT_RING asks for more)
+      int ring = 2, ring_max = 2;
+      while (ring_max < 4 && fixed_s + Ws * group_bytes(ring_max + 1) <= 227 * 1024) ++ring_max;
+      if (const char *r = getenv("KGE_SPLIT_RING")) { const int v = atoi(r); if (v >= 2 && v <= ring_max) ring = v; }
       while (Ws > 1 && fixed_s + Ws * group_bytes(ring) > 227 * 1024) --Ws;
       const size_t per_warp = group_bytes(ring);
       if (Ws >= (wpr == 2 ? 2 : 4) && fixed_s + Ws * per_warp <= 227 * 1024) {

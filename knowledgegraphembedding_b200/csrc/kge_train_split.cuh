@@ -101,13 +101,15 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   // Every row group owns a ring of D = a.ring slots (2..4).  The gather is bound by the bytes in flight per SM against
   // the L2 / DRAM latency (B200, cfg 3: 16 slots of 8 KB per SM gave the same 0.33 ms with 8 warps at 255 registers and
   // with 16 warps at 128; 12 slots were slower), so the ring is as deep as the shared memory allows.
-  // layout: [slots: nwarps x D x HS | q: HS | dq: De | sc[N] | gg[N] | scratch(32) | mbarriers: nwarps x D |
+  // layout: [slots: nwarps x D x HS | q: HS | dq: De | rot: 2 d | sc[N] | gg[N] | scratch(32) | mbarriers: nwarps x D |
   //          pair exchange: nwarps x 4 | parking slot of each group: nwarps], all derived from `smem`
   const int D = a.ring;
   float *slots = smem + (size_t)(D * warp) * HS;
   float *q = smem + (size_t)(D * nwarps) * HS;
   float *dq = q + HS;                           // compact [d | d]
-  float *sc = dq + Dq4;                         // [N]
+  float *rot = dq + Dq4;                        // [2][d4] cos / sin of the row's relation phases (RotatE)
+  const int d4 = (a.d + 3) & ~3;
+  float *sc = rot + 2 * d4;                     // [N]
   float *gg = sc + a.N;                         // [N]
   float *scratch = gg + a.N;                    // [32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
@@ -140,7 +142,11 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   // copies already in flight.
   int cons = 0;                                            // ring position of the next candidate to consume
   bool primed = false;                                     // the first D candidates of the current row are already issued
-  int64_t ids = 0;                                         // candidate ids of this warp (see issue())
+  // candidate ids of this warp, 32 at a time (see issue()): the current window, the next window of the same row
+  // (fetched 24 candidates ahead) and the first window of the next row (fetched a whole row ahead) -- the id loads
+  // never sit in front of a bulk copy (ncu r2d: they did, ~1 us of long-scoreboard stall per 32 candidates and warp)
+  int64_t ids = 0, ids_nxt = 0, ids_next_row = 0;
+  bool next_row_ready = false;
   int ids_base = -32;
   for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
     const int64_t b = a.row_begin + rl;
@@ -158,10 +164,22 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
     // by shuffle: no dependent global load sits in front of a bulk copy
     auto issue = [&](int s, int j) {                       // j-th candidate of this warp (of the row `cand` points to)
-      if (j >= ids_base + 32) {
+      if (j >= ids_base + 32) {                            // (j is a multiple of 32 here)
+        if (j == 0) {
+          if (next_row_ready) {
+            ids = ids_next_row;
+          } else {
+            const int n = warp + lane * nwarps;
+            ids = n < a.N ? cand[n] : 0;
+          }
+        } else {
+          ids = ids_nxt;
+        }
         ids_base = j;
-        const int n = warp + (j + lane) * nwarps;
-        ids = n < a.N ? cand[n] : 0;
+      }
+      if (j == ids_base + 8) {                             // next window of this row, 24 candidates ahead of its use
+        const int n = warp + (ids_base + 32 + lane) * nwarps;
+        ids_nxt = n < a.N ? cand[n] : 0;
       }
       int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
@@ -184,7 +202,14 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
     float *qout = ws.Qtab + (size_t)rl * a.De;
     for (int k = tid; k < a.d; k += blockDim.x) {
-      build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q, DP);
+      if constexpr (MODEL == KGE_ROTATE) {                 // model.py:209-212, once per row
+        float sn, cs;
+        sincos_rep(fdiv(Rr[k], a.scale), &sn, &cs);
+        rot[k] = cs; rot[d4 + k] = sn;
+        build_q_rot<HEAD>(F, cs, sn, k, a.d, q, DP);
+      } else {
+        build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q, DP);
+      }
       qout[k] = q[k];
       dq[k] = 0.f;
       if (CPLX) { qout[a.d + k] = q[DP + k]; dq[a.d + k] = 0.f; }
@@ -197,6 +222,11 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     for (int i = 0; i < NCL; ++i)
 #pragma unroll
       for (int h = 0; h < H; ++h) { acc[i][h][0] = pack2(0.f, 0.f); acc[i][h][1] = pack2(0.f, 0.f); }
+    next_row_ready = false;                                // (consumed by the priming above, if it was set)
+    if (has_next) {                                        // first id window of the NEXT row: needed after this row's loop
+      const int n = warp + lane * nwarps;
+      ids_next_row = n < a.N ? (a.cand + (b + gridDim.x) * a.cand_stride)[n] : 0;
+    }
     float Mw = -INFINITY;                                  // running max of alpha * s over this warp's rows
     const float *ql = q + c0 * 128 + lane * V;
     float qr[QREG ? NCL : 1][H][V];
@@ -336,6 +366,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     if (has_next) {
       cand = a.cand + (b + gridDim.x) * a.cand_stride;
       ids_base = -32;
+      next_row_ready = true;
       for (int k = 0; k + 1 < D; ++k)
         if (warp + k * nwarps < a.N) issue((cons + k) % D, k);
     }
@@ -421,7 +452,8 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     float *gRr = a.gR + rid * a.Dr;
     for (int k = tid; k < a.d; k += blockDim.x) {
       float dF0, dF1, dR0, dR1;
-      chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
+      if constexpr (MODEL == KGE_ROTATE) chain_q_rot<HEAD>(F, rot[k], rot[d4 + k], dq, k, a.d, a.scale, dF0, dF1, dR0);
+      else chain_q<MODEL, HEAD>(F, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
       if (ws.Dvec) {
         gF[k] = dF0;
         if constexpr (CPLX) gF[a.d + k] = dF1;
@@ -446,8 +478,14 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         atomicAdd(ws.cnt + target, 1);
       }
       const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
-      for (int k = tid; k < a.d; k += blockDim.x) build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q, DP);
-      __syncthreads();
+      // (tail-batch: q = fold(h, r) is the q of the negatives, still in shared memory, unless an id was out of range)
+      if (HEAD || ph != fid) {
+        for (int k = tid; k < a.d; k += blockDim.x) {
+          if constexpr (MODEL == KGE_ROTATE) build_q_rot<false>(Hrow, rot[k], rot[d4 + k], k, a.d, q, DP);
+          else build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q, DP);
+        }
+        __syncthreads();
+      }
       float part = 0.f;
       for (int k = tid; k < a.d; k += blockDim.x)
         part += op_forward<OPS>(q[k], CPLX ? q[DP + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale);
@@ -478,7 +516,8 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       float *gH = ws.Dvec ? ws.Dvec + (size_t)(3 * rl + 1) * a.De : a.gE + ph * a.De;
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dF0, dF1, dR0, dR1;
-        chain_q<MODEL, false>(Hrow, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
+        if constexpr (MODEL == KGE_ROTATE) chain_q_rot<false>(Hrow, rot[k], rot[d4 + k], dq, k, a.d, a.scale, dF0, dF1, dR0);
+        else chain_q<MODEL, false>(Hrow, Rr, dq, k, a.d, a.scale, dF0, dF1, dR0, dR1);
         if (ws.Dvec) {
           gH[k] = dF0;
           if constexpr (CPLX) gH[a.d + k] = dF1;

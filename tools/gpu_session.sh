@@ -15,12 +15,15 @@ for S in $STEPS; do
     variants)
       # A/B of kernel variants through environment switches (bench.py --no-extras: cfg 3 only)
       i=0
-      for CFG in "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=2 KGE_ENTITY_DEPTH=2" "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=2" \
-                 "KGE_SPLIT_VARIANT=2 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=3" "KGE_SPLIT_VARIANT=4 KGE_SPLIT_RING=3 KGE_ENTITY_DEPTH=3" \
-                 "KGE_SPLIT_VARIANT=2 KGE_ENTITY_WARPS=12 KGE_ENTITY_DEPTH=4" "KGE_KEEP_GRADS=1"; do
+      for CFG in "KGE_L2_HINTS=0" "KGE_L2_HINTS=1" "KGE_ENTITY_PARTS=1" "KGE_SPLIT_VARIANT=4" "KGE_ENTITY_DEPTH=2"; do
         i=$((i+1))
         env $CFG timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_ab$i.json 2> $OUT/bench_ab$i.err
         echo "ab$i [$CFG] rc=$?" >> $OUT/rc.txt
+      done ;;
+    nscale)
+      for NN in 64 128 512; do
+        timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity --negatives $NN --eval-queries 256 > $OUT/bench_n$NN.json 2> $OUT/bench_n$NN.err
+        echo "nscale $NN rc=$?" >> $OUT/rc.txt
       done ;;
     bench)  timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/rc.txt ;;
     hostprof) timeout 300 python tools/profile_host.py > $OUT/hostprof.txt 2>&1; echo "hostprof rc=$?" >> $OUT/rc.txt ;;

@@ -36,7 +36,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // rows_per_warp copies per warp; ids[warp_global * rows_per_warp + i] = row to fetch
-template <int DEPTH, bool READ>
+template <int DEPTH, bool READ, bool TWO = false>
 __global__ void gather_kernel(const float *__restrict__ table, const int *__restrict__ ids, int row_floats,
                               int rows_per_warp, float *__restrict__ sink) {
   extern __shared__ __align__(128) float smem[];
@@ -53,7 +53,13 @@ __global__ void gather_kernel(const float *__restrict__ table, const int *__rest
     if (lane == 0) {
       const int s = i % DEPTH;
       mbar_expect_tx(bars + s, bytes);
-      bulk_g2s(slots + (size_t)s * row_floats, table + (size_t)my[i] * row_floats, bytes, bars + s);
+      if (TWO) {                                           // the row as two half-row copies (real | imaginary halves)
+        bulk_g2s(slots + (size_t)s * row_floats, table + (size_t)my[i] * row_floats, bytes / 2, bars + s);
+        bulk_g2s(slots + (size_t)s * row_floats + row_floats / 2, table + (size_t)my[i] * row_floats + row_floats / 2,
+                 bytes / 2, bars + s);
+      } else {
+        bulk_g2s(slots + (size_t)s * row_floats, table + (size_t)my[i] * row_floats, bytes, bars + s);
+      }
     }
   };
   for (int i = 0; i < DEPTH && i < rows_per_warp; ++i) issue(i);
@@ -74,10 +80,10 @@ __global__ void gather_kernel(const float *__restrict__ table, const int *__rest
   if (READ && acc == 123.456f) sink[0] = acc;
 }
 
-template <int DEPTH, bool READ>
+template <int DEPTH, bool READ, bool TWO = false>
 static double run(const float *table, const int *ids, int row_floats, int warps, int rows_per_warp, float *sink, int sms) {
   const size_t smem = (size_t)warps * DEPTH * row_floats * 4 + (size_t)warps * DEPTH * 8 + 16;
-  auto k = gather_kernel<DEPTH, READ>;
+  auto k = gather_kernel<DEPTH, READ, TWO>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -117,9 +123,11 @@ int main() {
       const double g2 = run<2, false>(table, ids, row_floats, warps, rows_per_warp, sink, sms);
       const double g2r = run<2, true>(table, ids, row_floats, warps, rows_per_warp, sink, sms);
       const double g3 = warps <= 8 ? run<3, false>(table, ids, row_floats, warps, rows_per_warp, sink, sms) : -1.0;
+      const double g2two = run<2, false, true>(table, ids, row_floats, warps, rows_per_warp, sink, sms);
       printf("{\"table\": \"%s\", \"row_bytes\": %d, \"warps_per_sm\": %d, \"gather_gbs_depth2\": %.1f, "
-             "\"gather_plus_lds_read_gbs_depth2\": %.1f, \"gather_gbs_depth3\": %.1f}\n",
-             t.name, row_floats * 4, warps, g2, g2r, g3);
+             "\"gather_plus_lds_read_gbs_depth2\": %.1f, \"gather_gbs_depth3\": %.1f, "
+             "\"gather_gbs_depth2_two_half_row_copies\": %.1f}\n",
+             t.name, row_floats * 4, warps, g2, g2r, g3, g2two);
       cudaFree(ids);
     }
     cudaFree(table);
