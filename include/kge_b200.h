@@ -148,6 +148,11 @@ int kge_train_entity_pass(const kge_model_t *m, int mode, void *workspace, int64
  * reference's optimizer.zero_grad() at model.py:259 drops the grads, autograd re-creates zero tables). */
 int kge_zero(void *ptr, int64_t bytes, void *stream);
 
+/* model.py:263-266 (`positive_sample.cuda()` ...) and :305-310 (`.item()`): stage a host batch on the device and read the
+ * loss block back.  host_* are HOST pointers; pinned memory makes the H2D copy asynchronous on `stream`.              */
+int kge_copy_h2d(void *dst_device, const void *host_src, int64_t bytes, void *stream);
+int kge_copy_d2h_sync(void *host_dst, const void *src_device, int64_t bytes, void *stream);
+
 /* deterministic sum of weight[0..B) into out[0] (model.py:285 `subsampling_weight.sum()`)         */
 int kge_weight_sum(const float *weight, int64_t B, float *out, void *stream);
 

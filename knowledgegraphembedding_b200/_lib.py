@@ -65,6 +65,8 @@ PROTOTYPES = {
     "kge_train_entity_pass": (c_int, [_M, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                       c_void_p]),
     "kge_zero": (c_int, [c_void_p, c_int64, c_void_p]),
+    "kge_copy_h2d": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "kge_copy_d2h_sync": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "kge_weight_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "kge_loss_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int64,
                                   c_void_p, c_void_p]),

@@ -204,6 +204,23 @@ extern "C" int kge_zero(void *ptr, int64_t bytes, void *stream) {
   return KGE_OK;
 }
 
+// Batch staging for train_step (model.py:263-266 `.cuda()` copies, :305-310 `.item()` read-backs) without a framework
+// dispatch per tensor: plain cudaMemcpyAsync on the caller's stream.  Pinned host memory makes the H2D copy
+// asynchronous (the caller keeps the source alive until the stream has passed it); pageable memory is staged by the
+// driver before the call returns.
+extern "C" int kge_copy_h2d(void *dst_device, const void *host_src, int64_t bytes, void *stream) {
+  KGE_REQUIRE(dst_device && host_src && bytes >= 0, "bad arguments");
+  if (bytes) KGE_CUDA_OK(cudaMemcpyAsync(dst_device, host_src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return KGE_OK;
+}
+
+extern "C" int kge_copy_d2h_sync(void *host_dst, const void *src_device, int64_t bytes, void *stream) {
+  KGE_REQUIRE(host_dst && src_device && bytes >= 0, "bad arguments");
+  if (bytes) KGE_CUDA_OK(cudaMemcpyAsync(host_dst, src_device, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  KGE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return KGE_OK;
+}
+
 extern "C" int kge_weight_sum(const float *weight, int64_t B, float *out, void *stream) {
   KGE_REQUIRE(weight && out && B > 0, "bad arguments");
   weight_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(weight, B, out);

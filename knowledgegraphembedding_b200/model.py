@@ -29,10 +29,17 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _on_device(t, dev, dtype):
-    """t as a contiguous `dtype` tensor on `dev` (no torch dispatch at all when it already is: the staged batches are)."""
+def _on_device(t, dev, dtype, stage=None):
+    """t as a contiguous `dtype` tensor on `dev` (no torch dispatch at all when it already is: the staged batches are).
+    A host tensor of the right dtype goes through `stage(key_numel)` -> persistent device buffer + one cudaMemcpyAsync
+    (kge_copy_h2d) instead of a framework copy with a fresh allocation (model.py:263-266)."""
     if t.device == dev and t.dtype == dtype and t.is_contiguous():
         return t
+    if stage is not None and t.device.type == 'cpu' and t.dtype == dtype and t.is_contiguous():
+        buf = stage(t.numel())
+        _lib.call("kge_copy_h2d", ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(t.data_ptr()),
+                  t.numel() * t.element_size(), _stream(dev))
+        return buf.view(t.shape)
     return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
 
 
@@ -397,7 +404,12 @@ class KGEModel(nn.Module):
         out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
         model._prefetch_batch(train_iterator)     # opt-in (KGE_PREFETCH=1): next batch's next() + H2D under this step
         reg = float(getattr(args, 'regularization', 0.0))
-        host = out.cpu()                          # the step's single device->host sync (model.py:305-310 has 3-4)
+        # the step's single device->host sync (model.py:305-310 has 3-4): 32 bytes into a pinned buffer
+        host = model._ws.get('loss_host')
+        if host is None:
+            host = model._ws['loss_host'] = torch.empty(8, dtype=torch.float32).pin_memory()
+        _lib.call("kge_copy_d2h_sync", ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(out.data_ptr()), 32,
+                  _stream(out.device))
         code = int(host.view(torch.int32)[4])
         out = host.tolist()
         if code != 0:
@@ -493,11 +505,17 @@ class KGEModel(nn.Module):
             raise ValueError('mode %s not supported' % batch[3])
         # multi-GPU: this rank's positive rows only (the H2D copy and the kernels see rows [row_begin, row_end) of B)
         positive_sample, negative_sample, subsampling_weight, mode, B, row_begin = _shard_rows(batch)
-        positive = _on_device(positive_sample, dev, torch.int64)
-        negative = _on_device(negative_sample, dev, torch.int64)
+        # host batches are staged into persistent device buffers; the host tensors stay referenced until the next step
+        # (a pinned source must outlive its asynchronous copy)
+        model._ws['staged_host_batch'] = (positive_sample, negative_sample, subsampling_weight)
+        positive = _on_device(positive_sample, dev, torch.int64,
+                              lambda n: model._buffer('stage_pos', n, torch.int64, dev)[:n])
+        negative = _on_device(negative_sample, dev, torch.int64,
+                              lambda n: model._buffer('stage_neg', n, torch.int64, dev)[:n])
         rows, N = negative.shape
         uni = bool(getattr(args, 'uni_weight', False))
-        weight = None if uni else _on_device(subsampling_weight, dev, torch.float32)
+        weight = None if uni else _on_device(subsampling_weight, dev, torch.float32,
+                                             lambda n: model._buffer('stage_w', n, torch.float32, dev)[:n])
         reg = float(getattr(args, 'regularization', 0.0))
         adversarial = bool(args.negative_adversarial_sampling)
         alpha = float(args.adversarial_temperature) if adversarial else 1.0

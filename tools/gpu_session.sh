@@ -20,6 +20,13 @@ for S in $STEPS; do
         env $CFG timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_ab$i.json 2> $OUT/bench_ab$i.err
         echo "ab$i [$CFG] rc=$?" >> $OUT/rc.txt
       done ;;
+    mgpu)   # needs gpurun --gpus N
+      NG=$(nvidia-smi -L | wc -l)
+      timeout 1200 python -m pytest tests/test_multi_gpu.py -q -x --timeout=900 > $OUT/pytest_mgpu.log 2>&1; echo "pytest mgpu rc=$?" >> $OUT/rc.txt
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus $NG --no-cpu-baseline > $OUT/bench_g$NG.json 2> $OUT/bench_g$NG.err; echo "bench $NG gpus rc=$?" >> $OUT/rc.txt
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --impl reference --gpus $NG --steps 3 --warmup 1 > $OUT/bench_ref_g$NG.json 2> $OUT/bench_ref_g$NG.err; echo "ref $NG gpus rc=$?" >> $OUT/rc.txt ;;
     nscale)
       for NN in 64 128 512; do
         timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity --negatives $NN --eval-queries 256 > $OUT/bench_n$NN.json 2> $OUT/bench_n$NN.err
