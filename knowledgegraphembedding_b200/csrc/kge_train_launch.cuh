@@ -48,7 +48,7 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   if (const char *dp = getenv("KGE_ENTITY_DEPTH")) { const int v = atoi(dp); if (v >= 2 && v <= depth) depth = v; }
   while (We > 1 && 16 + (size_t)We * depth * (slotbytes + 16) > 227 * 1024) --We;
   e.depth = depth;
-  { const char *h = getenv("KGE_L2_HINTS"); e.l2_hints = !(h && h[0] == '0'); }
+  { const char *h = getenv("KGE_L2_HINTS"); e.l2_hints = h && h[0] == '1'; }   // measured: no gain at cfg 3, off by default
   const size_t esmem = 16 + (size_t)We * depth * (slotbytes + 16);
 #define KGE_ENT_LAUNCH(S, F)                                                                         \
   do {                                                                                               \
@@ -114,7 +114,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         const size_t total = fixed_s + Ws * per_warp;
         RowArgs ar = a;
         ar.ring = ring;
-        { const char *h = getenv("KGE_L2_HINTS"); ar.l2_hints = !(h && h[0] == '0'); }
+        { const char *h = getenv("KGE_L2_HINTS"); ar.l2_hints = h && h[0] == '1'; }
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
         // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
         // through ws.Dvec); without it the entity-side rows of the positives go to gE with atomics

@@ -29,7 +29,7 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _on_device(t, dev, dtype, stage=None):
+def _on_device(t, dev, dtype, stage=None, st=None):
     """t as a contiguous `dtype` tensor on `dev` (no torch dispatch at all when it already is: the staged batches are).
     A host tensor of the right dtype goes through `stage(key_numel)` -> persistent device buffer + one cudaMemcpyAsync
     (kge_copy_h2d) instead of a framework copy with a fresh allocation (model.py:263-266)."""
@@ -38,7 +38,7 @@ def _on_device(t, dev, dtype, stage=None):
     if stage is not None and t.device.type == 'cpu' and t.dtype == dtype and t.is_contiguous():
         buf = stage(t.numel())
         _lib.call("kge_copy_h2d", ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(t.data_ptr()),
-                  t.numel() * t.element_size(), _stream(dev))
+                  t.numel() * t.element_size(), st if st is not None else _stream(dev))
         return buf.view(t.shape)
     return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
 
@@ -509,13 +509,13 @@ class KGEModel(nn.Module):
         # (a pinned source must outlive its asynchronous copy)
         model._ws['staged_host_batch'] = (positive_sample, negative_sample, subsampling_weight)
         positive = _on_device(positive_sample, dev, torch.int64,
-                              lambda n: model._buffer('stage_pos', n, torch.int64, dev)[:n])
+                              lambda n: model._buffer('stage_pos', n, torch.int64, dev)[:n], st)
         negative = _on_device(negative_sample, dev, torch.int64,
-                              lambda n: model._buffer('stage_neg', n, torch.int64, dev)[:n])
+                              lambda n: model._buffer('stage_neg', n, torch.int64, dev)[:n], st)
         rows, N = negative.shape
         uni = bool(getattr(args, 'uni_weight', False))
         weight = None if uni else _on_device(subsampling_weight, dev, torch.float32,
-                                             lambda n: model._buffer('stage_w', n, torch.float32, dev)[:n])
+                                             lambda n: model._buffer('stage_w', n, torch.float32, dev)[:n], st)
         reg = float(getattr(args, 'regularization', 0.0))
         adversarial = bool(args.negative_adversarial_sampling)
         alpha = float(args.adversarial_temperature) if adversarial else 1.0

@@ -20,5 +20,11 @@ def test_peer_exchange_and_sharded_eval_against_oracle(backend):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KGE_PEER_BACKEND=backend))
-    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (res.stdout[-2000:], res.stderr[-4000:])
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, KGE_PEER_BACKEND=backend))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):                  # keep the workers' full output next to the other logs of the run
+        with open(os.path.join(out_dir, f"multi_gpu_worker_{backend}.log"), "w") as f:
+            f.write(res.stdout + "\n==== stderr ====\n" + res.stderr)
+    if not (res.returncode == 0 and res.stdout.strip().endswith("ok")):
+        sys.stderr.write(res.stdout[-3000:] + "\n" + res.stderr[-8000:])
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), "multi-GPU worker failed (output on stderr)"

@@ -57,6 +57,32 @@ def main():
     for i in range(steps):
         z.cpu()
     rt = (time.perf_counter() - t0) / steps
+    # (5) e2e in windows of 20 steps right after a device-resident burst (what bench.py's 20-step e2e region sees), with
+    # and without an nvidia-smi poller running next to it (bench.py samples clocks during its timed regions)
+    def windows(label, n=6):
+        for i in range(20):
+            m.train_step_async(opt, dev[i % 8], targs)
+        torch.cuda.synchronize()
+        out = []
+        for w in range(n):
+            t0 = time.perf_counter()
+            for i in range(20):
+                KGEModel.train_step(m, opt, iter([pin[i % 8]]), targs)
+            out.append((time.perf_counter() - t0) / 20 * 1e6)
+        print(f"e2e per 20-step window [{label}]: " + " ".join(f"{x:.0f}" for x in out) + " us")
+    windows("no poller")
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    windows("nvidia-smi -lms 100 running")
+    sampler.stop()
+    os.environ["KGE_PREFETCH"] = "1"
+    it = iter(pin * 40)
+    t0 = time.perf_counter()
+    for i in range(200):
+        KGEModel.train_step(m, opt, it, targs)
+    print(f"e2e with KGE_PREFETCH=1 (one batch ahead):   {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")
+    os.environ.pop("KGE_PREFETCH")
+    m._prefetched.clear()
     print(f"host time to enqueue one step (no sync): {host_launch * 1e6:.1f} us   [GPU-bound loop if > kernel time]")
     print(f"e2e step (pinned batch, log read back):     {e2e * 1e6:.1f} us")
     print(f"H2D of one batch + sync:                    {h2d * 1e6:.1f} us")
