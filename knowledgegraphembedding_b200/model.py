@@ -35,7 +35,7 @@ def _on_device(t, dev, dtype, stage=None, st=None):
     (kge_copy_h2d) instead of a framework copy with a fresh allocation (model.py:263-266)."""
     if t.device == dev and t.dtype == dtype and t.is_contiguous():
         return t
-    if stage is not None and t.device.type == 'cpu' and t.dtype == dtype and t.is_contiguous():
+    if stage is not None and t.device.type == 'cpu' and t.dtype == dtype and t.is_contiguous() and t.numel():
         buf = stage(t.numel())
         _lib.call("kge_copy_h2d", ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(t.data_ptr()),
                   t.numel() * t.element_size(), st if st is not None else _stream(dev))

@@ -20,6 +20,17 @@ for S in $STEPS; do
         env $CFG timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_ab$i.json 2> $OUT/bench_ab$i.err
         echo "ab$i [$CFG] rc=$?" >> $OUT/rc.txt
       done ;;
+    ncu_final)
+      B="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 512"
+      timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+        --log-file $OUT/launches.csv $B > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?" >> $OUT/rc.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"row_kernel_split|entity_kernel" -c 4 -o $OUT/prof_train \
+        $B > $OUT/ncu_train.log 2>&1; echo "ncu train rc=$?" >> $OUT/rc.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"count_ranks_kernel|rescore" -c 3 -o $OUT/prof_eval \
+        $B > $OUT/ncu_eval.log 2>&1; echo "ncu eval rc=$?" >> $OUT/rc.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_count_kernel|split_tf32" -c 3 -o $OUT/prof_gemm \
+        python bench.py --workload complex_wn18rr --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 2048 \
+        > $OUT/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?" >> $OUT/rc.txt ;;
     mgpu)   # needs gpurun --gpus N
       NG=$(nvidia-smi -L | wc -l)
       timeout 1200 python -m pytest tests/test_multi_gpu.py -q -x --timeout=900 > $OUT/pytest_mgpu.log 2>&1; echo "pytest mgpu rc=$?" >> $OUT/rc.txt
