@@ -75,14 +75,32 @@ def adam_bytes(numel):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed regions: in-process NVML every 5 ms (pynvml; a query costs
+    tens of microseconds of a host thread), or an `nvidia-smi -lms 100` child as the fallback."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.samples, self.bits, self.stop_flag, self.thread = None, [], 0, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML wants the physical one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -91,11 +109,28 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "samples": len(self.samples),
+                    "source": "nvml, 5 ms period, over the timed train regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -105,7 +140,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.startswith("Active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def ncu_traffic(wl):
@@ -657,10 +692,12 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--negatives", type=int, default=0, help="experiments: override the workload's negative_sample_size")
     ap.add_argument("--batch", type=int, default=0, help="experiments: override the workload's batch size per GPU")
+    ap.add_argument("--entities", type=int, default=0, help="experiments: override the workload's entity count")
     args = ap.parse_args()
-    if args.negatives or args.batch:                 # (shows up in `config`: not the BASELINE workload any more)
+    if args.negatives or args.batch or args.entities:     # (shows up in `config`: not the BASELINE workload any more)
         w = list(WORKLOADS[args.workload])
-        w[5], w[6] = args.batch or w[5], args.negatives or w[6]
+        w[1], w[5], w[6] = args.entities or w[1], args.batch or w[5], args.negatives or w[6]
+        w[11] = min(w[11], 20 * w[1])
         WORKLOADS[args.workload] = tuple(w)
     if args.impl == "reference":
         # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly

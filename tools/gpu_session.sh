@@ -38,6 +38,13 @@ for S in $STEPS; do
         bench.py --gpus $NG --no-cpu-baseline > $OUT/bench_g$NG.json 2> $OUT/bench_g$NG.err; echo "bench $NG gpus rc=$?" >> $OUT/rc.txt
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
         bench.py --impl reference --gpus $NG --steps 3 --warmup 1 > $OUT/bench_ref_g$NG.json 2> $OUT/bench_ref_g$NG.err; echo "ref $NG gpus rc=$?" >> $OUT/rc.txt ;;
+    escale)  # does the row kernel speed up when the entity table fits the L2 comfortably?
+      for NE in 3500 7000 14951 30000; do
+        timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,lts__t_sector_hit_rate.pct --clock-control none \
+          -k regex:"row_kernel_split|entity_kernel" -c 8 --csv --log-file $OUT/escale_$NE.csv \
+          python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 64 --entities $NE > $OUT/escale_$NE.log 2>&1
+        echo "escale $NE rc=$?" >> $OUT/rc.txt
+      done ;;
     nscale)
       for NN in 64 128 512; do
         timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity --negatives $NN --eval-queries 256 > $OUT/bench_n$NN.json 2> $OUT/bench_n$NN.err
