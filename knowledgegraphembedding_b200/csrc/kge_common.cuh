@@ -172,6 +172,14 @@ __device__ __forceinline__ float sigmoid(float x) {
   float e = expf(-fabsf(x));
   return x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
 }
+// sigmoid on the MUFU pipe (ex2 + rcp, ~2^-21 relative): the per-candidate softmax weight of the train kernel sits on the
+// warp's serial path, where the IEEE division of sigmoid() costs ~40 cycles of latency
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  const float e = __expf(-fabsf(x));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x >= 0.f ? r : e * r;
+}
 #endif
 
 }  // namespace kge

@@ -14,14 +14,14 @@
 // ranks) are therefore identical to the exact SIMT kernel's, whatever the tensor core's internal rounding is.
 //
 // Kernel anatomy (one CTA per 128-query tile, looping over 128-entity tiles):
-//   warp 0   TMA producer: per 32-wide k-block FOUR cp.async.bulk.tensor 2-D tiles (128 rows x 32 fp32, SWIZZLE_128B:
-//            Q_hi, Q_lo, E_hi, E_lo) into one stage of a 3-stage shared-memory ring, mbarrier complete_tx
-//   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) per stage
+//   warp 0   TMA producer: per 32-wide k-block FOUR cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B: Q_hi, Q_lo of 128 rows
+//            x 32 fp32, E_hi, E_lo of 256 rows x 32 fp32) into one 96 KB stage of a 2-stage ring, mbarrier complete_tx
+//   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8) per stage
 //            -- hi*hi, hi*lo, lo*hi on the same four tiles -- accumulating in TMEM; tcgen05.commit frees ring slots /
 //            publishes tiles.  (Round 1 streamed the three products as separate passes over two-tile stages: 32 KB of
-//            operands per 4 MMAs = 120 B/clk per SM, more than L2 delivers; ncu r1g: tensor pipe 52 % active.  Four
-//            tiles feed 12 MMAs: 80 B/clk.)
-//   warp 2   TMEM allocator (256 columns = two accumulator buffers)
+//            operands per 4 128x128x8 MMAs = 120 B/clk per SM, more than L2 delivers; ncu r1g: tensor pipe 52 % active.
+//            Four tiles with a 256-wide entity tile feed the equivalent of 24 such MMAs from 96 KB: 60 B/clk.)
+//   warp 2   TMEM allocator (512 columns = two 128 x 256 accumulator buffers)
 //   warps 4-7  epilogue: tcgen05.ld 32x32b (lane = query row), band test, filter bitmap, counts, ambiguous list
 #include <cuda.h>
 
@@ -29,8 +29,10 @@
 
 namespace kge {
 
-constexpr int GM = 128, GN = 128, GK = 32, GSTAGES = 3, GTHREADS = 256;
-constexpr uint32_t kTileBytes = GM * GK * 4;                  // 16 KB per operand tile
+constexpr int GM = 128, GN = 256, GK = 32, GSTAGES = 2, GTHREADS = 256;
+constexpr uint32_t kTileBytes = GM * GK * 4;                  // 16 KB per query tile (128 rows x 32 fp32)
+constexpr uint32_t kTileBytesB = GN * GK * 4;                 // 32 KB per entity tile (256 rows x 32 fp32)
+constexpr uint32_t kStageBytes = 2 * kTileBytes + 2 * kTileBytesB;   // Q_hi | Q_lo | E_hi | E_lo = 96 KB
 // eps = band * |q| * |e| with band = kBandSplit + kBandPerKBlock * (number of 32-wide k-blocks issued):
 //   kBandSplit      operand residuals (3 * 2^-20), the dropped lo*lo term, and the rounding of the canonical fp32 sum
 //   kBandPerKBlock  4 tcgen05.mma per k-block, each assumed to add at most 2^-22 of the magnitude bound |q||e| when it
@@ -121,8 +123,8 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
                   const GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
   uint8_t *gsm = gsm_raw + ((1024u - (s32(gsm_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles need 1024-B alignment
-  uint8_t *tiles = gsm;                                         // [GSTAGES][Q_hi | Q_lo | E_hi | E_lo][16 KB]
-  uint64_t *full = reinterpret_cast<uint64_t *>(gsm + 4 * GSTAGES * kTileBytes);
+  uint8_t *tiles = gsm;                                         // [GSTAGES][Q_hi | Q_lo | E_hi | E_lo]
+  uint64_t *full = reinterpret_cast<uint64_t *>(gsm + GSTAGES * kStageBytes);
   uint64_t *empty = full + GSTAGES;
   uint64_t *tfull = empty + GSTAGES;                            // [2] accumulator ready
   uint64_t *tempty = tfull + 2;                                 // [2] accumulator drained
@@ -144,7 +146,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmElo) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -161,13 +163,13 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
         const int j0 = (int)(a.ent_begin + jt * GN);
         for (int kb = 0; kb < nkb; ++kb) {
           const int kk = kb * GK;
-          uint8_t *t = tiles + (size_t)stage * 4 * kTileBytes;
+          uint8_t *t = tiles + (size_t)stage * kStageBytes;
           mb_wait(empty + stage, phase ^ 1);
-          mb_expect(full + stage, 4 * kTileBytes);
+          mb_expect(full + stage, kStageBytes);
           tma_2d(t, &tmQhi, kk, q0, full + stage);
           tma_2d(t + kTileBytes, &tmQlo, kk, q0, full + stage);
           tma_2d(t + 2 * kTileBytes, &tmEhi, kk, j0, full + stage);
-          tma_2d(t + 3 * kTileBytes, &tmElo, kk, j0, full + stage);
+          tma_2d(t + 2 * kTileBytes + kTileBytesB, &tmElo, kk, j0, full + stage);
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -187,9 +189,9 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mb_wait(full + stage, phase);
           tc_fence_after();
-          const uint8_t *t = tiles + (size_t)stage * 4 * kTileBytes;
+          const uint8_t *t = tiles + (size_t)stage * kStageBytes;
           const uint64_t qhi = smem_desc(t), qlo = smem_desc(t + kTileBytes);
-          const uint64_t ehi = smem_desc(t + 2 * kTileBytes), elo = smem_desc(t + 3 * kTileBytes);
+          const uint64_t ehi = smem_desc(t + 2 * kTileBytes), elo = smem_desc(t + 2 * kTileBytes + kTileBytesB);
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k) {                    // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
             const uint64_t o = (uint64_t)(k * 2);
@@ -218,10 +220,10 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
     for (int64_t jt = blockIdx.y; jt < ntiles_all; jt += gridDim.y, ++tile_it) {
       const int as = tile_it & 1;
       const int64_t j0 = a.ent_begin + jt * GN;
-      // entity norms of this tile (threads 128..255 -> 128 values), visible after the named barrier
-      {
-        const int64_t j = j0 + (threadIdx.x - 128);
-        enorm_s[as * GN + (threadIdx.x - 128)] = j < a.ent_end ? a.enorm[j] : 0.f;
+      // entity norms of this tile (threads 128..255 -> GN values), visible after the named barrier
+      for (int t = threadIdx.x - 128; t < GN; t += 128) {
+        const int64_t j = j0 + t;
+        enorm_s[as * GN + t] = j < a.ent_end ? a.enorm[j] : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mb_wait(tfull + as, (tile_it >> 1) & 1);
@@ -297,7 +299,7 @@ gemm_count_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -337,7 +339,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols) {
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -348,7 +350,7 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  const cuuint32_t box[2] = {GK, GM};
+  const cuuint32_t box[2] = {GK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -401,10 +403,10 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t K = m->entity_dim;
   CUtensorMap tQhi, tQlo, tEhi, tElo;
-  if ((rc = make_map(&tQhi, qhi, Q, K))) return rc;
-  if ((rc = make_map(&tQlo, qlo, Q, K))) return rc;
-  if ((rc = make_map(&tEhi, ehi, m->nentity, K))) return rc;
-  if ((rc = make_map(&tElo, elo, m->nentity, K))) return rc;
+  if ((rc = make_map(&tQhi, qhi, Q, K, GM))) return rc;
+  if ((rc = make_map(&tQlo, qlo, Q, K, GM))) return rc;
+  if ((rc = make_map(&tEhi, ehi, m->nentity, K, GN))) return rc;
+  if ((rc = make_map(&tElo, elo, m->nentity, K, GN))) return rc;
   GemmArgs a{};
   a.pos_score = pos_score; a.qnorm = qnorm; a.enorm = enorm; a.queries = queries; a.filter_bits = filter_bits;
   a.counts = counts; a.amb = (int2 *)amb_pairs; a.amb_count = amb_count; a.amb_capacity = (int)amb_capacity;
@@ -413,7 +415,7 @@ extern "C" int kge_eval_gemm_count_ranks(const kge_model_t *m, int mode, const f
   a.band = kge_eval_gemm_band(K);
   a.approx_out = approx_scores_out;
   KGE_CUDA_OK(cudaMemsetAsync(amb_count, 0, 2 * sizeof(int), st));
-  const size_t smem = 4 * GSTAGES * kTileBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
+  const size_t smem = GSTAGES * kStageBytes + (2 * GSTAGES + 4) * 8 + 16 + 2 * GN * 4 + 1024;
   KGE_CUDA_OK(cudaFuncSetAttribute(gemm_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int qtiles = (int)((Q + GM - 1) / GM);
   const int64_t jtiles = (ent_end - ent_begin + GN - 1) / GN;

@@ -249,6 +249,61 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         float part = 0.f;
         f2 part2 = pack2(0.f, 0.f);
         f2 u[UREG ? NCL : 1][H][2];
+        if constexpr (OP == OP_CDIST && QREG) {
+          // RotatE, staged so that the MUFU pipe streams: (A) differences and squared moduli of a group of chunks,
+          // (B) their reciprocal square roots back to back (the pipe takes a warp instruction every 8 cycles; issued one
+          // by one in front of its consumer, each rsqrt exposed its ~20-cycle latency -- ncu r2d: 36 % issue-slot use
+          // with no pipe above 40 %), (C) u = (a, b) / |.| and the distance |.| = a u_a + b u_b.
+          constexpr int SG = NCL >= 4 ? 4 : NCL;            // chunks per stage group (16 complex dimensions per lane)
+          f2 pacc[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};   // 4 short FFMA2 chains
+#pragma unroll
+          for (int g0 = 0; g0 < NCL; g0 += SG) {
+            f2 m2[SG][2];
+#pragma unroll
+            for (int i = 0; i < SG; ++i) {
+              float x0[V], x1[V];
+              load_shared<V>(x0, xl + (g0 + i) * 128);
+              load_shared<V>(x1, xl + DP + (g0 + i) * 128);
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const f2 av = sub2(pack2(qr[g0 + i][0][2 * jj], qr[g0 + i][0][2 * jj + 1]), pack2(x0[2 * jj], x0[2 * jj + 1]));
+                const f2 bv = sub2(pack2(qr[g0 + i][1][2 * jj], qr[g0 + i][1][2 * jj + 1]), pack2(x1[2 * jj], x1[2 * jj + 1]));
+                u[g0 + i][0][jj] = av;
+                u[g0 + i][1][jj] = bv;
+                m2[i][jj] = fma2(bv, bv, mul2(av, av));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < SG; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                float ma, mb;
+                unpack2(m2[i][jj], ma, mb);
+                // 1/|q - x|; at q == x the differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
+                m2[i][jj] = pack2(rsqrt_fast(fmaxf(ma, kFltMin)), rsqrt_fast(fmaxf(mb, kFltMin)));
+              }
+#pragma unroll
+            for (int i = 0; i < SG; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const f2 ua = mul2(u[g0 + i][0][jj], m2[i][jj]);
+                pacc[(2 * i + jj) & 1] = fma2(u[g0 + i][0][jj], ua, pacc[(2 * i + jj) & 1]);
+                u[g0 + i][0][jj] = ua;
+                const f2 ub = mul2(u[g0 + i][1][jj], m2[i][jj]);
+                pacc[2 + ((2 * i + jj) & 1)] = fma2(u[g0 + i][1][jj], ub, pacc[2 + ((2 * i + jj) & 1)]);
+                u[g0 + i][1][jj] = ub;
+              }
+            if constexpr (UREG) {
+              // (e) this warp's reads of the slot end with the last group's loads (their values fed stage A): hand the
+              // slot back to the bulk engine now, ahead of the reduction and the softmax bookkeeping
+              if (g0 + SG >= NCL && WPR == 1) {
+                __syncwarp();
+                if (n + D * nwarps < a.N) issue(s, it + D);
+              }
+            }
+          }
+          part2 = add2(add2(pacc[0], pacc[1]), add2(pacc[2], pacc[3]));
+        } else
 #pragma unroll
         for (int i = 0; i < NCL; ++i) {
           float x0[V], x1[V], q0[V], q1[V];
@@ -297,7 +352,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         }
         if (a.do_loss) {
           if constexpr (WPR == 1) part = warp_sum(part);
-          if constexpr (UREG) {
+          if constexpr (UREG && !(OP == OP_CDIST && QREG && WPR == 1)) {
             // every lane's reads of the slot fed the reduction above: the slot can take the next row already, while
             // the softmax bookkeeping and the accumulate step run from registers
             __syncwarp();
@@ -319,13 +374,13 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
                 for (int h = 0; h < H; ++h) { acc[i][h][0] = mul2(acc[i][h][0], r2); acc[i][h][1] = mul2(acc[i][h][1], r2); }
               Mw = z;
             }
-            coef = expf(z - Mw) * sigmoid(sv);
+            coef = __expf(z - Mw) * sigmoid_fast(sv);      // (2 ulp-level approximations: weights enter dL/dq at 1e-6)
           } else {
-            coef = sigmoid(sv);                            // uniform negatives: w = 1/N applied at the end
+            coef = sigmoid_fast(sv);                       // uniform negatives: w = 1/N applied at the end
           }
         } else {
           coef = a.dscore[(int64_t)rl * a.N + n];          // autograd backward: dL/ds is given
-          if constexpr (UREG) {
+          if constexpr (UREG && !(OP == OP_CDIST && QREG && WPR == 1)) {
             __syncwarp();
             if (n + D * nwarps < a.N) issue(s, it + D);
           }

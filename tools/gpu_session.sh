@@ -15,7 +15,7 @@ for S in $STEPS; do
     variants)
       # A/B of kernel variants through environment switches (bench.py --no-extras: cfg 3 only)
       i=0
-      for CFG in "KGE_L2_HINTS=0" "KGE_L2_HINTS=1" "KGE_ENTITY_PARTS=1" "KGE_SPLIT_VARIANT=4" "KGE_ENTITY_DEPTH=2"; do
+      for CFG in "KGE_SPLIT_VARIANT=2" "KGE_SPLIT_VARIANT=4" "KGE_SPLIT_VARIANT=1"; do
         i=$((i+1))
         env $CFG timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > $OUT/bench_ab$i.json 2> $OUT/bench_ab$i.err
         echo "ab$i [$CFG] rc=$?" >> $OUT/rc.txt

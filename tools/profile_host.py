@@ -71,6 +71,19 @@ def main():
             out.append((time.perf_counter() - t0) / 20 * 1e6)
         print(f"e2e per 20-step window [{label}]: " + " ".join(f"{x:.0f}" for x in out) + " us")
     windows("no poller")
+    # (6) the same with pinned batches that the device has never read before (first DMA from a freshly pinned region)
+    fresh = [(torch.from_numpy(p_).pin_memory(), torch.from_numpy(n_).pin_memory(), torch.from_numpy(w_).pin_memory(), md)
+             for p_, n_, w_, md in bench.make_batches(nentity, nrel, B, N, 40, seed=5)]
+    torch.cuda.synchronize()
+    for lo in (0, 20):
+        t0 = time.perf_counter()
+        for i in range(20):
+            KGEModel.train_step(m, opt, iter([fresh[lo + i]]), targs)
+        print(f"e2e, 20 steps over never-copied pinned batches: {(time.perf_counter() - t0) / 20 * 1e6:.0f} us")
+    t0 = time.perf_counter()
+    for i in range(40):
+        KGEModel.train_step(m, opt, iter([fresh[i]]), targs)
+    print(f"e2e, the same 40 batches again:                 {(time.perf_counter() - t0) / 40 * 1e6:.0f} us")
     sampler = bench.ClockSampler(0)
     sampler.start()
     windows("nvidia-smi -lms 100 running")
