@@ -126,6 +126,11 @@ int kge_train_rows_adam(const kge_model_t *m, int mode, int loss_kind, float adv
                         int64_t workspace_bytes, int32_t *err_flag, const kge_entity_adam_t *host_entity_adam,
                         void *stream);
 
+/* debug (KGE_ROW_PHASES=1): cycles per phase of the persistent row kernel, summed over CTAs, rows and launches:
+ * [0] query vector, [1] candidate loop, [2] row loss, [3] fold, [4] chain rule, [5] positive triple, [6] share of [1]
+ * spent waiting on the TMA mbarrier (warp 0 of each CTA).                                                          */
+int kge_debug_row_phase_cycles(uint64_t *host_out8, int reset);
+
 /* Device scratch for the single-read backward (kge_train_rows / kge_score_backward): per-pair dL/ds, the query
  * table, and the counting-sort arrays of the entity-major pass.  With workspace == NULL (or too small) the
  * two-sweep atomic kernel is used instead; results agree to rounding.                                        */

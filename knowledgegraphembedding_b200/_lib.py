@@ -56,6 +56,7 @@ PROTOTYPES = {
                                c_int64, c_void_p, c_void_p]),
     "kge_train_workspace_bytes": (c_int64, [_M, c_int64, c_int64]),
     "kge_train_plan": (c_int, [_M, c_int64, c_int64]),
+    "kge_debug_row_phase_cycles": (c_int, [POINTER(ctypes.c_uint64), c_int]),
     "kge_train_rows_adam": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                     POINTER(KgeEntityAdam), c_void_p]),

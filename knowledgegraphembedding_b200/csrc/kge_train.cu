@@ -99,6 +99,17 @@ __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t c
   }
 }
 
+// debug instrumentation of row_kernel_split (KGE_ROW_PHASES=1): where do the cycles of a row go?
+static unsigned long long *g_phase_dev = nullptr;
+unsigned long long *row_phase_counters() {
+  if (!getenv("KGE_ROW_PHASES")) return nullptr;
+  if (!g_phase_dev) {
+    if (cudaMalloc(&g_phase_dev, 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_phase_dev, 0, 8 * sizeof(unsigned long long));
+  }
+  return g_phase_dev;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -395,4 +406,16 @@ extern "C" int kge_train_entity_pass(const kge_model_t *m, int mode, void *works
 #undef KGE_ENT
   set_error("model %d not supported", m->model);
   return KGE_ERR_INVALID;
+}
+
+/* debug: cycles of thread 0 of every row_kernel_split CTA, summed over rows and launches since the last reset, per
+ * phase: [0] query vector, [1] candidate loop, [2] row loss, [3] fold, [4] chain rule, [5] positive triple,
+ * [6] of [1]: waiting on the TMA mbarrier (warp 0).  Only counted when KGE_ROW_PHASES=1. */
+extern "C" int kge_debug_row_phase_cycles(uint64_t *host_out8, int reset) {
+  KGE_REQUIRE(host_out8, "null pointer");
+  for (int i = 0; i < 8; ++i) host_out8[i] = 0;
+  if (!g_phase_dev) return KGE_OK;
+  KGE_CUDA_OK(cudaMemcpy(host_out8, g_phase_dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) KGE_CUDA_OK(cudaMemset(g_phase_dev, 0, 8 * sizeof(unsigned long long)));
+  return KGE_OK;
 }

@@ -42,7 +42,8 @@ struct RowArgs {
   const EntityAdam *entity_adam;   // host: fuse the entity table's Adam update into the entity-major pass (or NULL)
   int *entity_adam_applied;    // host out flag: the update was applied (gE was not written; the caller skips E in Adam)
   int ring;                    // single-read path: slots per row group in the TMA ring (2..4)
-  int l2_hints;                // single-read path: L2 residency hints on (KGE_L2_HINTS=0 turns them off)
+  int l2_hints;                // single-read path: L2 residency hints on (KGE_L2_HINTS=1)
+  unsigned long long *phase_cycles;   // debug (KGE_ROW_PHASES=1): [8] cycles of thread 0 per phase, summed over CTAs and rows
 };
 
 struct SplitWs {             // carved from the caller's workspace

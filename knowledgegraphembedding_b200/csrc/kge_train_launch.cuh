@@ -64,6 +64,8 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   return KGE_OK;
 }
 
+unsigned long long *row_phase_counters();   // kge_train.cu: device counters when KGE_ROW_PHASES=1, else nullptr
+
 // which register / shared-memory variant of row_kernel_split runs (KGE_SPLIT_VARIANT=0..4 overrides; see split_warps)
 static int split_variant() {
   const char *v = getenv("KGE_SPLIT_VARIANT");
@@ -114,6 +116,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         const size_t total = fixed_s + Ws * per_warp;
         RowArgs ar = a;
         ar.ring = ring;
+        ar.phase_cycles = row_phase_counters();
         { const char *h = getenv("KGE_L2_HINTS"); ar.l2_hints = h && h[0] == '1'; }
         SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
         // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass

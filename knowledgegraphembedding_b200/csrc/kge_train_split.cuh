@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     const float *Rr = a.R + rid * a.Dr;
     const int64_t *cand = a.cand + b * a.cand_stride;
     const bool has_next = rl + (int)gridDim.x < a.row_count;
+    long long tph = a.phase_cycles ? clock64() : 0;    // debug: cycles per phase of this row (thread 0)
 
     // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
     // by shuffle: no dependent global load sits in front of a bulk copy
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     }
     __syncthreads();
 
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 0, (unsigned long long)(t_ - tph)); tph = t_; }
     // ---- phase 1: per candidate, score (sweep 1) and deferred-normalised dL/dq (sweep 2) ------------------
     f2 acc[NCL][H][2];
 #pragma unroll
@@ -242,7 +244,9 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       for (int n = warp; n < a.N; n += nwarps, ++it) {
         const int s = cons;
         cons = cons + 1 == D ? 0 : cons + 1;
-        mbar_wait(gbars + s, (par >> s) & 1u);
+        { const long long tw_ = (a.phase_cycles && tid == 0) ? clock64() : 0;
+          mbar_wait(gbars + s, (par >> s) & 1u);
+          if (a.phase_cycles && tid == 0) atomicAdd(a.phase_cycles + 6, (unsigned long long)(clock64() - tw_)); }
         par ^= 1u << s;
         float *xl = slots + (size_t)s * HS + c0 * 128 + lane * V;
         // sweep 1: element values -> score; u = d(value)/dq stays in registers (VAR >= 1) or is parked in the slot
@@ -426,6 +430,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         if (warp + k * nwarps < a.N) issue((cons + k) % D, k);
     }
 
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 1, (unsigned long long)(t_ - tph)); tph = t_; }
     // ---- phase 2: loss of this row (model.py:270-288), dL/ds to the workspace ---------------------------------
     float factor;                                           // dL/dq = factor * (folded accumulators)
     if (a.do_loss) {
@@ -473,6 +478,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       __syncthreads();
     }
 
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 2, (unsigned long long)(t_ - tph)); tph = t_; }
     // ---- phase 4: fold the per-warp partial dL/dq.  Each warp parks its (scaled) accumulators in its own idle
     // TMA slot, then every thread sums one k over the warps in fixed order (deterministic, two barriers).
     {
@@ -500,6 +506,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // parked / folded slot words vs the next bulk copy
     __syncthreads();
     if (has_next && warp + (D - 1) * nwarps < a.N) issue(ps, D - 1);      // next row, candidate D-1 -> the parking slot
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 3, (unsigned long long)(t_ - tph)); tph = t_; }
     // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
     // With the fused optimizer (ws.Dvec) the entity-side gradient rows are written to the workspace and reach the
     // entity-major pass as "direct" entries of their target entity; otherwise they are added to gE with atomics.
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       red_add1(gRr + k, dR0);
       if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
     }
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 4, (unsigned long long)(t_ - tph)); tph = t_; }
     // ---- fused positive triple (model.py:277-279, 'single' mode = the non-head-batch association): the block
     // rebuilds q = fold(h, r), scores the positive tail, and pushes dL/ds+ through the same element functions.
     if (a.pos_row_loss) {
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         if constexpr (MODEL == KGE_COMPLEX) red_add1(gRr + a.d + k, dR1);
       }
     }
+    if (a.phase_cycles && tid == 0) { const long long t_ = clock64(); atomicAdd(a.phase_cycles + 5, (unsigned long long)(t_ - tph)); tph = t_; }
     __syncthreads();                                        // q / dq / sc are rewritten by the next row
     primed = has_next;
   }

@@ -150,8 +150,6 @@ class KGEModel(nn.Module):
 
         self._ws = {}           # lazily allocated device workspaces (not part of state_dict)
         self._filter_cache = None
-        self._prefetched = {}   # id(iterator) -> batch held ahead (opt-in input pipelining, see _prefetch_batch)
-        self.prefetch_batches = False
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _device(self):
@@ -401,8 +399,10 @@ class KGEModel(nn.Module):
                 p.grad = None
         else:
             optimizer.zero_grad()
-        out = model.train_step_async(optimizer, model._next_batch(train_iterator), args)
-        model._prefetch_batch(train_iterator)     # opt-in (KGE_PREFETCH=1): next batch's next() + H2D under this step
+        # exactly one batch per call, pulled at the call (model.py:261).  (Round 1 pulled the batch of step i+1 ahead and
+        # copied it on a side stream; with the staging copies of train_step_async that measured SLOWER -- 0.97 vs 0.75 ms
+        # per step on B200 -- and changed the iterator contract, so it is gone.)
+        out = model.train_step_async(optimizer, next(train_iterator), args)
         reg = float(getattr(args, 'regularization', 0.0))
         # the step's single device->host sync (model.py:305-310 has 3-4): 32 bytes into a pinned buffer
         host = model._ws.get('loss_host')
@@ -431,55 +431,6 @@ class KGEModel(nn.Module):
             'loss': out[2]
         }
         return log
-
-    # ---- input pipelining.  Default = the reference's contract: exactly one next(train_iterator) per train_step call,
-    # at the call (model.py:261), copied on the current stream (model.py:263-266).  Opt-in with KGE_PREFETCH=1 (or
-    # model.prefetch_batches = True): the batch of step i+1 is pulled right after launching step i and copied on a
-    # side stream, so next() and the H2D copy run under step i's kernels.  One batch is then held ahead PER ITERATOR
-    # (alternating several iterators loses nothing); exhaustion or a loader error is re-raised at the call that
-    # would have hit it; one extra batch is drawn after the last step of a run.
-    def _stage_batch(self, batch, stream=None):
-        dev = self.entity_embedding.device
-        if stream is None:
-            return batch
-        shard = _shard_rows(batch)
-        with torch.cuda.stream(stream):
-            staged = shard._replace(
-                positive=shard.positive.to(device=dev, dtype=torch.int64, non_blocking=True),
-                negative=shard.negative.to(device=dev, dtype=torch.int64, non_blocking=True),
-                weight=shard.weight.to(device=dev, dtype=torch.float32, non_blocking=True))
-        return staged
-
-    def _next_batch(self, iterator):
-        held = self._prefetched.pop(id(iterator), None) if self._prefetched else None
-        if held is not None and held[0] is iterator:
-            _, batch, error, stream = held
-            if error is not None:
-                raise error
-            if stream is not None:
-                cur = torch.cuda.current_stream(self.entity_embedding.device)
-                cur.wait_stream(stream)
-                for t in batch[:3]:
-                    if t.is_cuda:
-                        t.record_stream(cur)
-            return batch
-        return next(iterator)
-
-    def _prefetch_batch(self, iterator):
-        if not (self.prefetch_batches or os.environ.get('KGE_PREFETCH')) or self.entity_embedding.device.type != 'cuda':
-            return
-        try:
-            batch = next(iterator)
-        except Exception as exc:                  # StopIteration (finite iterators) or a loader error: re-raise next call
-            self._prefetched[id(iterator)] = (iterator, None, exc, None)
-            return
-        stream = None
-        if not batch[1].is_cuda:
-            stream = self._ws.get('copy_stream')
-            if stream is None:
-                stream = self._ws['copy_stream'] = torch.cuda.Stream(self.entity_embedding.device)
-            batch = self._stage_batch(batch, stream)
-        self._prefetched[id(iterator)] = (iterator, batch, None, stream)    # keeps the iterator alive: id() stays unique
 
     def _exchange_slices(self, B, world, N):
         """How many regions the multi-GPU exchange of one step is cut into (KGE_PEER_SLICES, default 1 = no slicing).

@@ -45,6 +45,9 @@ for S in $STEPS; do
           python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity --eval-queries 64 --entities $NE > $OUT/escale_$NE.log 2>&1
         echo "escale $NE rc=$?" >> $OUT/rc.txt
       done ;;
+    phases) timeout 300 python tools/row_phases.py > $OUT/row_phases.txt 2>&1; timeout 300 python tools/row_phases.py --negatives 64 >> $OUT/row_phases.txt 2>&1; echo "phases rc=$?" >> $OUT/rc.txt ;;
+    gemmbench) timeout 400 python bench.py --workload complex_wn18rr --no-extras --no-cpu-baseline --no-parity --eval-queries 4096 > $OUT/bench_complex.json 2> $OUT/bench_complex.err; echo "gemmbench rc=$?" >> $OUT/rc.txt
+               timeout 600 python -m pytest tests -m gpu -q -k "tcgen05 or tensor_core or full_size_eval or runpy_wn18rr" --timeout=600 > $OUT/pytest_gemm.log 2>&1; echo "pytest gemm rc=$?" >> $OUT/rc.txt ;;
     nscale)
       for NN in 64 128 512; do
         timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity --negatives $NN --eval-queries 256 > $OUT/bench_n$NN.json 2> $OUT/bench_n$NN.err

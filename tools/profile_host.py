@@ -88,14 +88,6 @@ def main():
     sampler.start()
     windows("nvidia-smi -lms 100 running")
     sampler.stop()
-    os.environ["KGE_PREFETCH"] = "1"
-    it = iter(pin * 40)
-    t0 = time.perf_counter()
-    for i in range(200):
-        KGEModel.train_step(m, opt, it, targs)
-    print(f"e2e with KGE_PREFETCH=1 (one batch ahead):   {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")
-    os.environ.pop("KGE_PREFETCH")
-    m._prefetched.clear()
     print(f"host time to enqueue one step (no sync): {host_launch * 1e6:.1f} us   [GPU-bound loop if > kernel time]")
     print(f"e2e step (pinned batch, log read back):     {e2e * 1e6:.1f} us")
     print(f"H2D of one batch + sync:                    {h2d * 1e6:.1f} us")
