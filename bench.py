@@ -411,6 +411,7 @@ class Bench:
                "fused_entity_adam": m.entity_embedding.grad is None, "model": m, "opt": opt, "targs": targs}
         px = m._ws.get('peer')
         out["peer"] = px
+        out["shard"] = m._ws.get('shard') or None
         out["nreg"] = int(m._ws.get('exchange_regions', 1)) if px else 1
         if e2e:
             pin_pool = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory(),
@@ -444,24 +445,32 @@ class Bench:
 
     def parity(self, wl, steps=2):
         """The timed path against the C oracle on the same seeded full batches (losses 1e-5, tables outlier bound);
-        raises if it fails: a fast kernel whose results differ from the reference's is not done."""
+        raises if it fails: a fast kernel whose results differ from the reference's is not done.  Multi-GPU: the ranks
+        step the GLOBAL batch (B rows per rank) together, rank 0 runs the oracle's single-device step on all of it."""
         torch = self.torch
         from knowledgegraphembedding_b200 import KGEModel
-        from oracle import c_oracle as C
         model, nentity, nrel, d, gamma, B, N, lr, de, dr, reg, _ = WORKLOADS[wl]
         m, opt, targs, st = self.build_model(wl)
-        ts = C.TrainState(model, st, gamma, d)
+        ts = None
+        if self.rank == 0:
+            from oracle import c_oracle as C
+            ts = C.TrainState(model, st, gamma, d)
         worst = 0.0
-        for b in make_batches(nentity, nrel, B, N, steps, seed=11):
+        for b in make_batches(nentity, nrel, B * self.world, N, steps, seed=11):
             log = KGEModel.train_step(m, opt, iter([tuple(torch.from_numpy(x) if isinstance(x, np.ndarray) else x
                                                           for x in b)]), targs)
-            ref = C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
-            worst = max(worst, max(abs(log[k] - ref[k]) / abs(ref[k]) for k in ref))
+            if ts is not None:
+                ref = C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
+                worst = max(worst, max(abs(log[k] - ref[k]) / abs(ref[k]) for k in ref))
+        self.barrier()
+        if ts is None:
+            return None
         E = m.entity_embedding.detach().cpu().numpy()
         bad = float(np.mean(np.abs(E - ts.state["entity_embedding"]) > 1e-5 * np.abs(ts.state["entity_embedding"]).max()))
         ok = worst <= 1e-5 and bad < 1e-4
         res = {"against": "oracle/kge_oracle.c full-batch train_step (pinned to the reference's goldens)", "steps": steps,
-               "max_rel_loss_err": worst, "entity_table_outlier_fraction": bad, "tolerance": 1e-5, "ok": bool(ok)}
+               "global_rows": B * self.world, "max_rel_loss_err": worst, "entity_table_outlier_fraction": bad,
+               "tolerance": 1e-5, "ok": bool(ok)}
         if not ok:
             raise SystemExit("bench.py parity check failed: " + json.dumps(res))
         return res
@@ -547,7 +556,7 @@ def run_gpu(args):
             del t2, m2
             torch.cuda.empty_cache()
 
-    parity = b.parity(wl) if (world == 1 and not args.no_parity) else None
+    parity = b.parity(wl) if not args.no_parity else None
 
     if rank != 0:
         if world > 1:
@@ -629,9 +638,16 @@ def run_gpu(args):
     else:
         ref_cuda = port = None
     px = tr["peer"]
-    exchange_path = ("nvlink_peer_memory/%s%s (kge_peer_reduce_adam)" % (px.backend, "+nvswitch_multicast" if px.multicast else "")
-                     if px else ("nccl_allreduce + kge_adam_step" if world > 1 else
-                                 ("entity Adam fused in kge_train_rows_adam + kge_adam_step over R" if fused else "kge_adam_step")))
+    sh = tr["shard"]
+    if sh:
+        exchange_path = ("entity-sharded optimizer over nvlink_peer_memory/%s: row kernel stores q / dL/ds / ids into every rank's "
+                         "gather area, owners run sort + entity-major backward + fused Adam and store the updated rows into "
+                         "every replica (kge_train_rows_sharded / kge_train_entity_sharded); exposed = wait for the relation-table exchange "
+                         "(kge_peer_reduce_adam on a second stream) + final barrier" % sh['peer'].backend)
+    else:
+        exchange_path = ("nvlink_peer_memory/%s%s (kge_peer_reduce_adam)" % (px.backend, "+nvswitch_multicast" if px.multicast else "")
+                         if px else ("nccl_allreduce + kge_adam_step" if world > 1 else
+                                     ("entity Adam fused in kge_train_rows_adam + kge_adam_step over R" if fused else "kge_adam_step")))
     # kernels of libkge_b200.so per step: weight_sum, row_kernel_split, scan_tiles, scan_apply, scatter_pairs,
     # entity_kernel per region, loss_finalize, and adam_kernel (1 GPU / NCCL path) or peer_reduce_adam + peer_finish per region
     nreg = tr["nreg"]
@@ -639,7 +655,9 @@ def run_gpu(args):
         "metric": METRIC, "value": tr["value"], "unit": "scores/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(wl, world),
-        "clocks": clocks, "gpu_launches": (6 + nreg + (2 * nreg if px else 1)) * args.steps,
+        # sharded step: weight_sum, push_ids, row_kernel_split, 2 barriers, 2 gathered_pairs, 2 scans, entity_kernel,
+        # peer_reduce_adam, peer_finish, loss_finalize
+        "clocks": clocks, "gpu_launches": (13 if sh else 6 + nreg + (2 * nreg if px else 1)) * args.steps,
         "e2e": {"value": tr["e2e_value"], "unit": "scores/s", "ms_per_step": tr["ms_e2e"], "h2d_bytes_per_step": tr["h2d"],
                 "d2h_bytes_per_step": tr["d2h"], "last_loss": tr["last_loss"],
                 "what": "KGEModel.train_step (default settings: one next() per call, H2D on the compute stream) on pinned "
@@ -651,7 +669,9 @@ def run_gpu(args):
                                "frac": (a_train + adam_bytes(nentity * De + nrel * Dr)) / (tr["ms_per_step"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
         "exchange": {"path": exchange_path, "exposed_exchange_and_optimizer_ms": tr["exchange_ms"],
                      "regions_per_step": nreg,
-                     "bytes_reduced_per_rank": 4 * (nentity * De + nrel * Dr) if world > 1 else 0},
+                     "bytes_reduced_per_rank": (4 * nrel * Dr if sh else 4 * (nentity * De + nrel * Dr)) if world > 1 else 0,
+                     "nvlink_bytes_in_per_rank": (int((world - 1) * (4 * nentity * De / world + B * (De + 2 * N) * 4
+                                                                      + 3 * B * De * 4 / world)) if sh else None)},
         "eval": ev, "workloads": extras,
     }
     emit(line)

@@ -302,6 +302,51 @@ int kge_peer_reduce_adam(const kge_peer_group_t *host_group, uint32_t epoch, con
                          float *rows_out, double lr, double beta1, double beta2, double eps, double l3_coefficient,
                          int32_t *err_flag, void *stream);
 
+/* ---- entity-sharded optimizer for batch-sharded multi-GPU training ("owner computes"; no counterpart in the single-device
+ *      reference, it replaces model.py:301-303 across G replicas without ever forming or exchanging a dense gradient) ----
+ * Rank g owns the entity rows [g*base + min(g, rem), +base (+1 if g < rem)), base = nentity / G, rem = nentity % G, and
+ * is the only rank that keeps current Adam moments for them.  Every rank's peer block (kge_peer_alloc or a symmetric-
+ * memory allocator; same layout everywhere) holds the rank's ENTITY TABLE itself and a gather area of
+ * kge_train_gather_bytes() bytes.  One step:
+ *   1. kge_train_rows_sharded: the single-read row kernel over this rank's positive rows.  Its outputs -- query vectors,
+ *      dL/ds, candidate ids, target ids of the positives' gradient rows -- are stored into section `rank` of EVERY block
+ *      with NVLink stores straight from the kernel; each gradient row of a positive triple is stored only into the block
+ *      of the rank that owns its target entity.  grad_relation / grad_modulus / row losses stay local (they go through
+ *      kge_peer_reduce_adam as a small region).
+ *   2. kge_peer_barrier(channel 2, exchange_err = 1): every rank's rows are in; a bad index anywhere raises everywhere.
+ *   3. kge_train_entity_sharded: counting sort of the gathered pairs that hit the owned range, entity-major backward with
+ *      the fused Adam update of kge_train_rows_adam on the owned rows, and the updated row is stored into every rank's
+ *      table (owner computes, all replicas take the same bits).
+ *   4. kge_peer_barrier(channel 3): every rank's parameter stores have landed; the next step may read the table and
+ *      overwrite the gather area.
+ * Wire traffic per rank and step: (G-1)/G of the entity table inbound (the parameter rows) + the gathered (G-1) x
+ * rows x (entity_dim + 2N) floats -- half of what a gradient reduce-scatter + parameter all-gather moves -- and it is
+ * issued from inside the compute kernels, so no exchange kernel is exposed.  m->entity must point into block[rank]. */
+typedef struct kge_shard {
+  int32_t world, rank;
+  void *block[KGE_PEER_MAX_RANKS];     /* base of every rank's peer block as mapped in this process; [rank] is local */
+  int64_t block_bytes;                 /* size of each block                                                         */
+  int64_t gather_offset;               /* byte offset (multiple of 256) of the gather area inside each block         */
+  int64_t rows_max;                    /* row capacity per rank of the gather area                                   */
+  int32_t rows_of[KGE_PEER_MAX_RANKS]; /* positive rows each rank holds in this step (<= rows_max)                   */
+} kge_shard_t;
+
+int64_t kge_train_gather_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N);
+int64_t kge_train_shard_workspace_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N);
+int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                           const int64_t *positive, const int64_t *negative, const float *weight,
+                           const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N, float *row_loss,
+                           float *pos_row_loss, float *grad_relation, float *grad_modulus,
+                           const kge_shard_t *host_shard, int32_t *err_flag, void *stream);
+int kge_train_entity_sharded(const kge_model_t *m, int mode, int64_t N, const kge_shard_t *host_shard, void *workspace,
+                             int64_t workspace_bytes, const kge_entity_adam_t *host_entity_adam, int32_t *err_flag,
+                             void *stream);
+/* cross-GPU barrier on `stream` over the flag blocks of the group (channels 2 and 3; epoch = 1, 2, 3, ... per channel);
+ * exchange_err != 0: a non-zero *err_flag on any rank becomes non-zero on every rank.  Bounded wait like
+ * kge_peer_reduce_adam (err_flag := 2).  The flag block must hold 8 * KGE_PEER_MAX_RANKS uint32.               */
+int kge_peer_barrier(const kge_peer_group_t *host_group, int channel, uint32_t epoch, int exchange_err,
+                     int32_t *err_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,11 @@ class KgePeerGroup(Structure):
                 ("flags", c_void_p * PEER_MAX_RANKS), ("multicast", c_void_p)]
 
 
+class KgeShard(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("block", c_void_p * PEER_MAX_RANKS), ("block_bytes", c_int64),
+                ("gather_offset", c_int64), ("rows_max", c_int64), ("rows_of", c_int32 * PEER_MAX_RANKS)]
+
+
 # name -> (restype, argtypes): exactly the prototypes of include/kge_b200.h
 _M = POINTER(KgeModelStruct)
 PROTOTYPES = {
@@ -97,6 +102,14 @@ PROTOTYPES = {
     "kge_peer_reduce_adam": (c_int, [POINTER(KgePeerGroup), ctypes.c_uint32, POINTER(KgeAdamTensor), c_int, c_int64,
                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_double, c_double,
                                      c_double, c_double, c_double, c_void_p, c_void_p]),
+    "kge_train_gather_bytes": (c_int64, [_M, c_int, c_int64, c_int64]),
+    "kge_train_shard_workspace_bytes": (c_int64, [_M, c_int, c_int64, c_int64]),
+    "kge_train_rows_sharded": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                       c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(KgeShard),
+                                       c_void_p, c_void_p]),
+    "kge_train_entity_sharded": (c_int, [_M, c_int, c_int64, POINTER(KgeShard), c_void_p, c_int64,
+                                         POINTER(KgeEntityAdam), c_void_p, c_void_p]),
+    "kge_peer_barrier": (c_int, [POINTER(KgePeerGroup), c_int, ctypes.c_uint32, c_int, c_void_p, c_void_p]),
     "kge_l3_partials": (c_int, [POINTER(KgeAdamTensor), c_int, c_void_p, c_int64, c_void_p]),
     "kge_eval_filter_bits_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                                             c_int64, c_void_p, c_void_p]),

@@ -256,9 +256,72 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_finish_kernel(const PeerArg
   }
 }
 
+// Stand-alone cross-GPU barrier (entity-sharded step): one warp.  Thread r publishes `epoch` (and, with err exchange,
+// this rank's error flag) in rank r's flag block, then waits for rank r's epoch here; a peer's error becomes ours, so
+// every rank cancels the same update and raises.  Channels 0/1 belong to kge_peer_reduce_adam; the error words of
+// channel c live in channel c + 4.
+struct BarrierArgs {
+  uint32_t *flags[PEER_MAX];
+  int world, rank, channel, exchange_err;
+  uint32_t epoch;
+  int32_t *err;
+  unsigned long long timeout_ns;
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const BarrierArgs a) {
+  const int t = threadIdx.x;
+  if (t >= a.world) return;
+  if (a.exchange_err) {
+    const uint32_t mine = a.err ? (uint32_t)*reinterpret_cast<volatile int32_t *>(a.err) : 0u;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + (a.channel + 4) * PEER_MAX + a.rank), "r"(mine)
+                 : "memory");
+  }
+  __threadfence_system();
+  st_release_sys(a.flags[t] + a.channel * PEER_MAX + a.rank, a.epoch);
+  const uint32_t *f = a.flags[a.rank] + a.channel * PEER_MAX + t;
+  const unsigned long long t0 = global_ns();
+  bool ok = true;
+  while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
+    if (global_ns() - t0 > a.timeout_ns) {
+      if (a.err) atomicExch(a.err, 2);
+      ok = false;
+      break;
+    }
+    __nanosleep(100);
+  }
+  if (ok && a.exchange_err && a.err) {
+    uint32_t theirs;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(theirs) : "l"(a.flags[a.rank] + (a.channel + 4) * PEER_MAX + t)
+                 : "memory");
+    if (theirs) atomicCAS(a.err, 0, (int32_t)theirs);
+  }
+}
+
+static unsigned long long peer_timeout_ns() {
+  const char *t = getenv("KGE_PEER_TIMEOUT_S");            // a rank that is later than this aborts the step (err_flag 2)
+  const double secs = t ? atof(t) : 0.0;
+  return secs > 0.0 ? (unsigned long long)(secs * 1e9) : kPeerTimeoutNsDefault;
+}
+
 }  // namespace kge
 
 using namespace kge;
+
+extern "C" int kge_peer_barrier(const kge_peer_group_t *grp, int channel, uint32_t epoch, int exchange_err,
+                                int32_t *err_flag, void *stream) {
+  KGE_REQUIRE(grp && grp->world >= 2 && grp->world <= PEER_MAX && grp->rank >= 0 && grp->rank < grp->world,
+              "bad peer group");
+  KGE_REQUIRE(channel >= 2 && channel <= 3, "barrier channels 2 and 3 are free (0 and 1 belong to kge_peer_reduce_adam)");
+  BarrierArgs a{};
+  a.world = grp->world; a.rank = grp->rank; a.channel = channel; a.exchange_err = exchange_err; a.epoch = epoch;
+  a.err = err_flag; a.timeout_ns = peer_timeout_ns();
+  for (int r = 0; r < grp->world; ++r) {
+    KGE_REQUIRE(grp->flags[r], "peer %d is not mapped", r);
+    a.flags[r] = (uint32_t *)grp->flags[r];
+  }
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
 
 extern "C" int kge_peer_alloc(int device, int64_t bytes, void **ptr) {
   KGE_REQUIRE(ptr && bytes > 0, "bad arguments");
@@ -335,11 +398,7 @@ extern "C" int kge_peer_reduce_adam(const kge_peer_group_t *grp, uint32_t epoch,
   a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2); a.eps = (float)eps;
   a.l3x3 = (float)(3.0 * l3_coefficient);
   a.err = err_flag;
-  {
-    const char *t = getenv("KGE_PEER_TIMEOUT_S");          // a rank that is later than this aborts the step (err_flag 2)
-    const double secs = t ? atof(t) : 0.0;
-    a.timeout_ns = secs > 0.0 ? (unsigned long long)(secs * 1e9) : kPeerTimeoutNsDefault;
-  }
+  a.timeout_ns = peer_timeout_ns();
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = 148 * 12;
   // multicast use: bit 0 = reduce through the switch (multimem.ld_reduce), bit 1 = broadcast through it (multimem.st)

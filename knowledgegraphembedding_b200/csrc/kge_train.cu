@@ -99,6 +99,71 @@ __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t c
   }
 }
 
+// ---- entity-sharded multi-GPU step: the owner of an entity range sorts the pairs gathered from ALL ranks ----------
+// Gather area of every rank's peer block (identical layout; R = row capacity per rank, section s is written by rank s):
+//   ids [G][R][N] int32 candidate ids | Gs [G][R][N] dL/ds | Qtab [G][R][De] query vectors |
+//   Dvec [G][3R][De] gradient rows of the positive triples (a row is present only in its owner's block) | dids [G][3R]
+struct GatherLayout { size_t ids, Gs, Qtab, Dvec, dids, total; };
+static size_t align256(size_t x);
+static GatherLayout gather_layout(int world, int64_t R, int64_t N, int64_t De) {
+  GatherLayout g;
+  size_t o = 0;
+  g.ids = o;  o += align256((size_t)world * R * N * 4);
+  g.Gs = o;   o += align256((size_t)world * R * N * 4);
+  g.Qtab = o; o += align256((size_t)world * R * De * 4);
+  g.Dvec = o; o += align256((size_t)world * 3 * R * De * 4);
+  g.dids = o; o += align256((size_t)world * 3 * R * 4);
+  g.total = o;
+  return g;
+}
+
+struct GatherArgs {
+  const int *ids;
+  const float *Gs;
+  const int *dids;
+  int world, R, N;
+  int rows_of[KGE_PEER_MAX_RANKS];
+  int eb, ee;                                              // entity range this rank owns
+};
+
+// this rank's candidate ids, as int32, into section `rank` of every block (clamped like the row kernel's gathers)
+__global__ void push_ids_kernel(const int64_t *__restrict__ neg, int64_t n, int64_t nentity, int *dst, const Mirror mir,
+                                int32_t *err) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t id = neg[i];
+    if ((uint64_t)id >= (uint64_t)nentity) { if (err) *err = 1; id = 0; }
+    store_all(mir, dst + i, (int)id);
+  }
+}
+
+// PLACE = false: histogram of the gathered pairs and direct rows whose entity lies in [eb, ee);
+// PLACE = true: scatter them (perm = gathered row index s * R + rl, or -(1 + gathered direct index))
+template <bool PLACE>
+__global__ void gathered_pairs_kernel(const GatherArgs g, int *__restrict__ cnt_or_cursor, int *__restrict__ perm,
+                                      float *__restrict__ gsorted) {
+  const int64_t per = (int64_t)g.R * g.N, pairs = per * g.world, dper = 3ll * g.R, total = pairs + dper * g.world;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int id, row;
+    float gv = 0.f;
+    if (p < pairs) {
+      const int s = (int)(p / per), rl = (int)((p % per) / g.N);
+      if (rl >= g.rows_of[s]) continue;
+      id = g.ids[p];
+      row = s * g.R + rl;
+      if (PLACE) gv = g.Gs[p];
+    } else {
+      const int64_t i = p - pairs;
+      const int s = (int)(i / dper), j = (int)(i % dper);
+      if (j / 3 >= g.rows_of[s]) continue;
+      id = g.dids[i];
+      row = -(1 + (int)i);
+    }
+    if (id < g.eb || id >= g.ee) continue;
+    const int pos = atomicAdd(cnt_or_cursor + id, 1);
+    if (PLACE) { perm[pos] = row; gsorted[pos] = gv; }
+  }
+}
+
 // debug instrumentation of row_kernel_split (KGE_ROW_PHASES=1): where do the cycles of a row go?
 static unsigned long long *g_phase_dev = nullptr;
 unsigned long long *row_phase_counters() {
@@ -396,6 +461,177 @@ extern "C" int kge_train_entity_pass(const kge_model_t *m, int mode, void *works
   const int reserve = rs ? atoi(rs) : 0;       // measured at 2 GPUs: 0, 8, 24 equal, 48 slower
 #define KGE_ENT(MODEL) \
   case MODEL: return launch_entity_model<MODEL>(head, a, ws, ent_begin, ent_end, slice_index, st, reserve);
+  switch (m->model) {
+    KGE_ENT(KGE_TRANSE)
+    KGE_ENT(KGE_DISTMULT)
+    KGE_ENT(KGE_COMPLEX)
+    KGE_ENT(KGE_ROTATE)
+    KGE_ENT(KGE_PROTATE)
+  }
+#undef KGE_ENT
+  set_error("model %d not supported", m->model);
+  return KGE_ERR_INVALID;
+}
+
+// ---- entity-sharded multi-GPU step (owner computes): see include/kge_b200.h ------------------------------------------
+static int shard_mirror(const kge_model_t *m, const kge_shard_t *sh, int64_t N, Mirror &mir, GatherLayout &L) {
+  KGE_REQUIRE(sh && sh->world >= 2 && sh->world <= KGE_PEER_MAX_RANKS && sh->rank >= 0 && sh->rank < sh->world,
+              "bad shard description");
+  KGE_REQUIRE(sh->rows_max >= 1 && m->nentity >= sh->world && m->nentity < (1ll << 31), "bad shard shape");
+  KGE_REQUIRE(sh->world * sh->rows_max * (N + 3) < (1ll << 31), "too many pairs for 32-bit sort positions");
+  L = gather_layout(sh->world, sh->rows_max, N, m->entity_dim);
+  KGE_REQUIRE(sh->gather_offset >= 0 && sh->gather_offset % 256 == 0 &&
+                  (size_t)sh->gather_offset + L.total <= (size_t)sh->block_bytes,
+              "gather area does not fit the peer block");
+  const char *base = (const char *)sh->block[sh->rank];
+  KGE_REQUIRE(base && (const char *)m->entity >= base &&
+                  (const char *)(m->entity + m->nentity * m->entity_dim) <= base + sh->block_bytes,
+              "the entity table must live inside the local peer block (the owners store updated rows into it)");
+  mir = Mirror{};
+  mir.world = sh->world; mir.rank = sh->rank;
+  mir.ent_base = (int)(m->nentity / sh->world); mir.ent_rem = (int)(m->nentity % sh->world);
+  for (int r = 0; r < sh->world; ++r) {
+    KGE_REQUIRE(sh->block[r] && sh->rows_of[r] >= 0 && sh->rows_of[r] <= sh->rows_max, "bad shard entry %d", r);
+    mir.delta[r] = (long long)((const char *)sh->block[r] - base);
+  }
+  return KGE_OK;
+}
+
+extern "C" int64_t kge_train_gather_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N) {
+  if (!m || world < 1 || rows_max < 1 || N < 1) return 0;
+  return (int64_t)gather_layout(world, rows_max, N, m->entity_dim).total;
+}
+
+extern "C" int64_t kge_train_shard_workspace_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N) {
+  if (!m || world < 1 || rows_max < 1 || N < 1) return 0;
+  return (int64_t)(align256((size_t)(2 * m->nentity + 1) * 4 + 64) + align256((size_t)((m->nentity + 1023) / 1024) * 4) +
+                   2 * align256((size_t)world * rows_max * (N + 3) * 4));
+}
+
+extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_kind, float adversarial_temperature,
+                                      const int64_t *positive, const int64_t *negative, const float *weight,
+                                      const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N,
+                                      float *row_loss, float *pos_row_loss, float *grad_relation, float *grad_modulus,
+                                      const kge_shard_t *host_shard, int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(loss_kind == KGE_LOSS_NEG_ADVERSARIAL || loss_kind == KGE_LOSS_NEG_UNIFORM, "bad loss_kind %d", loss_kind);
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "mode %d not supported", mode);
+  KGE_REQUIRE(m->model != KGE_PROTATE || grad_modulus, "pRotatE needs grad_modulus");
+  KGE_REQUIRE(!weight || weight_sum, "subsampling weights need their sum (kge_weight_sum)");
+  Mirror mir;
+  GatherLayout L;
+  if ((rc = shard_mirror(m, host_shard, N, mir, L))) return rc;
+  const kge_shard_t &sh = *host_shard;
+  KGE_REQUIRE(row_count == sh.rows_of[sh.rank] && row_count <= B_total, "row_count does not match the shard description");
+  KGE_REQUIRE(kge_train_plan(m, sh.rows_max, N) & KGE_PLAN_ENTITY_ADAM,
+              "kge_train_plan does not offer the fused entity optimizer for this shape");
+  if (row_count == 0) return KGE_OK;
+  KGE_REQUIRE(positive && negative && row_loss && pos_row_loss && grad_relation, "null pointer");
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char *g = (char *)sh.block[sh.rank] + sh.gather_offset;
+  const int64_t R = sh.rows_max, De = m->entity_dim;
+  {
+    const int64_t n = row_count * N;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    push_ids_kernel<<<grid, 256, 0, st>>>(negative, n, m->nentity, (int *)(g + L.ids) + (size_t)sh.rank * R * N, mir, err_flag);
+    KGE_CUDA_OK(cudaGetLastError());
+  }
+  SplitWs ws{};
+  ws.G = (float *)(g + L.Gs) + (size_t)sh.rank * R * N;
+  ws.Qtab = (float *)(g + L.Qtab) + (size_t)sh.rank * R * De;
+  ws.Dvec = (float *)(g + L.Dvec) + (size_t)sh.rank * 3 * R * De;
+  ws.dids = (int *)(g + L.dids) + (size_t)sh.rank * 3 * R;
+  RowArgs a{};
+  bool head;
+  if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
+  a.positive = positive; a.row_begin = 0; a.row_count = (int)row_count; a.N = (int)N;
+  a.do_loss = 1; a.loss_kind = loss_kind; a.alpha = adversarial_temperature;
+  a.weight = weight; a.wsum = weight_sum; a.uniform_u = 1.0f / (float)B_total;
+  a.row_loss = row_loss; a.pos_row_loss = pos_row_loss;
+  a.gR = grad_relation; a.gM = grad_modulus; a.err = err_flag;
+  int fused_positive = 0, deferred = 0;
+  a.fused_positive = &fused_positive;
+  a.defer_entity = 1;
+  a.entity_deferred = &deferred;
+  a.mir = mir;
+  a.shard_ws = &ws;
+  rc = launch_rows(m, head, a, st);
+  if (rc) return rc;
+  KGE_REQUIRE(deferred && fused_positive, "internal: the single-read row kernel did not run for the entity-sharded step");
+  return KGE_OK;
+}
+
+extern "C" int kge_train_entity_sharded(const kge_model_t *m, int mode, int64_t N, const kge_shard_t *host_shard,
+                                        void *workspace, int64_t workspace_bytes,
+                                        const kge_entity_adam_t *host_entity_adam, int32_t *err_flag, void *stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "mode %d not supported", mode);
+  KGE_REQUIRE(workspace && host_entity_adam && host_entity_adam->exp_avg && host_entity_adam->exp_avg_sq &&
+                  host_entity_adam->step >= 1, "bad entity optimizer state");
+  Mirror mir;
+  GatherLayout L;
+  if ((rc = shard_mirror(m, host_shard, N, mir, L))) return rc;
+  const kge_shard_t &sh = *host_shard;
+  KGE_REQUIRE(workspace_bytes >= kge_train_shard_workspace_bytes(m, sh.world, sh.rows_max, N), "workspace too small");
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(m->device))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t R = sh.rows_max, nentity = m->nentity;
+  const char *g = (const char *)sh.block[sh.rank] + sh.gather_offset;
+  // local sort arrays
+  SplitWs ws{};
+  char *wp = (char *)workspace;
+  ws.cnt = (int *)wp;
+  ws.cursor = ws.cnt + (nentity + 1);
+  ws.queue = ws.cursor + nentity;
+  wp += align256((size_t)(2 * nentity + 1) * 4 + 64);
+  ws.tile_tot = (int *)wp; wp += align256((size_t)((nentity + 1023) / 1024) * 4);
+  const size_t cap = (size_t)sh.world * R * (N + 3);
+  ws.perm = (int *)wp;      wp += align256(cap * 4);
+  ws.gsorted = (float *)wp;
+  ws.Qtab = (float *)(g + L.Qtab);
+  ws.Dvec = (float *)(g + L.Dvec);
+  KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * nentity + 1) + 16) * 4, st));
+  GatherArgs ga{};
+  ga.ids = (const int *)(g + L.ids); ga.Gs = (const float *)(g + L.Gs); ga.dids = (const int *)(g + L.dids);
+  ga.world = sh.world; ga.R = (int)R; ga.N = (int)N;
+  for (int r = 0; r < sh.world; ++r) ga.rows_of[r] = sh.rows_of[r];
+  ga.eb = sh.rank * mir.ent_base + (sh.rank < mir.ent_rem ? sh.rank : mir.ent_rem);
+  ga.ee = ga.eb + mir.ent_base + (sh.rank < mir.ent_rem ? 1 : 0);
+  {
+    const int64_t total = (int64_t)sh.world * R * (N + 3);
+    int g2 = (int)((total + 255) / 256);
+    if (g2 > 148 * 16) g2 = 148 * 16;
+    const int tiles = (int)((nentity + 1023) / 1024);
+    gathered_pairs_kernel<false><<<g2, 256, 0, st>>>(ga, ws.cnt, nullptr, nullptr);
+    KGE_CUDA_OK(cudaGetLastError());
+    scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, nentity);
+    KGE_CUDA_OK(cudaGetLastError());
+    scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, nentity);
+    KGE_CUDA_OK(cudaGetLastError());
+    gathered_pairs_kernel<true><<<g2, 256, 0, st>>>(ga, ws.cursor, ws.perm, ws.gsorted);
+    KGE_CUDA_OK(cudaGetLastError());
+  }
+  const kge_entity_adam_t &o = *host_entity_adam;
+  EntityAdam ea{};
+  ea.exp_avg = o.exp_avg; ea.exp_avg_sq = o.exp_avg_sq;
+  ea.s = adam_scalars(o.lr, o.beta1, o.beta2, o.eps, o.l3_coefficient, o.step);
+  ea.l3 = o.l3_coefficient != 0.0;
+  ea.reg_partials = o.reg_partials; ea.n_reg_partials = o.n_reg_partials;
+  const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
+  RowArgs a{};
+  a.E = m->entity; a.modulus = m->modulus; a.nentity = nentity;
+  a.De = (int)m->entity_dim; a.d = cplx ? (int)(m->entity_dim / 2) : (int)m->entity_dim;
+  a.scale = phase_scale(m); a.N = (int)N; a.row_count = (int)(sh.world * R);
+  a.do_loss = 1; a.err = err_flag; a.entity_adam = &ea; a.mir = mir;
+  const bool head = mode == KGE_HEAD_BATCH;
+#define KGE_ENT(MODEL) \
+  case MODEL: return launch_entity_model<MODEL>(head, a, ws, ga.eb, ga.ee, 0, st, 0);
   switch (m->model) {
     KGE_ENT(KGE_TRANSE)
     KGE_ENT(KGE_DISTMULT)

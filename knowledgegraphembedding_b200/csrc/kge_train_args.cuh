@@ -15,6 +15,18 @@ struct EntityAdam {
   int64_t n_reg_partials;
 };
 
+// Multi-GPU run with the entity-sharded optimizer (kge_train_rows_sharded / kge_train_entity_sharded): every rank maps
+// every rank's peer block (identical layout), rank g owns the entity rows [g*base + min(g, rem), ...) and is the only
+// one to update them.  delta[r] = byte distance from an address inside the local block to the same address inside
+// rank r's block, so a value is mirrored with one extra store per peer.  world == 0: single device, nothing mirrored.
+struct Mirror {
+  int world, rank;
+  int ent_base, ent_rem;                   // balanced contiguous entity ranges: the first `rem` ranks own base + 1 rows
+  long long delta[KGE_PEER_MAX_RANKS];
+};
+
+struct SplitWs;
+
 struct RowArgs {
   const float *E, *R, *modulus;
   const int64_t *positive;     // [B_total, 3]
@@ -44,12 +56,34 @@ struct RowArgs {
   int ring;                    // single-read path: slots per row group in the TMA ring (2..4)
   int l2_hints;                // single-read path: L2 residency hints on (KGE_L2_HINTS=1)
   unsigned long long *phase_cycles;   // debug (KGE_ROW_PHASES=1): [8] cycles of thread 0 per phase, summed over CTAs and rows
+  Mirror mir;                  // entity-sharded multi-GPU step: where the row kernel's outputs are mirrored to
+  const SplitWs *shard_ws;     // host: with mir.world > 1, the (peer-visible) arrays the row kernel writes
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ int owner_of(const Mirror &m, int64_t id) {
+  const int64_t cut = (int64_t)m.ent_rem * (m.ent_base + 1);
+  return id < cut ? (int)(id / (m.ent_base + 1)) : m.ent_rem + (int)((id - cut) / m.ent_base);
+}
+template <typename T>
+__device__ __forceinline__ T *at_rank(const Mirror &m, T *p, int r) {
+  return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + m.delta[r]);
+}
+// store to the local block and to the same place in every peer's block (plain stores: the cross-GPU barrier that
+// follows the kernel fences them at system scope)
+template <typename T>
+__device__ __forceinline__ void store_all(const Mirror &m, T *p, T v) {
+  *p = v;
+  for (int r = 0; r < m.world; ++r)
+    if (r != m.rank) *at_rank(m, p, r) = v;
+}
+#endif
 
 struct SplitWs {             // carved from the caller's workspace
   float *G;                  // [rows, N]   dL/ds of every negative pair
   float *Qtab;               // [rows, De]  query vectors
-  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets
+  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets (NULL in the row kernel of the entity-sharded
+                             //             step: the owner histograms the gathered pairs itself)
   int *cursor;               // [nentity]   scatter cursors
   int *queue;                // [16]        dynamic entity queues of entity_kernel (one per entity slice)
   int *tile_tot;             // [ceil(nentity / 1024)] totals of the scan tiles

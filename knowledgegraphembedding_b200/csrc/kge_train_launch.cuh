@@ -20,6 +20,7 @@ static int launch_entity_pass(const RowArgs &a, const SplitWs &ws, int64_t ent_b
   e.ent_begin = ent_begin; e.ent_count = ent_end - ent_begin;
   e.N = a.N; e.d = a.d; e.De = a.De; e.scale = a.scale;
   e.need_gmod = (MODEL == KGE_PROTATE && !a.do_loss) ? 1 : 0;
+  e.mir = a.mir;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -83,10 +84,15 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
   const bool want_adam = a.entity_adam != nullptr;
   if (vec4 && nunits <= 32 * (CPLX ? 8 : 16) && !getenv("KGE_NO_TMA")) {
     const size_t rowbytes = (size_t)a.De * 4;
-    const bool split = workspace && (a.gE || want_adam) && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
-                       workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
-                       split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity,
-                                           want_adam && a.pos_row_loss && !a.defer_entity);
+    // entity-sharded multi-GPU step: the row kernel writes into the peer-visible arrays of a.shard_ws, the sort and the
+    // entity pass belong to the owners (kge_train_entity_sharded)
+    const bool sharded = a.mir.world > 1 && a.shard_ws != nullptr;
+    const bool split = sharded ? (a.do_loss && a.pos_row_loss && a.loss_kind != KGE_LOSS_POSITIVE &&
+                                  split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity, true))
+                               : (workspace && (a.gE || want_adam) && !(a.do_loss && a.loss_kind == KGE_LOSS_POSITIVE) &&
+                                  workspace_bytes >= split_workspace_bytes(a.row_count, a.N, a.De, a.nentity) &&
+                                  split_path_shape_ok(a.row_count, a.N, a.De, a.d, CPLX, a.nentity,
+                                                      want_adam && a.pos_row_loss && !a.defer_entity));
     // ---- single-read path: row-major forward + dL/dq, counting sort, entity-major dL/dx -----------------
     if (split) {
       constexpr int Hs = CPLX ? 2 : 1;
@@ -111,6 +117,16 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       while (ring_max < 4 && fixed_s + Ws * group_bytes(ring_max + 1) <= 227 * 1024) ++ring_max;
       if (const char *r = getenv("KGE_SPLIT_RING")) { const int v = atoi(r); if (v >= 2 && v <= ring_max) ring = v; }
       while (Ws > 1 && fixed_s + Ws * group_bytes(ring) > 227 * 1024) --Ws;
+      // KGE_SPLIT_CTAS=2 (experiment): two CTAs of half the warps per SM, so that the block-wide phases of one row
+      // (query vector, loss, fold, chain rule, positive triple: ~29 % of a row's cycles at cfg 3) run under the
+      // candidate loop of the other CTA's row
+      int ctas = 1;
+      if (const char *c = getenv("KGE_SPLIT_CTAS")) {
+        if (c[0] == '2' && wpr == 1 && Ws >= 8 && 2 * (fixed_s + (Ws / 2) * group_bytes(ring) + 1024) <= 227 * 1024) {
+          ctas = 2;
+          Ws /= 2;
+        }
+      }
       const size_t per_warp = group_bytes(ring);
       if (Ws >= (wpr == 2 ? 2 : 4) && fixed_s + Ws * per_warp <= 227 * 1024) {
         const size_t total = fixed_s + Ws * per_warp;
@@ -118,17 +134,19 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         ar.ring = ring;
         ar.phase_cycles = row_phase_counters();
         { const char *h = getenv("KGE_L2_HINTS"); ar.l2_hints = h && h[0] == '1'; }
-        SplitWs ws = carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
-        // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
-        // through ws.Dvec); without it the entity-side rows of the positives go to gE with atomics
-        if (!(want_adam && a.pos_row_loss && !a.defer_entity)) ws.Dvec = nullptr;
-        KGE_REQUIRE(ws.Dvec || a.gE, "grad_entity is required when the entity optimizer is not fused");
-        KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
+        SplitWs ws = sharded ? *a.shard_ws : carve_split_ws(workspace, a.row_count, a.N, a.De, a.nentity);
+        if (!sharded) {
+          // the fused optimizer needs the positive triple in the same launch (its gradient rows reach the entity pass
+          // through ws.Dvec); without it the entity-side rows of the positives go to gE with atomics
+          if (!(want_adam && a.pos_row_loss && !a.defer_entity)) ws.Dvec = nullptr;
+          KGE_REQUIRE(ws.Dvec || a.gE, "grad_entity is required when the entity optimizer is not fused");
+          KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * a.nentity + 1) + 16) * 4, st));
+        }
         // persistent CTAs (one per SM: the slots take the whole shared memory), rows are dealt round-robin
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int sgrid = grid < sms ? grid : sms;
+        const int sgrid = grid < sms * ctas ? grid : sms * ctas;
 #define KGE_SPLIT_LAUNCH2(NCH, VAR)                                                                    \
   do {                                                                                                 \
     auto k = row_kernel_split<MODEL, HEAD, NCH, VAR>;                                                  \
@@ -153,6 +171,10 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
 #undef KGE_SPLIT_LAUNCH2
         KGE_CUDA_OK(cudaGetLastError());
         if (a.fused_positive && a.pos_row_loss) *a.fused_positive = 1;
+        if (sharded) {
+          if (a.entity_deferred) *a.entity_deferred = 1;
+          return KGE_OK;
+        }
         {
           const int tiles = (int)((a.nentity + 1023) / 1024);
           scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, a.nentity);
@@ -175,6 +197,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
         return launch_entity_pass<MODEL, HEAD>(a, ws, 0, a.nentity, 0, st);
       }
     }
+    KGE_REQUIRE(!sharded, "the entity-sharded step needs the single-read path (check kge_train_plan first)");
     // ---- two-sweep TMA kernel ------------------------------------------------------------------------------
     const size_t base = sizeof(float) * (2 * (size_t)((a.De + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
     const size_t fixed = base + 16;
@@ -190,6 +213,7 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       return KGE_OK;
     }
   }
+  KGE_REQUIRE(a.mir.world <= 1, "the entity-sharded step needs the single-read path (check kge_train_plan first)");
   if (vec4) {
     auto k = row_kernel<MODEL, HEAD, 4>;
     if (smem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
       if (lane == 0 && hw == 0) {
-        atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
+        if (ws.cnt) atomicAdd(ws.cnt + id, 1);            // histogram for the entity-major pass
         uint64_t *bar = gbars + s;
         float *dst = slots + (size_t)s * HS;
         const float *src = a.E + id * a.De;
@@ -211,9 +211,9 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       } else {
         build_q<MODEL, HEAD>(F, Rr, k, a.d, a.scale, q, DP);
       }
-      qout[k] = q[k];
+      store_all(a.mir, qout + k, q[k]);                    // (entity-sharded multi-GPU step: every rank gets the row)
       dq[k] = 0.f;
-      if (CPLX) { qout[a.d + k] = q[DP + k]; dq[a.d + k] = 0.f; }
+      if (CPLX) { store_all(a.mir, qout + a.d + k, q[DP + k]); dq[a.d + k] = 0.f; }
     }
     __syncthreads();
 
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
         const float sv = sc[n];
         lacc += w * log_sigmoid(-sv);
         const float g = 0.5f * u * w * sigmoid(sv);
-        gout[n] = g;
+        store_all(a.mir, gout + n, g);
         if constexpr (MODEL == KGE_PROTATE) gmod += -g * (a.gamma - sv) / modulus;   // -g * sum|sin|
       }
       const float row_val = block_reduce(lacc, scratch, false);
@@ -510,7 +510,9 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     // ---- phase 5: chain rule into the fixed entity row and the relation row -----------------------------
     // With the fused optimizer (ws.Dvec) the entity-side gradient rows are written to the workspace and reach the
     // entity-major pass as "direct" entries of their target entity; otherwise they are added to gE with atomics.
+    // (entity-sharded multi-GPU step: the row goes to the block of the rank that owns the target entity, and only there)
     float *gF = ws.Dvec ? ws.Dvec + (size_t)(3 * rl) * a.De : a.gE + fid * a.De;
+    if (a.mir.world > 1) gF = at_rank(a.mir, gF, owner_of(a.mir, fid));
     float *gRr = a.gR + rid * a.Dr;
     for (int k = tid; k < a.d; k += blockDim.x) {
       float dF0, dF1, dR0, dR1;
@@ -537,8 +539,8 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       if ((uint64_t)pt >= (uint64_t)a.nentity) pt = 0;
       if (ws.Dvec && tid < 3) {                             // direct entries of this row: (fixed, head, tail)
         const int64_t target = tid == 0 ? fid : (tid == 1 ? ph : pt);
-        ws.dids[3 * rl + tid] = (int)target;
-        atomicAdd(ws.cnt + target, 1);
+        store_all(a.mir, ws.dids + 3 * rl + tid, (int)target);
+        if (ws.cnt) atomicAdd(ws.cnt + target, 1);
       }
       const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
       // (tail-batch: q = fold(h, r) is the q of the negatives, still in shared memory, unless an id was out of range)
@@ -562,6 +564,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       }
       const float gop = dsum_of<MODEL>(gp, modulus);
       float *gT = ws.Dvec ? ws.Dvec + (size_t)(3 * rl + 2) * a.De : a.gE + pt * a.De;
+      if (a.mir.world > 1) gT = at_rank(a.mir, gT, owner_of(a.mir, pt));
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dq0 = 0.f, dq1 = 0.f, dx0 = 0.f, dx1 = 0.f;
         op_backward<OPS>(q[k], CPLX ? q[DP + k] : 0.f, Trow[k], CPLX ? Trow[a.d + k] : 0.f, a.scale, gop, dq0, dq1, dx0, dx1);
@@ -577,6 +580,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       }
       __syncthreads();
       float *gH = ws.Dvec ? ws.Dvec + (size_t)(3 * rl + 1) * a.De : a.gE + ph * a.De;
+      if (a.mir.world > 1) gH = at_rank(a.mir, gH, owner_of(a.mir, ph));
       for (int k = tid; k < a.d; k += blockDim.x) {
         float dF0, dF1, dR0, dR1;
         if constexpr (MODEL == KGE_ROTATE) chain_q_rot<false>(Hrow, rot[k], rot[d4 + k], dq, k, a.d, a.scale, dF0, dF1, dR0);
@@ -628,6 +632,7 @@ struct EntArgs {
   int l3;
   double *reg_partials;      // [gridDim.x]
   const int32_t *err;        // a bad index in this step cancels the update (model.py:86-146 raises before the optimizer)
+  Mirror mir;                // entity-sharded multi-GPU step: the updated rows are also stored into every peer's table
 };
 
 // One warp per (entity, part) task, S parts per row.  dL/dx is element-wise (no row reduction), so splitting the
@@ -854,6 +859,10 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
             float t0, t1, t2, t3;
             unpack2(p01, t0, t1); unpack2(p23, t2, t3);
             st4_hint(a.E + hb + u * V, make_float4(t0, t1, t2, t3), pol_e);
+            if (a.mir.world > 1) {                          // owner computes, every replica takes the same bits (NVLink stores)
+              for (int r = 0; r < a.mir.world; ++r)
+                if (r != a.mir.rank) *reinterpret_cast<float4 *>(at_rank(a.mir, a.E + hb + u * V, r)) = make_float4(t0, t1, t2, t3);
+            }
             unpack2(m01, t0, t1); unpack2(m23, t2, t3);
             st4_hint(a.exp_avg + hb + u * V, make_float4(t0, t1, t2, t3), pol_mv);
             unpack2(v01, t0, t1); unpack2(v23, t2, t3);

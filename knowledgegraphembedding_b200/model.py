@@ -225,6 +225,7 @@ class KGEModel(nn.Module):
             raise IndexError('index out of range in sample (entity/relation id outside the embedding table)')
 
     def _apply(self, fn, *args, **kwargs):      # .cuda()/.to(): workspaces belong to the old device
+        self._release_shard()
         self._ws = {}
         return super(KGEModel, self)._apply(fn, *args, **kwargs)
 
@@ -364,12 +365,184 @@ class KGEModel(nn.Module):
         sliced = getattr(optimizer, '_kge_sliced_moments', None)
         if not sliced:
             return
-        from .peer import gather_sliced_moments
-        regions, offsets = sliced
+        from .peer import gather_moment_ranges
         params = self._trainable()
         pairs = [(optimizer.state[p]['exp_avg'], optimizer.state[p]['exp_avg_sq']) for p in params if len(optimizer.state[p])]
-        gather_sliced_moments(pairs, list(offsets)[:len(pairs)], list(regions))
+        gather_moment_ranges(pairs, list(sliced)[:len(pairs)])
         optimizer._kge_sliced_moments = None
+
+    def _own_moments(self, optimizer, layout):
+        """Record which rank keeps which element ranges of exp_avg / exp_avg_sq current (peer.moment_ranges /
+        entity_ranges, one tuple per trainable parameter); a change of ownership gathers the moments first, and
+        optimizer.state_dict() (run.py:106) gathers them through a pre-hook."""
+        held = getattr(optimizer, '_kge_sliced_moments', None)
+        if held is not None and held != layout:
+            self._gather_moments(optimizer)
+        if not getattr(optimizer, '_kge_hooked', False):
+            optimizer.register_state_dict_pre_hook(lambda opt: self._gather_moments(opt))
+            optimizer._kge_hooked = True
+        optimizer._kge_sliced_moments = layout
+
+    # ---- entity-sharded optimizer (multi-GPU; include/kge_b200.h `kge_train_rows_sharded`) ------------------------------
+    def _release_shard(self):
+        """Move the entity table out of the peer block of the entity-sharded step and unmap the block (device change,
+        larger batch, end of life).  No exchange may be in flight: every step ends with a cross-GPU barrier."""
+        held = self._ws.pop('shard', None)
+        if held is None:
+            return
+        torch.cuda.synchronize(held['dev'])
+        if self.entity_embedding.data_ptr() == held['e_view'].data_ptr():
+            with torch.no_grad():
+                self.entity_embedding.data = self.entity_embedding.data.clone()
+        self._ws.pop('own_desc', None)
+        held['peer'].close()
+
+    def _shard_state(self, B, N, rank, world, dev):
+        """Peer block of the entity-sharded step, [flags | dR dM row-losses | entity table | gather area], created on the
+        first step (collective) and re-created when a larger batch arrives; the entity Parameter's storage is moved into
+        it so that the owners of other entity ranges can store updated rows in place.  None: not available."""
+        if os.environ.get('KGE_PEER_DENSE') or os.environ.get('KGE_NO_PEER') or os.environ.get('KGE_KEEP_GRADS') \
+                or self._ws.get('peer') is False or self._ws.get('shard') is False:
+            return None
+        if self.nentity < world or self.entity_dim % 4:
+            return None
+        lib = _lib.load()
+        rows_max = -(-int(B) // world)
+        held = self._ws.get('shard')
+        if held is not None and (held['rows_cap'] < rows_max or held['N'] != N or held['world'] != world or held['dev'] != dev):
+            self._release_shard()
+            held = None
+        E, R = self.entity_embedding, self.relation_embedding
+        if held is None:
+            desc = self._own_descriptor()
+            if not (lib.kge_train_plan(ctypes.byref(desc), rows_max, N) & _lib.PLAN_ENTITY_ADAM):
+                return None
+            from .peer import PeerExchange, _align256
+            nR4 = (R.numel() + 3) // 4 * 4
+            small = nR4 + 4 + 2 * rows_max * world + 64
+            e_bytes = _align256(E.numel() * 4)
+            g_bytes = int(lib.kge_train_gather_bytes(ctypes.byref(desc), world, rows_max, N))
+            try:
+                peer = PeerExchange(dev, small, extra_bytes=e_bytes + g_bytes)
+            except _lib.KgeError as exc:
+                logging.warning('entity-sharded optimizer disabled (no peer memory): %s' % exc)
+                self._ws['shard'] = False
+                return None
+            wbytes = int(lib.kge_train_shard_workspace_bytes(ctypes.byref(desc), world, rows_max, N))
+            held = self._ws['shard'] = {
+                'peer': peer, 'rows_cap': rows_max, 'N': N, 'world': world, 'dev': dev,
+                'gather_offset': peer.extra_offset + e_bytes,
+                'e_view': peer.extra[:E.numel() * 4].view(torch.float32).view(E.shape),
+                'wsp': torch.empty(wbytes, dtype=torch.uint8, device=dev), 'wbytes': wbytes, 'views': {},
+                'reg_scratch': torch.zeros(148, dtype=torch.float64, device=dev),
+            }
+        if E.data_ptr() != held['e_view'].data_ptr():
+            with torch.no_grad():
+                held['e_view'].copy_(E.data)
+                E.data = held['e_view']
+            self._ws.pop('own_desc', None)
+        return held
+
+    def _train_step_sharded(self, held, optimizer, positive, negative, weight, B, rows, N, row_begin, mode_id, loss_kind,
+                            alpha, reg, st):
+        """One train step with the entity-sharded optimizer (see include/kge_b200.h): row kernel with mirrored outputs ->
+        barrier -> owner's sort + entity-major backward + fused Adam with NVLink parameter stores; the relation table
+        (and modulus) and the loss rows go through the small dense exchange; barrier.  Returns the loss buffer."""
+        model = self
+        dev = held['dev']
+        peer = held['peer']
+        rank, world = peer.rank, peer.world
+        E, R = model.entity_embedding, model.relation_embedding
+        err = model._err_flag()
+        desc = model._own_descriptor()
+        nR = R.numel()
+        nR4 = (nR + 3) // 4 * 4
+        ws = held['views'].get(B)
+        if ws is None:
+            total = nR4 + 4 + 2 * B
+            flat = peer.workspace[:total]
+            ws = held['views'][B] = {
+                'flat': flat, 'gR': flat[:nR].view_as(R), 'gM': flat[nR4:nR4 + 1].view(1, 1),
+                'pos_row': flat[nR4 + 4:nR4 + 4 + B], 'neg_row': flat[nR4 + 4 + B:total], 'param_floats': nR4 + 4,
+                'rows_sum': model._buffer('rows_sum', 2 * B, torch.float32, dev)[:2 * B],
+                'wsum': model._buffer('wsum', 1, torch.float32, dev),
+                'reg': model._buffer('reg_partials', 148 * 8, torch.float64, dev),
+                'rows_of': [hi - lo for lo, hi in (shard_bounds(B, r, world) for r in range(world))],
+            }
+        out = model._ws['loss_out']
+        events = model._ws.get('kernel_events')
+        xevents = model._ws.get('exchange_events')
+        params = model._trainable()
+        gM = ws['gM'] if model.model_name == 'pRotatE' else None
+        grads = [None, ws['gR']] + ([gM] if gM is not None else [])
+
+        from .peer import entity_ranges, moment_ranges
+        offsets = [0, 0] + ([nR4] if gM is not None else [])
+        small = moment_ranges(offsets[1:], [p.numel() for p in params[1:]], [(0, ws['param_floats'] // 4)], world)
+        model._own_moments(optimizer, (entity_ranges(model.nentity, model.entity_dim, world),) + small)
+        model._ws['exchange_regions'] = 1
+
+        group = optimizer.param_groups[0]
+        hyper = (float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']))
+        entries = []
+        for i, (p, g) in enumerate(zip(params, grads)):
+            state = optimizer.state[p]
+            if len(state) == 0:
+                state['step'] = torch.tensor(0.0, dtype=torch.float32)
+                state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            state['step'] += 1
+            entries.append((p.data_ptr(), g.data_ptr() if g is not None else None, state['exp_avg'].data_ptr(),
+                            state['exp_avg_sq'].data_ptr(), p.numel(), int(state['step'].item()),
+                            1 if (reg != 0.0 and i < 2) else 0))
+
+        _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
+        if weight is not None:
+            _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
+        if reg != 0.0:               # value of the L3 term from the replicated tables, before any owner updates them
+            tensors = (_lib.KgeAdamTensor * 2)(*[_lib.KgeAdamTensor(*c) for c in entries[:2]])
+            _lib.call("kge_l3_partials", tensors, 2, _ptr(ws['reg']), ws['reg'].numel(), st)
+        shard = peer.shard(held['gather_offset'], held['rows_cap'], ws['rows_of'])
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _lib.call("kge_train_rows_sharded", ctypes.byref(desc), mode_id, loss_kind, alpha, _ptr(positive), _ptr(negative),
+                  _ptr(weight[row_begin:]) if weight is not None else None,
+                  _ptr(ws['wsum']) if weight is not None else None, B, rows, N, _ptr(ws['neg_row'][row_begin:]),
+                  _ptr(ws['pos_row'][row_begin:]), _ptr(ws['gR']), _ptr(gM), ctypes.byref(shard), _ptr(err), st)
+        peer.barrier(2, err, st, exchange_err=True)      # every rank's rows are in every block; errors are shared
+        # the relation table's (small, dense) exchange runs on a second stream under the owners' entity pass
+        main = torch.cuda.current_stream(dev)
+        side = model._ws.get('exchange_stream')
+        if side is None:
+            side = model._ws['exchange_stream'] = torch.cuda.Stream(dev)
+        side.wait_stream(main)
+        peer.reduce_adam(entries[1:], hyper, ws['param_floats'], (0, ws['param_floats'] // 4), ws['param_floats'], 2 * B,
+                         ws['rows_sum'], err, ctypes.c_void_p(side.cuda_stream), l3=reg)
+        e0 = entries[0]
+        ea = _lib.KgeEntityAdam(exp_avg=e0[2], exp_avg_sq=e0[3], step=e0[5], lr=hyper[0], beta1=hyper[1], beta2=hyper[2],
+                                eps=hyper[3], l3_coefficient=reg,
+                                reg_partials=held['reg_scratch'].data_ptr() if reg != 0.0 else None, n_reg_partials=148)
+        _lib.call("kge_train_entity_sharded", ctypes.byref(desc), mode_id, N, ctypes.byref(shard), _ptr(held['wsp']),
+                  held['wbytes'], ctypes.byref(ea), _ptr(err), st)
+        if events is not None:
+            ev1.record()
+            events.append((ev0, ev1))
+        if xevents is not None:
+            xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xev0.record()
+        main.wait_stream(side)
+        peer.barrier(3, err, st)                         # every owner's parameter rows have landed in every table
+        if xevents is not None:
+            xev1.record()
+            xevents.append((xev0, xev1))
+        for p in params:
+            p.grad = None
+        model._ws['update_cancelled_on_error'] = False
+        _lib.call("kge_loss_finalize", _ptr(ws['rows_sum'][:B]), _ptr(ws['rows_sum'][B:]), _ptr(weight),
+                  _ptr(ws['wsum']) if weight is not None else None, B, reg,
+                  _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel() if reg != 0.0 else 0, _ptr(out), st)
+        return out
 
     @staticmethod
     def _fusable_adam(model, optimizer):
@@ -474,9 +647,15 @@ class KGEModel(nn.Module):
         mode_id = _lib.MODE_IDS[mode]
 
         err = model._err_flag()
-        desc = model._own_descriptor()
         rank, world = _dist()
         fused_adam = KGEModel._fusable_adam(model, optimizer)
+        if world > 1 and fused_adam:
+            # multi-GPU default: entity-sharded optimizer (owner computes; no dense gradient, no exchange kernel)
+            held = model._shard_state(B, N, rank, world, dev)
+            if held is not None:
+                return model._train_step_sharded(held, optimizer, positive, negative, weight, B, rows, N, row_begin,
+                                                 mode_id, loss_kind, alpha, reg, st)
+        desc = model._own_descriptor()
         # which kernels run for this shape (cached per shape): the single-read path can also apply the entity table's
         # Adam update inside the backward -- on one device, with a stock Adam, unless the caller wants p.grad
         wkey = (rows, N, desc.entity_dim, desc.nentity)
@@ -522,14 +701,9 @@ class KGEModel(nn.Module):
             from .peer import exchange_regions
             regions, entity_slices = exchange_regions(ws['param_floats'], model.nentity, model.entity_dim,
                                                       model._exchange_slices(B, world, N))
-            layout = (tuple(regions), tuple((g.data_ptr() - ws['flat'].data_ptr()) // 4 for g in grads))
-            held = getattr(optimizer, '_kge_sliced_moments', None)
-            if held is not None and held != layout:
-                model._gather_moments(optimizer)             # ownership of the moments moves: make them whole first
-            if not getattr(optimizer, '_kge_hooked', False):
-                optimizer.register_state_dict_pre_hook(lambda opt: model._gather_moments(opt))
-                optimizer._kge_hooked = True
-            optimizer._kge_sliced_moments = layout
+            from .peer import moment_ranges
+            offsets = [(g.data_ptr() - ws['flat'].data_ptr()) // 4 for g in grads]
+            model._own_moments(optimizer, moment_ranges(offsets, [p.numel() for p in params], regions, world))
             model._ws['exchange_regions'] = len(regions)
         elif world > 1 and getattr(optimizer, '_kge_sliced_moments', None):
             model._gather_moments(optimizer)

@@ -14,7 +14,12 @@ import torch
 
 from . import _lib
 
-FLAG_BYTES = 1024          # 2 channels x KGE_PEER_MAX_RANKS uint32, padded; the workspace starts 16-byte aligned after it
+FLAG_BYTES = 1024          # 8 channels x KGE_PEER_MAX_RANKS uint32 (0/1: kge_peer_reduce_adam, 2/3: kge_peer_barrier, 6/7: its
+#                            error words), padded; the workspace starts 16-byte aligned after it
+
+
+def _align256(n):
+    return (int(n) + 255) // 256 * 256
 
 
 def region_slices(region, world):
@@ -63,7 +68,7 @@ class PeerExchange:
     handles through kge_peer_alloc/export/open (unicast NVLink loads and stores).  KGE_PEER_BACKEND=symm|ipc forces one,
     KGE_PEER_MULTICAST=0|1 overrides whether the multicast mapping is used (default: only above 4 ranks)."""
 
-    def __init__(self, device, workspace_floats, group=None):
+    def __init__(self, device, workspace_floats, group=None, extra_bytes=0):
         import torch.distributed as dist
         self.device = device
         self.group = group
@@ -71,7 +76,12 @@ class PeerExchange:
         if not (2 <= self.world <= _lib.PEER_MAX_RANKS):
             raise _lib.KgeError("peer exchange supports 2..%d ranks" % _lib.PEER_MAX_RANKS)
         self.capacity = int(workspace_floats)
-        nbytes = FLAG_BYTES + 4 * self.capacity
+        # [flags | workspace | extra]: `extra` (entity-sharded step) holds the entity table and the gather area
+        self.extra_offset = _align256(FLAG_BYTES + 4 * self.capacity)
+        self.extra_bytes = int(extra_bytes)
+        nbytes = self.extra_offset + self.extra_bytes if extra_bytes else FLAG_BYTES + 4 * self.capacity
+        self.block_bytes = nbytes
+        self._epochs = {}
         self._local = ctypes.c_void_p()
         self._mapped = []
         self._symm = None
@@ -90,6 +100,8 @@ class PeerExchange:
             self.close()
             raise _lib.KgeError("peer memory unavailable: " + ("; ".join(errors) or "no backend"))
         self.backend = "symm" if self._symm is not None else "ipc"
+        self.block_ptrs = [int(p) for p in ptrs]
+        self.extra = self._block[self.extra_offset:self.extra_offset + self.extra_bytes] if extra_bytes else None
         self.struct = _lib.KgePeerGroup(world=self.world, rank=self.rank)
         for r, p in enumerate(ptrs):
             self.struct.flags[r] = p
@@ -134,7 +146,7 @@ class PeerExchange:
         mc = int(getattr(handle, "multicast_ptr", 0) or 0)
         self._symm, self._block = handle, block
         self.multicast = mc + shift if mc else 0
-        self.workspace = block[FLAG_BYTES:].view(torch.float32)
+        self.workspace = block[FLAG_BYTES:FLAG_BYTES + 4 * self.capacity].view(torch.float32)
         return [p + shift for p in ptrs]
 
     def _init_ipc(self, nbytes):
@@ -172,7 +184,7 @@ class PeerExchange:
             return None, why
         block = torch.as_tensor(_DeviceBlock(self._local.value, nbytes), device=device)
         self._block = block
-        self.workspace = block[FLAG_BYTES:].view(torch.float32)        # [capacity] fp32, zero-initialised
+        self.workspace = block[FLAG_BYTES:FLAG_BYTES + 4 * self.capacity].view(torch.float32)    # zero-initialised
         return ptrs, []
 
     def reduce_adam(self, entries, hyper, param_floats, region, row_offset, row_floats, rows_out, err, stream, l3=0.0):
@@ -185,6 +197,21 @@ class PeerExchange:
                   region[0], region[1], lo4, hi4, row_offset, row_floats,
                   ctypes.c_void_p(rows_out.data_ptr()) if row_floats else None, *hyper, float(l3),
                   ctypes.c_void_p(err.data_ptr()), stream)
+
+    def barrier(self, channel, err, stream, exchange_err=False):
+        """Cross-GPU barrier on `stream` (kge_peer_barrier; channel 2 or 3, every rank calls it in the same order)."""
+        epoch = self._epochs[channel] = self._epochs.get(channel, 0) + 1
+        _lib.call("kge_peer_barrier", ctypes.byref(self.struct), channel, epoch, 1 if exchange_err else 0,
+                  ctypes.c_void_p(err.data_ptr()) if err is not None else None, stream)
+
+    def shard(self, gather_offset, rows_max, rows_of):
+        """kge_shard_t of the entity-sharded step for this group's blocks."""
+        sh = _lib.KgeShard(world=self.world, rank=self.rank, block_bytes=self.block_bytes,
+                           gather_offset=int(gather_offset), rows_max=int(rows_max))
+        for r in range(self.world):
+            sh.block[r] = self.block_ptrs[r]
+            sh.rows_of[r] = int(rows_of[r])
+        return sh
 
     def close(self):
         """Unmap the peers' blocks and release the local one (the caller makes sure no exchange is in flight)."""
@@ -204,23 +231,55 @@ class PeerExchange:
             pass
 
 
-def gather_sliced_moments(tensors, offsets, regions, group=None):
-    """After peer-exchange steps exp_avg / exp_avg_sq are current only on the rank owning each slice.  Broadcast every
-    owned piece from its owner so that all ranks hold the full moments (before optimizer.state_dict(), or before
-    switching to the replicated Adam / another region layout).  tensors: [(exp_avg, exp_avg_sq)] per parameter,
-    offsets: the parameter's first float inside the workspace, regions: the exchange regions of the steps so far."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    for (m, v), off in zip(tensors, offsets):
-        n = m.numel()
-        fm, fv = m.view(-1), v.view(-1)
+def moment_ranges(offsets, numels, regions, world):
+    """Who keeps which part of the Adam moments current after kge_peer_reduce_adam steps over `regions`: per tensor
+    (first workspace float `offsets[i]`, `numels[i]` elements) a tuple of (rank, begin, end) element ranges."""
+    out = []
+    for off, n in zip(offsets, numels):
+        rs = []
         for region in regions:
             for r, (lo4, hi4) in enumerate(region_slices(region, world)):
                 a, b = max(4 * lo4, off) - off, min(4 * hi4, off + n) - off
                 if a < b:
-                    src = dist.get_global_rank(group, r) if group is not None else r
-                    dist.broadcast(fm[a:b], src=src, group=group)
-                    dist.broadcast(fv[a:b], src=src, group=group)
+                    rs.append((r, int(a), int(b)))
+        out.append(tuple(rs))
+    return tuple(out)
 
 
-__all__ = ["PeerExchange", "region_slices", "exchange_regions", "gather_sliced_moments"]
+def entity_ranges(nentity, entity_dim, world):
+    """Moment ownership of the entity table in the entity-sharded step: rank r owns the rows
+    [r*base + min(r, rem), + base (+1 if r < rem)) -- the same split as kge_shard_t / Mirror::ent_base, ent_rem."""
+    base, rem = divmod(int(nentity), int(world))
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        if hi > lo:
+            out.append((r, lo * int(entity_dim), hi * int(entity_dim)))
+        lo = hi
+    return tuple(out)
+
+
+def gather_moment_ranges(tensors, ranges, group=None):
+    """After sliced-optimizer steps exp_avg / exp_avg_sq are current only on the rank owning each range.  Broadcast
+    every owned piece from its owner so that all ranks hold the full moments (before optimizer.state_dict(), or before
+    switching to the replicated Adam / another ownership layout).  tensors: [(exp_avg, exp_avg_sq)] per parameter,
+    ranges: per parameter the (rank, begin, end) element ranges (moment_ranges / entity_ranges)."""
+    import torch.distributed as dist
+    for (m, v), rs in zip(tensors, ranges):
+        fm, fv = m.view(-1), v.view(-1)
+        for r, a, b in rs:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            dist.broadcast(fm[a:b], src=src, group=group)
+            dist.broadcast(fv[a:b], src=src, group=group)
+
+
+def gather_sliced_moments(tensors, offsets, regions, group=None):
+    """gather_moment_ranges for the region layout of kge_peer_reduce_adam (offsets: each parameter's first float
+    inside the workspace, regions: the exchange regions of the steps so far)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    gather_moment_ranges(tensors, moment_ranges(offsets, [m.numel() for m, _ in tensors], regions, world), group)
+
+
+__all__ = ["PeerExchange", "region_slices", "exchange_regions", "gather_sliced_moments", "moment_ranges",
+           "entity_ranges", "gather_moment_ranges"]

@@ -1,8 +1,10 @@
 """Worker of tests/test_multi_gpu.py (one process per GPU, launched with torch.distributed.run).
 
 Checks on N >= 2 B200s, against the numpy oracle of the reference's single-device train step on the WHOLE batch:
-  * batch-sharded training through the NVLink peer-memory exchange (kge_peer_reduce_adam): losses, tables and gathered
-    Adam moments within 1e-5, replicas bit-identical on every rank, optimizer.state_dict() whole on every rank;
+  * batch-sharded training with the entity-sharded optimizer (kge_train_rows_sharded / kge_train_entity_sharded: the
+    multi-GPU default) and through the dense NVLink peer-memory exchange (kge_peer_reduce_adam, KGE_PEER_DENSE=1):
+    losses, tables and gathered Adam moments within 1e-5, replicas bit-identical on every rank,
+    optimizer.state_dict() whole on every rank;
   * the same through the NCCL all-reduce path (KGE_NO_PEER behaviour), and that the two paths agree;
   * switching an optimizer from the peer path to the NCCL path mid-run (moments gathered automatically);
   * entity-sharded filtered ranking: ranks equal the oracle's;
@@ -24,7 +26,8 @@ from conftest import outlier_fraction, relinf          # noqa: E402
 from knowledgegraphembedding_b200 import KGEModel      # noqa: E402
 from oracle import kge_oracle as O                     # noqa: E402
 
-FLAGS = {"TransE": (False, False), "RotatE": (True, False), "pRotatE": (False, False), "ComplEx": (True, True)}
+FLAGS = {"TransE": (False, False), "RotatE": (True, False), "pRotatE": (False, False), "ComplEx": (True, True),
+         "DistMult": (False, False)}
 TOL = 1e-5
 
 
@@ -65,6 +68,8 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
     rank, world = dist.get_rank(), dist.get_world_size()
     st = O.init_tables(model, nentity, nrel, d, gamma, *FLAGS[model], seed=3)
     pool = batches(nentity, nrel, B, N, steps, seed=7)
+    sharded_expected = N >= 8 and nentity >= world and (d * (2 if FLAGS[model][0] else 1)) % 4 == 0 and \
+        (d if FLAGS[model][0] else d) % 4 == 0
     args = types.SimpleNamespace(cuda=True, negative_adversarial_sampling=adversarial, adversarial_temperature=0.5,
                                  uni_weight=uni_weight, regularization=reg)
     ref = O.TrainState(model, st, gamma, d)
@@ -72,8 +77,11 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
                 for b in pool]
 
     results = {}
-    for path in ("peer", "nccl", "switch"):
+    for path in ("sharded", "peer", "nccl", "switch"):
         m = build(model, nentity, nrel, d, gamma, st, dev)
+        os.environ.pop("KGE_PEER_DENSE", None)
+        if path == "peer":
+            os.environ["KGE_PEER_DENSE"] = "1"
         if path == "nccl":
             m._ws['peer'] = False
         opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
@@ -88,6 +96,10 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
             if rank == 0:
                 print("peer backend:", m._ws['peer'].backend, "multicast" if m._ws['peer'].multicast else "unicast", flush=True)
             assert getattr(opt, '_kge_sliced_moments', None) is not None
+        if path == "sharded" and sharded_expected:
+            assert isinstance(m._ws.get('shard'), dict), "entity-sharded optimizer was not active"
+            assert m.entity_embedding.data_ptr() == m._ws['shard']['e_view'].data_ptr()
+            assert getattr(opt, '_kge_sliced_moments', None) is not None and m.entity_embedding.grad is None
         sd = opt.state_dict()                    # run.py:106 -- gathers the sliced moments on the peer path
         assert getattr(opt, '_kge_sliced_moments', None) is None
         for log, want in zip(logs, ref_logs):
@@ -106,9 +118,11 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
                 assert relinf(g, w) <= 1e-4, (model, path, name, key, relinf(g, w))
                 identical_on_all_ranks(mom[key], f"{model}/{path}/{name}/{key}")
         results[path] = {n: getattr(m, n).detach().clone() for n in names}
-    for n in results["peer"]:
-        a, b = results["peer"][n].cpu().numpy(), results["nccl"][n].cpu().numpy()
-        assert outlier_fraction(a, b, TOL) <= 1e-3, (model, n)
+    os.environ.pop("KGE_PEER_DENSE", None)
+    for other in ("peer", "sharded"):
+        for n in results[other]:
+            a, b = results[other][n].cpu().numpy(), results["nccl"][n].cpu().numpy()
+            assert outlier_fraction(a, b, TOL) <= 1e-3, (model, other, n)
     if rank == 0:
         print(f"train ok: {model} nentity={nentity} d={d} B={B} N={N} world={world}", flush=True)
 
@@ -132,12 +146,17 @@ def check_full_size(dev):
         oracle = ([C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0) for b in pool], ts)
     dist.barrier()
     out = {}
-    for path in ("peer", "nccl"):
+    for path in ("sharded", "peer", "nccl"):
         m = build(model, nentity, nrel, d, gamma, st, dev)
+        os.environ.pop("KGE_PEER_DENSE", None)
+        if path == "peer":
+            os.environ["KGE_PEER_DENSE"] = "1"
         if path == "nccl":
             m._ws['peer'] = False
         opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=lr)
         logs = [KGEModel.train_step(m, opt, iter([as_torch(b)]), args) for b in pool]
+        if path == "sharded":
+            assert isinstance(m._ws.get('shard'), dict), "entity-sharded optimizer was not active at full size"
         sd = opt.state_dict()
         for name in ("entity_embedding", "relation_embedding"):
             identical_on_all_ranks(getattr(m, name), f"full/{path}/{name}")
@@ -153,15 +172,18 @@ def check_full_size(dev):
                 assert outlier_fraction(got, want, TOL) <= 1e-4 and np.max(np.abs(got - want)) <= 2.5 * lr * steps, (path, name)
             assert relinf(out[path][3], ts.m["entity_embedding"]) <= 1e-4, path
             assert relinf(out[path][4], ts.v["entity_embedding"]) <= 1e-4, path
+        m._release_shard()
         del m, opt
         torch.cuda.empty_cache()
-    for a, b in zip(out["peer"][0], out["nccl"][0]):
-        for k in a:
-            assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]), (k, a[k], b[k])
-    for i, what in ((1, "E"), (2, "R")):
-        got, want = out["peer"][i], out["nccl"][i]
-        assert outlier_fraction(got, want, TOL) <= 1e-4 and np.max(np.abs(got - want)) <= 2.5 * lr * steps, what
-    assert relinf(out["peer"][3], out["nccl"][3]) <= 1e-4 and relinf(out["peer"][4], out["nccl"][4]) <= 1e-4
+    os.environ.pop("KGE_PEER_DENSE", None)
+    for other in ("peer", "sharded"):
+        for a, b in zip(out[other][0], out["nccl"][0]):
+            for k in a:
+                assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]), (other, k, a[k], b[k])
+        for i, what in ((1, "E"), (2, "R")):
+            got, want = out[other][i], out["nccl"][i]
+            assert outlier_fraction(got, want, TOL) <= 1e-4 and np.max(np.abs(got - want)) <= 2.5 * lr * steps, (other, what)
+        assert relinf(out[other][3], out["nccl"][3]) <= 1e-4 and relinf(out[other][4], out["nccl"][4]) <= 1e-4, other
     if rank == 0:
         print(f"full-size ok: world={world}", flush=True)
 
@@ -194,6 +216,12 @@ def main():
     check_case("TransE", 1000, 11, 50, 9.0, 16, 16, 3, dev, adversarial=False, uni_weight=True)   # model.py:274-275,281-283
     check_case("TransE", 200, 3, 8, 6.0, 1, 4, 2, dev)                 # fewer rows than ranks: some ranks hold no row
     check_case("ComplEx", 1001, 7, 32, 20.0, 64, 32, 3, dev, reg=1e-3)   # -r: L3 gradient inside the peer exchange
+    # shapes the entity-sharded optimizer takes (rows of 16-byte multiples, >= 8 candidates): ragged rows per rank with
+    # the modulus, uniform weights, fewer rows than ranks, -r on a real-valued model
+    check_case("pRotatE", 517, 3, 12, 6.0, 33, 8, 3, dev)
+    check_case("TransE", 1000, 11, 48, 9.0, 16, 16, 3, dev, adversarial=False, uni_weight=True)
+    check_case("TransE", 200, 3, 8, 6.0, 1, 8, 2, dev)
+    check_case("DistMult", 777, 5, 20, 10.0, 40, 24, 3, dev, reg=1e-3)
     check_eval(dev)
     check_full_size(dev)
     dist.barrier()

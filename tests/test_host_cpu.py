@@ -188,6 +188,50 @@ for k in ("entity_embedding", "relation_embedding"):
     mineT = torch.from_numpy(mine[k].copy()); other = mineT.clone()
     dist.broadcast(other, src=0)
     assert torch.equal(mineT, other), "replicas differ"                      # bit-identical on every rank
+# the entity-sharded optimizer (kge_train_rows_sharded / kge_train_entity_sharded), restated over gloo at the level of
+# its ownership rules: rank r alone sums the gradient rows of ITS entity range over all ranks' row shards, runs Adam there
+# with moments nobody else keeps, and its rows reach every replica; the relation table goes through the region scheme.
+from knowledgegraphembedding_b200.peer import entity_ranges, gather_moment_ranges, moment_ranges
+mine = {k: v.copy() for k, v in st.items()}
+ref = O.TrainState("RotatE", st, gamma, d)
+De = 2 * d
+own = entity_ranges(nentity, De, world)
+nE_, nR_ = mine["entity_embedding"].size, mine["relation_embedding"].size
+small = moment_ranges([0], [nR_], [(0, nR_ // 4)], world)
+mE, vE = np.zeros(nE_, np.float32), np.zeros(nE_, np.float32)
+mR, vR = np.zeros(nR_, np.float32), np.zeros(nR_, np.float32)
+for step in (1, 2):
+    rng2 = np.random.RandomState(200 + step)
+    pos = np.stack([rng2.randint(nentity, size=B), rng2.randint(nrel, size=B), rng2.randint(nentity, size=B)], 1)
+    neg = rng2.randint(nentity, size=(B, N)); w = (rng2.rand(B) + 0.1).astype(np.float32)
+    O.train_step(ref, (pos, neg, w, "head-batch"), lr=lr, adversarial=True, alpha=1.0)
+    neg_s = O.forward("RotatE", mine, (pos, neg), "head-batch", gamma, d); pos_s = O.forward("RotatE", mine, pos, "single", gamma, d)
+    _, _, _, dneg, dpos = O.loss_and_dscore(neg_s, pos_s, w, True, 1.0, False)
+    b, e = shard_bounds(B, rank, world)
+    g1 = O.score_backward("RotatE", mine, (pos[b:e], neg[b:e]), "head-batch", dneg[b:e], gamma, d)
+    g2 = O.score_backward("RotatE", mine, pos[b:e], "single", dpos[b:e], gamma, d)
+    for name, ranges, mm, vv in (("entity_embedding", own, mE, vE), ("relation_embedding", small[0], mR, vR)):
+        part = torch.from_numpy((g1[name] + g2[name]).astype(np.float32).ravel())
+        gathered = [torch.zeros_like(part) for _ in range(world)]
+        dist.all_gather(gathered, part)                     # stand-in for the rows the owner reads from its gather area
+        flat = mine[name].reshape(-1)
+        new = torch.from_numpy(flat.copy())
+        for r, a, b_ in ranges:
+            if r == rank:
+                g = gathered[0].numpy()[a:b_].copy()
+                for q in range(1, world):
+                    g = g + gathered[q].numpy()[a:b_]
+                O.adam_update(flat[a:b_], g, mm[a:b_], vv[a:b_], step, lr)
+                new[a:b_] = torch.from_numpy(flat[a:b_])
+        for r, a, b_ in ranges:
+            dist.broadcast(new[a:b_], src=r)                # the owner's NVLink stores into every replica
+        flat[...] = new.numpy()
+for k in ("entity_embedding", "relation_embedding"):
+    assert np.max(np.abs(mine[k] - ref.state[k])) <= 1e-5 * np.max(np.abs(ref.state[k])) + 2 * lr * 1e-3, k
+pairs = [(torch.from_numpy(mE), torch.from_numpy(vE)), (torch.from_numpy(mR), torch.from_numpy(vR))]
+gather_moment_ranges(pairs, (own,) + small)
+assert np.max(np.abs(mE - ref.adam["entity_embedding"]["m"].ravel())) <= 1e-6
+assert np.max(np.abs(vR - ref.adam["relation_embedding"]["v"].ravel())) <= 1e-6
 dist.destroy_process_group()
 print("ok")
 """
@@ -227,6 +271,48 @@ def test_peer_exchange_region_arithmetic():
                 assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
                 sizes = [b - a for a, b in sl]
                 assert max(sizes) - min(sizes) <= 1
+
+
+def test_entity_ownership_matches_the_kernels_rule():
+    """peer.entity_ranges (host: who keeps which Adam moments) against the device rule of Mirror / owner_of
+    (csrc/kge_train_args.cuh): base = nentity / G, the first nentity % G ranks own one row more."""
+    from knowledgegraphembedding_b200.peer import entity_ranges
+    from knowledgegraphembedding_b200.model import shard_bounds
+
+    def owner_of(i, base, rem):                            # restatement of the device function
+        cut = rem * (base + 1)
+        return i // (base + 1) if i < cut else rem + (i - cut) // base
+
+    for nentity, world, De in ((14951, 8, 2000), (14951, 2, 2000), (123182, 8, 1000), (40943, 4, 1000), (9, 8, 4), (8, 8, 4)):
+        base, rem = divmod(nentity, world)
+        rs = entity_ranges(nentity, De, world)
+        assert rs[0][1] == 0 and rs[-1][2] == nentity * De and all(a[2] == b[1] for a, b in zip(rs, rs[1:]))
+        for r, a, b in rs:
+            assert (a // De, b // De) == shard_bounds(nentity, r, world)
+            for i in {a // De, b // De - 1, (a // De + b // De) // 2}:
+                assert owner_of(i, base, rem) == r
+
+
+def test_shard_abi_argument_errors_without_a_gpu():
+    import ctypes
+    from knowledgegraphembedding_b200 import _lib
+    lib = _lib.load()
+    m = _lib.KgeModelStruct(model=_lib.ROTATE, device=0, nentity=100, nrelation=5, hidden_dim=8, entity_dim=16,
+                            relation_dim=8, gamma=6.0, embedding_range=1.0, entity=4096, relation=8192, modulus=None)
+    assert lib.kge_train_gather_bytes(ctypes.byref(m), 2, 8, 16) >= 2 * 8 * (16 * 4 * 2 + 16 * 4 * 4 + 12)
+    assert lib.kge_train_shard_workspace_bytes(ctypes.byref(m), 2, 8, 16) >= 2 * 8 * 19 * 8
+    sh = _lib.KgeShard(world=1, rank=0)
+    rc = lib.kge_train_rows_sharded(ctypes.byref(m), _lib.TAIL_BATCH, 0, 1.0, None, None, None, None, 8, 4, 16, None, None,
+                                    None, None, ctypes.byref(sh), None, None)
+    assert rc == _lib.ERR_INVALID and b"bad shard description" in lib.kge_last_error()
+    sh = _lib.KgeShard(world=2, rank=0, block_bytes=1 << 20, gather_offset=256, rows_max=4)
+    sh.block[0], sh.block[1] = 1 << 30, 1 << 31
+    rc = lib.kge_train_rows_sharded(ctypes.byref(m), _lib.TAIL_BATCH, 0, 1.0, None, None, None, None, 8, 4, 16, None, None,
+                                    None, None, ctypes.byref(sh), None, None)
+    assert rc == _lib.ERR_INVALID and b"entity table must live inside the local peer block" in lib.kge_last_error()
+    grp = _lib.KgePeerGroup(world=2, rank=0)
+    rc = lib.kge_peer_barrier(ctypes.byref(grp), 0, 1, 0, None, None)
+    assert rc == _lib.ERR_INVALID and b"channels 2 and 3" in lib.kge_last_error()
 
 
 def test_peer_abi_argument_errors_without_a_gpu():
