@@ -311,8 +311,9 @@ int kge_peer_reduce_adam(const kge_peer_group_t *host_group, uint32_t epoch, con
  *   1. kge_train_rows_sharded: the single-read row kernel over this rank's positive rows.  Its outputs -- query vectors,
  *      dL/ds, candidate ids, target ids of the positives' gradient rows -- are stored into section `rank` of EVERY block
  *      with NVLink stores straight from the kernel; each gradient row of a positive triple is stored only into the block
- *      of the rank that owns its target entity.  grad_relation / grad_modulus / row losses stay local (they go through
- *      kge_peer_reduce_adam as a small region).
+ *      of the rank that owns its target entity, and each pair adds one count to the histogram in its owner's block.
+ *      grad_relation / grad_modulus / row losses stay local (they go through kge_peer_reduce_adam as a small region).
+ *      aux_stream (may be NULL): a second stream on which the id mirror runs next to the row kernel.
  *   2. kge_peer_barrier(channel 2, exchange_err = 1): every rank's rows are in; a bad index anywhere raises everywhere.
  *   3. kge_train_entity_sharded: counting sort of the gathered pairs that hit the owned range, entity-major backward with
  *      the fused Adam update of kge_train_rows_adam on the owned rows, and the updated row is stored into every rank's
@@ -325,6 +326,8 @@ int kge_peer_reduce_adam(const kge_peer_group_t *host_group, uint32_t epoch, con
 typedef struct kge_shard {
   int32_t world, rank;
   void *block[KGE_PEER_MAX_RANKS];     /* base of every rank's peer block as mapped in this process; [rank] is local */
+  void *multicast;                     /* NVSwitch multicast mapping of the blocks (address of block base; one
+                                          multimem.st writes every replica), or NULL: one NVLink store per peer      */
   int64_t block_bytes;                 /* size of each block                                                         */
   int64_t gather_offset;               /* byte offset (multiple of 256) of the gather area inside each block         */
   int64_t rows_max;                    /* row capacity per rank of the gather area                                   */
@@ -337,14 +340,15 @@ int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_kind, float 
                            const int64_t *positive, const int64_t *negative, const float *weight,
                            const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N, float *row_loss,
                            float *pos_row_loss, float *grad_relation, float *grad_modulus,
-                           const kge_shard_t *host_shard, int32_t *err_flag, void *stream);
+                           const kge_shard_t *host_shard, int32_t *err_flag, void *stream, void *aux_stream);
 int kge_train_entity_sharded(const kge_model_t *m, int mode, int64_t N, const kge_shard_t *host_shard, void *workspace,
                              int64_t workspace_bytes, const kge_entity_adam_t *host_entity_adam, int32_t *err_flag,
                              void *stream);
 /* cross-GPU barrier on `stream` over the flag blocks of the group (channels 2 and 3; epoch = 1, 2, 3, ... per channel);
- * exchange_err != 0: a non-zero *err_flag on any rank becomes non-zero on every rank.  Bounded wait like
+ * exchange_err != 0: a non-zero *err_flag on any rank becomes non-zero on every rank.  phase 0 = arrive and wait; 1 =
+ * arrive only and 2 = wait only (same epoch), so that independent kernels can run between the two.  Bounded wait like
  * kge_peer_reduce_adam (err_flag := 2).  The flag block must hold 8 * KGE_PEER_MAX_RANKS uint32.               */
-int kge_peer_barrier(const kge_peer_group_t *host_group, int channel, uint32_t epoch, int exchange_err,
+int kge_peer_barrier(const kge_peer_group_t *host_group, int channel, uint32_t epoch, int exchange_err, int phase,
                      int32_t *err_flag, void *stream);
 
 #ifdef __cplusplus

@@ -43,7 +43,8 @@ class KgePeerGroup(Structure):
 
 
 class KgeShard(Structure):
-    _fields_ = [("world", c_int32), ("rank", c_int32), ("block", c_void_p * PEER_MAX_RANKS), ("block_bytes", c_int64),
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("block", c_void_p * PEER_MAX_RANKS), ("multicast", c_void_p),
+                ("block_bytes", c_int64),
                 ("gather_offset", c_int64), ("rows_max", c_int64), ("rows_of", c_int32 * PEER_MAX_RANKS)]
 
 
@@ -106,10 +107,10 @@ PROTOTYPES = {
     "kge_train_shard_workspace_bytes": (c_int64, [_M, c_int, c_int64, c_int64]),
     "kge_train_rows_sharded": (c_int, [_M, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                        c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(KgeShard),
-                                       c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p]),
     "kge_train_entity_sharded": (c_int, [_M, c_int, c_int64, POINTER(KgeShard), c_void_p, c_int64,
                                          POINTER(KgeEntityAdam), c_void_p, c_void_p]),
-    "kge_peer_barrier": (c_int, [POINTER(KgePeerGroup), c_int, ctypes.c_uint32, c_int, c_void_p, c_void_p]),
+    "kge_peer_barrier": (c_int, [POINTER(KgePeerGroup), c_int, ctypes.c_uint32, c_int, c_int, c_void_p, c_void_p]),
     "kge_l3_partials": (c_int, [POINTER(KgeAdamTensor), c_int, c_void_p, c_int64, c_void_p]),
     "kge_eval_filter_bits_lookup": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64,
                                             c_int64, c_void_p, c_void_p]),

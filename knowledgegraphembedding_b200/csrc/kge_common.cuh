@@ -134,6 +134,16 @@ __device__ __forceinline__ void st4_hint(float *p, float4 v, uint64_t pol) {
                : "memory");
 }
 
+// ---- NVSwitch multicast stores (NVLS): one store writes the same address in every rank's replica of a multicast-mapped
+// allocation (the local one included) ----------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st_b32(void *mc, uint32_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_v4(float *mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // ---- packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two IEEE-rn operations ------------
 struct f2 { unsigned long long v; };
 __device__ __forceinline__ f2 pack2(float lo, float hi) {

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_finish_kernel(const PeerArg
 struct BarrierArgs {
   uint32_t *flags[PEER_MAX];
   int world, rank, channel, exchange_err;
+  int phase;                       // 0: arrive and wait, 1: arrive only, 2: wait only (for an arrival published earlier)
   uint32_t epoch;
   int32_t *err;
   unsigned long long timeout_ns;
@@ -270,13 +271,16 @@ struct BarrierArgs {
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const BarrierArgs a) {
   const int t = threadIdx.x;
   if (t >= a.world) return;
-  if (a.exchange_err) {
-    const uint32_t mine = a.err ? (uint32_t)*reinterpret_cast<volatile int32_t *>(a.err) : 0u;
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + (a.channel + 4) * PEER_MAX + a.rank), "r"(mine)
-                 : "memory");
+  if (a.phase != 2) {
+    if (a.exchange_err) {
+      const uint32_t mine = a.err ? (uint32_t)*reinterpret_cast<volatile int32_t *>(a.err) : 0u;
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + (a.channel + 4) * PEER_MAX + a.rank), "r"(mine)
+                   : "memory");
+    }
+    __threadfence_system();
+    st_release_sys(a.flags[t] + a.channel * PEER_MAX + a.rank, a.epoch);
   }
-  __threadfence_system();
-  st_release_sys(a.flags[t] + a.channel * PEER_MAX + a.rank, a.epoch);
+  if (a.phase == 1) return;
   const uint32_t *f = a.flags[a.rank] + a.channel * PEER_MAX + t;
   const unsigned long long t0 = global_ns();
   bool ok = true;
@@ -306,13 +310,15 @@ static unsigned long long peer_timeout_ns() {
 
 using namespace kge;
 
-extern "C" int kge_peer_barrier(const kge_peer_group_t *grp, int channel, uint32_t epoch, int exchange_err,
+extern "C" int kge_peer_barrier(const kge_peer_group_t *grp, int channel, uint32_t epoch, int exchange_err, int phase,
                                 int32_t *err_flag, void *stream) {
   KGE_REQUIRE(grp && grp->world >= 2 && grp->world <= PEER_MAX && grp->rank >= 0 && grp->rank < grp->world,
               "bad peer group");
   KGE_REQUIRE(channel >= 2 && channel <= 3, "barrier channels 2 and 3 are free (0 and 1 belong to kge_peer_reduce_adam)");
   BarrierArgs a{};
+  KGE_REQUIRE(phase >= 0 && phase <= 2, "phase: 0 = arrive + wait, 1 = arrive, 2 = wait");
   a.world = grp->world; a.rank = grp->rank; a.channel = channel; a.exchange_err = exchange_err; a.epoch = epoch;
+  a.phase = phase;
   a.err = err_flag; a.timeout_ns = peer_timeout_ns();
   for (int r = 0; r < grp->world; ++r) {
     KGE_REQUIRE(grp->flags[r], "peer %d is not mapped", r);

@@ -102,10 +102,12 @@ __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t c
 // ---- entity-sharded multi-GPU step: the owner of an entity range sorts the pairs gathered from ALL ranks ----------
 // Gather area of every rank's peer block (identical layout; R = row capacity per rank, section s is written by rank s):
 //   ids [G][R][N] int32 candidate ids | Gs [G][R][N] dL/ds | Qtab [G][R][De] query vectors |
-//   Dvec [G][3R][De] gradient rows of the positive triples (a row is present only in its owner's block) | dids [G][3R]
-struct GatherLayout { size_t ids, Gs, Qtab, Dvec, dids, total; };
+//   Dvec [G][3R][De] gradient rows of the positive triples (a row is present only in its owner's block) | dids [G][3R] |
+//   hist [nentity] this rank's pairs per entity (all entities; local atomics of its row kernel): the owner of an entity
+//   range sums the G histograms of that range with NVLink loads
+struct GatherLayout { size_t ids, Gs, Qtab, Dvec, dids, hist, total; };
 static size_t align256(size_t x);
-static GatherLayout gather_layout(int world, int64_t R, int64_t N, int64_t De) {
+static GatherLayout gather_layout(int world, int64_t R, int64_t N, int64_t De, int64_t nentity) {
   GatherLayout g;
   size_t o = 0;
   g.ids = o;  o += align256((size_t)world * R * N * 4);
@@ -113,6 +115,7 @@ static GatherLayout gather_layout(int world, int64_t R, int64_t N, int64_t De) {
   g.Qtab = o; o += align256((size_t)world * R * De * 4);
   g.Dvec = o; o += align256((size_t)world * 3 * R * De * 4);
   g.dids = o; o += align256((size_t)world * 3 * R * 4);
+  g.hist = o; o += align256((size_t)nentity * 4);
   g.total = o;
   return g;
 }
@@ -136,31 +139,63 @@ __global__ void push_ids_kernel(const int64_t *__restrict__ neg, int64_t n, int6
   }
 }
 
-// PLACE = false: histogram of the gathered pairs and direct rows whose entity lies in [eb, ee);
-// PLACE = true: scatter them (perm = gathered row index s * R + rl, or -(1 + gathered direct index))
-template <bool PLACE>
-__global__ void gathered_pairs_kernel(const GatherArgs g, int *__restrict__ cnt_or_cursor, int *__restrict__ perm,
-                                      float *__restrict__ gsorted) {
-  const int64_t per = (int64_t)g.R * g.N, pairs = per * g.world, dper = 3ll * g.R, total = pairs + dper * g.world;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    int id, row;
-    float gv = 0.f;
-    if (p < pairs) {
-      const int s = (int)(p / per), rl = (int)((p % per) / g.N);
-      if (rl >= g.rows_of[s]) continue;
-      id = g.ids[p];
-      row = s * g.R + rl;
-      if (PLACE) gv = g.Gs[p];
-    } else {
-      const int64_t i = p - pairs;
-      const int s = (int)(i / dper), j = (int)(i % dper);
-      if (j / 3 >= g.rows_of[s]) continue;
-      id = g.dids[i];
-      row = -(1 + (int)i);
+// scan_tiles_kernel over the sum of all ranks' histograms, restricted to the owned entity range
+__global__ void __launch_bounds__(1024) scan_tiles_gathered_kernel(const int *hist, const Mirror mir, int eb, int ee,
+                                                                   int *__restrict__ cursor, int *__restrict__ tile_tot,
+                                                                   int64_t n) {
+  __shared__ int warp_tot[32];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int v = 0;
+  if (i >= eb && i < ee) {
+    for (int r = 0; r < mir.world; ++r) {
+      int x;
+      asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(x) : "l"(at_rank(mir, hist + i, r)) : "memory");
+      v += x;
     }
+  }
+  int total;
+  const int excl = block_exclusive_scan_1024(v, warp_tot, total);
+  if (i < n) cursor[i] = excl;
+  if (threadIdx.x == 0) tile_tot[blockIdx.x] = total;
+}
+
+// Scatter of the gathered pairs and direct rows whose entity lies in the owned range [eb, ee): perm = gathered row index
+// s * R + rl, or -(1 + gathered direct index).  blockIdx.y = source rank; VEC ids (one 16-byte load) per thread and trip.
+template <int VEC>
+__global__ void gathered_scatter_kernel(const GatherArgs g, int *__restrict__ cursor, int *__restrict__ perm,
+                                        float *__restrict__ gsorted) {
+  const int s = blockIdx.y, rows = g.rows_of[s];
+  const int n = rows * g.N;                                // (world * R * (N + 3) < 2^31 is checked by the host)
+  const size_t base = (size_t)s * g.R * g.N;
+  const int stride = gridDim.x * blockDim.x * VEC;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < n; i += stride) {
+    int id[VEC];
+    float gv[VEC];
+    if constexpr (VEC == 4) {
+      const int4 a = *reinterpret_cast<const int4 *>(g.ids + base + i);
+      const float4 b = *reinterpret_cast<const float4 *>(g.Gs + base + i);
+      id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w;
+      gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+    } else {
+      id[0] = g.ids[base + i];
+      gv[0] = g.Gs[base + i];
+    }
+    const int row = s * g.R + i / g.N;                     // VEC == 4: N % 4 == 0, the four pairs share their row
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (id[v] < g.eb || id[v] >= g.ee) continue;
+      const int pos = atomicAdd(cursor + id[v], 1);
+      perm[pos] = row;
+      gsorted[pos] = gv[v];
+    }
+  }
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < 3 * rows; j += gridDim.x * blockDim.x) {
+    const int i = s * 3 * g.R + j;
+    const int id = g.dids[i];
     if (id < g.eb || id >= g.ee) continue;
-    const int pos = atomicAdd(cnt_or_cursor + id, 1);
-    if (PLACE) { perm[pos] = row; gsorted[pos] = gv; }
+    const int pos = atomicAdd(cursor + id, 1);
+    perm[pos] = -(1 + i);
+    gsorted[pos] = 0.f;
   }
 }
 
@@ -479,7 +514,7 @@ static int shard_mirror(const kge_model_t *m, const kge_shard_t *sh, int64_t N, 
               "bad shard description");
   KGE_REQUIRE(sh->rows_max >= 1 && m->nentity >= sh->world && m->nentity < (1ll << 31), "bad shard shape");
   KGE_REQUIRE(sh->world * sh->rows_max * (N + 3) < (1ll << 31), "too many pairs for 32-bit sort positions");
-  L = gather_layout(sh->world, sh->rows_max, N, m->entity_dim);
+  L = gather_layout(sh->world, sh->rows_max, N, m->entity_dim, m->nentity);
   KGE_REQUIRE(sh->gather_offset >= 0 && sh->gather_offset % 256 == 0 &&
                   (size_t)sh->gather_offset + L.total <= (size_t)sh->block_bytes,
               "gather area does not fit the peer block");
@@ -494,12 +529,16 @@ static int shard_mirror(const kge_model_t *m, const kge_shard_t *sh, int64_t N, 
     KGE_REQUIRE(sh->block[r] && sh->rows_of[r] >= 0 && sh->rows_of[r] <= sh->rows_max, "bad shard entry %d", r);
     mir.delta[r] = (long long)((const char *)sh->block[r] - base);
   }
+  if (sh->multicast) {
+    KGE_REQUIRE(((uintptr_t)sh->multicast & 15) == 0 && ((uintptr_t)base & 15) == 0, "multicast mapping is not 16-byte aligned");
+    mir.mc_delta = (long long)((const char *)sh->multicast - base);
+  }
   return KGE_OK;
 }
 
 extern "C" int64_t kge_train_gather_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N) {
   if (!m || world < 1 || rows_max < 1 || N < 1) return 0;
-  return (int64_t)gather_layout(world, rows_max, N, m->entity_dim).total;
+  return (int64_t)gather_layout(world, rows_max, N, m->entity_dim, m->nentity).total;
 }
 
 extern "C" int64_t kge_train_shard_workspace_bytes(const kge_model_t *m, int world, int64_t rows_max, int64_t N) {
@@ -512,7 +551,7 @@ extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_k
                                       const int64_t *positive, const int64_t *negative, const float *weight,
                                       const float *weight_sum, int64_t B_total, int64_t row_count, int64_t N,
                                       float *row_loss, float *pos_row_loss, float *grad_relation, float *grad_modulus,
-                                      const kge_shard_t *host_shard, int32_t *err_flag, void *stream) {
+                                      const kge_shard_t *host_shard, int32_t *err_flag, void *stream, void *aux_stream) {
   int rc = check_model(m);
   if (rc) return rc;
   KGE_REQUIRE(loss_kind == KGE_LOSS_NEG_ADVERSARIAL || loss_kind == KGE_LOSS_NEG_UNIFORM, "bad loss_kind %d", loss_kind);
@@ -533,18 +572,34 @@ extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_k
   cudaStream_t st = (cudaStream_t)stream;
   char *g = (char *)sh.block[sh.rank] + sh.gather_offset;
   const int64_t R = sh.rows_max, De = m->entity_dim;
+  // the id mirror is independent of the row kernel: with an auxiliary stream it runs next to it (joined at the end)
+  cudaStream_t aux = aux_stream ? (cudaStream_t)aux_stream : st;
+  static thread_local cudaEvent_t fork_ev[16] = {}, join_ev[16] = {};
+  const int dv = m->device & 15;
+  if (aux != st) {
+    if (!fork_ev[dv]) {
+      KGE_CUDA_OK(cudaEventCreateWithFlags(&fork_ev[dv], cudaEventDisableTiming));
+      KGE_CUDA_OK(cudaEventCreateWithFlags(&join_ev[dv], cudaEventDisableTiming));
+    }
+    KGE_CUDA_OK(cudaEventRecord(fork_ev[dv], st));
+    KGE_CUDA_OK(cudaStreamWaitEvent(aux, fork_ev[dv], 0));
+  }
   {
     const int64_t n = row_count * N;
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    push_ids_kernel<<<grid, 256, 0, st>>>(negative, n, m->nentity, (int *)(g + L.ids) + (size_t)sh.rank * R * N, mir, err_flag);
+    push_ids_kernel<<<grid, 256, 0, aux>>>(negative, n, m->nentity, (int *)(g + L.ids) + (size_t)sh.rank * R * N, mir,
+                                           err_flag);
     KGE_CUDA_OK(cudaGetLastError());
   }
+  if (aux != st) KGE_CUDA_OK(cudaEventRecord(join_ev[dv], aux));
   SplitWs ws{};
   ws.G = (float *)(g + L.Gs) + (size_t)sh.rank * R * N;
   ws.Qtab = (float *)(g + L.Qtab) + (size_t)sh.rank * R * De;
   ws.Dvec = (float *)(g + L.Dvec) + (size_t)sh.rank * 3 * R * De;
   ws.dids = (int *)(g + L.dids) + (size_t)sh.rank * 3 * R;
+  ws.cnt = (int *)(g + L.hist);                            // this rank's histogram; the owners read their ranges of it
+  KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, (size_t)m->nentity * 4, st));   // (every peer's scan of the last step is done)
   RowArgs a{};
   bool head;
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;
@@ -560,6 +615,7 @@ extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_k
   a.mir = mir;
   a.shard_ws = &ws;
   rc = launch_rows(m, head, a, st);
+  if (aux != st) KGE_CUDA_OK(cudaStreamWaitEvent(st, join_ev[dv], 0));
   if (rc) return rc;
   KGE_REQUIRE(deferred && fused_positive, "internal: the single-read row kernel did not run for the entity-sharded step");
   return KGE_OK;
@@ -596,7 +652,7 @@ extern "C" int kge_train_entity_sharded(const kge_model_t *m, int mode, int64_t 
   ws.gsorted = (float *)wp;
   ws.Qtab = (float *)(g + L.Qtab);
   ws.Dvec = (float *)(g + L.Dvec);
-  KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, ((size_t)(2 * nentity + 1) + 16) * 4, st));
+  KGE_CUDA_OK(cudaMemsetAsync(ws.queue, 0, 16 * 4, st));
   GatherArgs ga{};
   ga.ids = (const int *)(g + L.ids); ga.Gs = (const float *)(g + L.Gs); ga.dids = (const int *)(g + L.dids);
   ga.world = sh.world; ga.R = (int)R; ga.N = (int)N;
@@ -604,17 +660,21 @@ extern "C" int kge_train_entity_sharded(const kge_model_t *m, int mode, int64_t 
   ga.eb = sh.rank * mir.ent_base + (sh.rank < mir.ent_rem ? sh.rank : mir.ent_rem);
   ga.ee = ga.eb + mir.ent_base + (sh.rank < mir.ent_rem ? 1 : 0);
   {
-    const int64_t total = (int64_t)sh.world * R * (N + 3);
-    int g2 = (int)((total + 255) / 256);
-    if (g2 > 148 * 16) g2 = 148 * 16;
+    // every rank histogrammed its own pairs while its row kernel ran; the tile scan sums the G histograms of the owned
+    // range (NVLink loads) and treats every other entity as empty
+    const int *hist = (const int *)(g + L.hist);
     const int tiles = (int)((nentity + 1023) / 1024);
-    gathered_pairs_kernel<false><<<g2, 256, 0, st>>>(ga, ws.cnt, nullptr, nullptr);
-    KGE_CUDA_OK(cudaGetLastError());
-    scan_tiles_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, nentity);
+    scan_tiles_gathered_kernel<<<tiles, 1024, 0, st>>>(hist, mir, ga.eb, ga.ee, ws.cursor, ws.tile_tot, nentity);
     KGE_CUDA_OK(cudaGetLastError());
     scan_apply_kernel<<<tiles, 1024, 0, st>>>(ws.cnt, ws.cursor, ws.tile_tot, nentity);
     KGE_CUDA_OK(cudaGetLastError());
-    gathered_pairs_kernel<true><<<g2, 256, 0, st>>>(ga, ws.cursor, ws.perm, ws.gsorted);
+    const bool vec = N % 4 == 0;
+    const int64_t per = R * N / (vec ? 4 : 1);
+    int gx = (int)((per + 255) / 256);
+    if (gx > 148 * 16 / sh.world) gx = 148 * 16 / sh.world;
+    if (gx < 1) gx = 1;
+    if (vec) gathered_scatter_kernel<4><<<dim3(gx, sh.world), 256, 0, st>>>(ga, ws.cursor, ws.perm, ws.gsorted);
+    else gathered_scatter_kernel<1><<<dim3(gx, sh.world), 256, 0, st>>>(ga, ws.cursor, ws.perm, ws.gsorted);
     KGE_CUDA_OK(cudaGetLastError());
   }
   const kge_entity_adam_t &o = *host_entity_adam;

@@ -23,6 +23,8 @@ struct Mirror {
   int world, rank;
   int ent_base, ent_rem;                   // balanced contiguous entity ranges: the first `rem` ranks own base + 1 rows
   long long delta[KGE_PEER_MAX_RANKS];
+  long long mc_delta;                      // != 0: byte distance to the NVSwitch multicast mapping of the blocks -- one
+                                           // multimem.st replaces the local store and the world - 1 peer stores
 };
 
 struct SplitWs;
@@ -67,12 +69,19 @@ __device__ __forceinline__ int owner_of(const Mirror &m, int64_t id) {
 }
 template <typename T>
 __device__ __forceinline__ T *at_rank(const Mirror &m, T *p, int r) {
-  return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + m.delta[r]);
+  return reinterpret_cast<T *>(reinterpret_cast<uintptr_t>(p) + m.delta[r]);
 }
 // store to the local block and to the same place in every peer's block (plain stores: the cross-GPU barrier that
 // follows the kernel fences them at system scope)
 template <typename T>
 __device__ __forceinline__ void store_all(const Mirror &m, T *p, T v) {
+  static_assert(sizeof(T) == 4, "store_all moves 32-bit values");
+  if (m.mc_delta) {
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    multimem_st_b32(reinterpret_cast<char *>(p) + m.mc_delta, bits);
+    return;
+  }
   *p = v;
   for (int r = 0; r < m.world; ++r)
     if (r != m.rank) *at_rank(m, p, r) = v;
@@ -82,8 +91,8 @@ __device__ __forceinline__ void store_all(const Mirror &m, T *p, T v) {
 struct SplitWs {             // carved from the caller's workspace
   float *G;                  // [rows, N]   dL/ds of every negative pair
   float *Qtab;               // [rows, De]  query vectors
-  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets (NULL in the row kernel of the entity-sharded
-                             //             step: the owner histograms the gathered pairs itself)
+  int *cnt;                  // [nentity + 1] histogram -> exclusive offsets (row kernel of the entity-sharded step: this
+                             //             rank's peer-visible histogram, which the owners read over NVLink)
   int *cursor;               // [nentity]   scatter cursors
   int *queue;                // [16]        dynamic entity queues of entity_kernel (one per entity slice)
   int *tile_tot;             // [ceil(nentity / 1024)] totals of the scan tiles

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
       if (lane == 0 && hw == 0) {
-        if (ws.cnt) atomicAdd(ws.cnt + id, 1);            // histogram for the entity-major pass
+        atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
         uint64_t *bar = gbars + s;
         float *dst = slots + (size_t)s * HS;
         const float *src = a.E + id * a.De;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
       if (ws.Dvec && tid < 3) {                             // direct entries of this row: (fixed, head, tail)
         const int64_t target = tid == 0 ? fid : (tid == 1 ? ph : pt);
         store_all(a.mir, ws.dids + 3 * rl + tid, (int)target);
-        if (ws.cnt) atomicAdd(ws.cnt + target, 1);
+        atomicAdd(ws.cnt + target, 1);
       }
       const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
       // (tail-batch: q = fold(h, r) is the q of the negatives, still in shared memory, unless an id was out of range)
@@ -858,8 +858,13 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
             adam_pair_fast(p23, acc[c][h][1], m23, v23, a.adam, l3, racc);
             float t0, t1, t2, t3;
             unpack2(p01, t0, t1); unpack2(p23, t2, t3);
-            st4_hint(a.E + hb + u * V, make_float4(t0, t1, t2, t3), pol_e);
-            if (a.mir.world > 1) {                          // owner computes, every replica takes the same bits (NVLink stores)
+            // entity-sharded multi-GPU step: owner computes, every replica takes the same bits -- one multicast store
+            // through the NVSwitch, or the local store plus one NVLink store per peer
+            if (a.mir.mc_delta) {
+              multimem_st_v4(reinterpret_cast<float *>(reinterpret_cast<char *>(a.E + hb + u * V) + a.mir.mc_delta),
+                             make_float4(t0, t1, t2, t3));
+            } else {
+              st4_hint(a.E + hb + u * V, make_float4(t0, t1, t2, t3), pol_e);
               for (int r = 0; r < a.mir.world; ++r)
                 if (r != a.mir.rank) *reinterpret_cast<float4 *>(at_rank(a.mir, a.E + hb + u * V, r)) = make_float4(t0, t1, t2, t3);
             }

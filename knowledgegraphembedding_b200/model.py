@@ -447,84 +447,95 @@ class KGEModel(nn.Module):
                             alpha, reg, st):
         """One train step with the entity-sharded optimizer (see include/kge_b200.h): row kernel with mirrored outputs ->
         barrier -> owner's sort + entity-major backward + fused Adam with NVLink parameter stores; the relation table
-        (and modulus) and the loss rows go through the small dense exchange; barrier.  Returns the loss buffer."""
+        (and modulus) and the loss rows go through the small dense exchange on a second stream; barrier.  Returns the
+        loss buffer.  Everything that does not change from step to step is cached per batch size, and the optimizer
+        bookkeeping runs on the host while the row kernel is already in flight."""
         model = self
         dev = held['dev']
         peer = held['peer']
-        rank, world = peer.rank, peer.world
+        world = peer.world
         E, R = model.entity_embedding, model.relation_embedding
         err = model._err_flag()
         desc = model._own_descriptor()
-        nR = R.numel()
-        nR4 = (nR + 3) // 4 * 4
+        params = model._trainable()
         ws = held['views'].get(B)
         if ws is None:
+            from .peer import entity_ranges, moment_ranges
+            nR = R.numel()
+            nR4 = (nR + 3) // 4 * 4
             total = nR4 + 4 + 2 * B
             flat = peer.workspace[:total]
+            rows_of = [hi - lo for lo, hi in (shard_bounds(B, r, world) for r in range(world))]
+            has_mod = model.model_name == 'pRotatE'
+            small = moment_ranges([0] + ([nR4] if has_mod else []), [p.numel() for p in params[1:]], [(0, (nR4 + 4) // 4)], world)
             ws = held['views'][B] = {
-                'flat': flat, 'gR': flat[:nR].view_as(R), 'gM': flat[nR4:nR4 + 1].view(1, 1),
+                'flat': flat, 'gR': flat[:nR].view_as(R), 'gM': flat[nR4:nR4 + 1].view(1, 1) if has_mod else None,
                 'pos_row': flat[nR4 + 4:nR4 + 4 + B], 'neg_row': flat[nR4 + 4 + B:total], 'param_floats': nR4 + 4,
                 'rows_sum': model._buffer('rows_sum', 2 * B, torch.float32, dev)[:2 * B],
                 'wsum': model._buffer('wsum', 1, torch.float32, dev),
                 'reg': model._buffer('reg_partials', 148 * 8, torch.float64, dev),
-                'rows_of': [hi - lo for lo, hi in (shard_bounds(B, r, world) for r in range(world))],
+                'shard': peer.shard(held['gather_offset'], held['rows_cap'], rows_of),
+                'layout': (entity_ranges(model.nentity, model.entity_dim, world),) + small,
             }
+            ws['ptrs'] = {k: _ptr(ws[k]) for k in ('flat', 'gR', 'gM', 'wsum', 'reg')}
         out = model._ws['loss_out']
         events = model._ws.get('kernel_events')
         xevents = model._ws.get('exchange_events')
-        params = model._trainable()
-        gM = ws['gM'] if model.model_name == 'pRotatE' else None
-        grads = [None, ws['gR']] + ([gM] if gM is not None else [])
+        pt = ws['ptrs']
+        wsum_ptr = pt['wsum'] if weight is not None else None
 
-        from .peer import entity_ranges, moment_ranges
-        offsets = [0, 0] + ([nR4] if gM is not None else [])
-        small = moment_ranges(offsets[1:], [p.numel() for p in params[1:]], [(0, ws['param_floats'] // 4)], world)
-        model._own_moments(optimizer, (entity_ranges(model.nentity, model.entity_dim, world),) + small)
+        main = torch.cuda.current_stream(dev)
+        side = model._ws.get('exchange_stream')          # id mirror next to the row kernel; relation-table exchange next
+        if side is None:                                 # to the entity pass
+            side = model._ws['exchange_stream'] = torch.cuda.Stream(dev)
+        side_ptr = ctypes.c_void_p(side.cuda_stream)
+        # ---- launches that need nothing from the optimizer: the row kernel is in flight before the host bookkeeping ----
+        _lib.call("kge_zero", pt['flat'], ws['flat'].numel() * 4, st)
+        if weight is not None:
+            _lib.call("kge_weight_sum", _ptr(weight), B, pt['wsum'], st)
+        if reg != 0.0:               # value of the L3 term from the replicated tables, before any owner updates them
+            tensors = (_lib.KgeAdamTensor * 2)(_lib.KgeAdamTensor(E.data_ptr(), None, None, None, E.numel(), 1, 1),
+                                               _lib.KgeAdamTensor(R.data_ptr(), None, None, None, R.numel(), 1, 1))
+            _lib.call("kge_l3_partials", tensors, 2, pt['reg'], ws['reg'].numel(), st)
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _lib.call("kge_train_rows_sharded", ctypes.byref(desc), mode_id, loss_kind, alpha, _ptr(positive), _ptr(negative),
+                  _ptr(weight[row_begin:]) if weight is not None else None, wsum_ptr, B, rows, N,
+                  _ptr(ws['neg_row'][row_begin:]), _ptr(ws['pos_row'][row_begin:]), pt['gR'], pt['gM'],
+                  ctypes.byref(ws['shard']), _ptr(err), st, side_ptr)
+        peer.barrier(2, err, st, exchange_err=True)      # every rank's rows are in every block; errors are shared
+
+        # ---- torch.optim.Adam bookkeeping (host only; state created lazily exactly like torch/optim/adam.py) ----------
+        model._own_moments(optimizer, ws['layout'])
         model._ws['exchange_regions'] = 1
-
         group = optimizer.param_groups[0]
         hyper = (float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']))
+        grads = [None, ws['gR'], ws['gM']]
         entries = []
-        for i, (p, g) in enumerate(zip(params, grads)):
+        for i, p in enumerate(params):
             state = optimizer.state[p]
             if len(state) == 0:
                 state['step'] = torch.tensor(0.0, dtype=torch.float32)
                 state['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             state['step'] += 1
+            g = grads[i]
             entries.append((p.data_ptr(), g.data_ptr() if g is not None else None, state['exp_avg'].data_ptr(),
                             state['exp_avg_sq'].data_ptr(), p.numel(), int(state['step'].item()),
                             1 if (reg != 0.0 and i < 2) else 0))
 
-        _lib.call("kge_zero", _ptr(ws['flat']), ws['flat'].numel() * 4, st)
-        if weight is not None:
-            _lib.call("kge_weight_sum", _ptr(weight), B, _ptr(ws['wsum']), st)
-        if reg != 0.0:               # value of the L3 term from the replicated tables, before any owner updates them
-            tensors = (_lib.KgeAdamTensor * 2)(*[_lib.KgeAdamTensor(*c) for c in entries[:2]])
-            _lib.call("kge_l3_partials", tensors, 2, _ptr(ws['reg']), ws['reg'].numel(), st)
-        shard = peer.shard(held['gather_offset'], held['rows_cap'], ws['rows_of'])
-        if events is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        _lib.call("kge_train_rows_sharded", ctypes.byref(desc), mode_id, loss_kind, alpha, _ptr(positive), _ptr(negative),
-                  _ptr(weight[row_begin:]) if weight is not None else None,
-                  _ptr(ws['wsum']) if weight is not None else None, B, rows, N, _ptr(ws['neg_row'][row_begin:]),
-                  _ptr(ws['pos_row'][row_begin:]), _ptr(ws['gR']), _ptr(gM), ctypes.byref(shard), _ptr(err), st)
-        peer.barrier(2, err, st, exchange_err=True)      # every rank's rows are in every block; errors are shared
         # the relation table's (small, dense) exchange runs on a second stream under the owners' entity pass
-        main = torch.cuda.current_stream(dev)
-        side = model._ws.get('exchange_stream')
-        if side is None:
-            side = model._ws['exchange_stream'] = torch.cuda.Stream(dev)
         side.wait_stream(main)
         peer.reduce_adam(entries[1:], hyper, ws['param_floats'], (0, ws['param_floats'] // 4), ws['param_floats'], 2 * B,
-                         ws['rows_sum'], err, ctypes.c_void_p(side.cuda_stream), l3=reg)
+                         ws['rows_sum'], err, side_ptr, l3=reg)
         e0 = entries[0]
         ea = _lib.KgeEntityAdam(exp_avg=e0[2], exp_avg_sq=e0[3], step=e0[5], lr=hyper[0], beta1=hyper[1], beta2=hyper[2],
                                 eps=hyper[3], l3_coefficient=reg,
                                 reg_partials=held['reg_scratch'].data_ptr() if reg != 0.0 else None, n_reg_partials=148)
-        _lib.call("kge_train_entity_sharded", ctypes.byref(desc), mode_id, N, ctypes.byref(shard), _ptr(held['wsp']),
+        _lib.call("kge_train_entity_sharded", ctypes.byref(desc), mode_id, N, ctypes.byref(ws['shard']), _ptr(held['wsp']),
                   held['wbytes'], ctypes.byref(ea), _ptr(err), st)
+        peer.barrier(3, err, st, phase=1)                # my parameter stores are issued (arrival only)
         if events is not None:
             ev1.record()
             events.append((ev0, ev1))
@@ -532,16 +543,15 @@ class KGEModel(nn.Module):
             xev0, xev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             xev0.record()
         main.wait_stream(side)
-        peer.barrier(3, err, st)                         # every owner's parameter rows have landed in every table
+        _lib.call("kge_loss_finalize", _ptr(ws['rows_sum'][:B]), _ptr(ws['rows_sum'][B:]), _ptr(weight), wsum_ptr, B, reg,
+                  pt['reg'] if reg != 0.0 else None, ws['reg'].numel() if reg != 0.0 else 0, _ptr(out), st)
+        peer.barrier(3, err, st, phase=2)                # every owner's parameter rows have landed in every table
         if xevents is not None:
             xev1.record()
             xevents.append((xev0, xev1))
         for p in params:
             p.grad = None
         model._ws['update_cancelled_on_error'] = False
-        _lib.call("kge_loss_finalize", _ptr(ws['rows_sum'][:B]), _ptr(ws['rows_sum'][B:]), _ptr(weight),
-                  _ptr(ws['wsum']) if weight is not None else None, B, reg,
-                  _ptr(ws['reg']) if reg != 0.0 else None, ws['reg'].numel() if reg != 0.0 else 0, _ptr(out), st)
         return out
 
     @staticmethod

@@ -82,6 +82,7 @@ class PeerExchange:
         nbytes = self.extra_offset + self.extra_bytes if extra_bytes else FLAG_BYTES + 4 * self.capacity
         self.block_bytes = nbytes
         self._epochs = {}
+        self.mc_block = 0
         self._local = ctypes.c_void_p()
         self._mapped = []
         self._symm = None
@@ -93,7 +94,7 @@ class PeerExchange:
             ptrs, why = self._agree(self._try(self._init_symm, nbytes))
             errors += why
         if ptrs is None and want in ("auto", "ipc"):
-            self.multicast = 0
+            self.multicast = self.mc_block = 0
             ptrs, why = self._init_ipc(nbytes)
             errors += why
         if ptrs is None:
@@ -146,6 +147,7 @@ class PeerExchange:
         mc = int(getattr(handle, "multicast_ptr", 0) or 0)
         self._symm, self._block = handle, block
         self.multicast = mc + shift if mc else 0
+        self.mc_block = self.multicast                       # multicast address of the block base (entity-sharded step)
         self.workspace = block[FLAG_BYTES:FLAG_BYTES + 4 * self.capacity].view(torch.float32)
         return [p + shift for p in ptrs]
 
@@ -198,16 +200,21 @@ class PeerExchange:
                   ctypes.c_void_p(rows_out.data_ptr()) if row_floats else None, *hyper, float(l3),
                   ctypes.c_void_p(err.data_ptr()), stream)
 
-    def barrier(self, channel, err, stream, exchange_err=False):
-        """Cross-GPU barrier on `stream` (kge_peer_barrier; channel 2 or 3, every rank calls it in the same order)."""
-        epoch = self._epochs[channel] = self._epochs.get(channel, 0) + 1
-        _lib.call("kge_peer_barrier", ctypes.byref(self.struct), channel, epoch, 1 if exchange_err else 0,
-                  ctypes.c_void_p(err.data_ptr()) if err is not None else None, stream)
+    def barrier(self, channel, err, stream, exchange_err=False, phase=0):
+        """Cross-GPU barrier on `stream` (kge_peer_barrier; channel 2 or 3, every rank calls it in the same order).
+        phase 1 publishes the arrival only, a later phase 2 waits for everybody's."""
+        if phase != 2:
+            self._epochs[channel] = self._epochs.get(channel, 0) + 1
+        _lib.call("kge_peer_barrier", ctypes.byref(self.struct), channel, self._epochs[channel], 1 if exchange_err else 0,
+                  phase, ctypes.c_void_p(err.data_ptr()) if err is not None else None, stream)
 
     def shard(self, gather_offset, rows_max, rows_of):
         """kge_shard_t of the entity-sharded step for this group's blocks."""
         sh = _lib.KgeShard(world=self.world, rank=self.rank, block_bytes=self.block_bytes,
                            gather_offset=int(gather_offset), rows_max=int(rows_max))
+        # KGE_SHARD_MULTICAST=0|1: mirror through the NVSwitch multicast mapping (symmetric-memory backend only)
+        if self.mc_block and os.environ.get("KGE_SHARD_MULTICAST", "1") != "0":
+            sh.multicast = self.mc_block
         for r in range(self.world):
             sh.block[r] = self.block_ptrs[r]
             sh.rows_of[r] = int(rows_of[r])

@@ -113,9 +113,13 @@ def check_case(model, nentity, nrel, d, gamma, B, N, steps, dev, lr=1e-3, advers
                 (model, path, name, relinf(got, want))
             identical_on_all_ranks(getattr(m, name), f"{model}/{path}/{name}")
             mom = sd['state'][idx]
+            # free-running steps: the kinked models (|x|, |sin x|) amplify summation-order noise from the second step on
+            # (tests/test_gpu_fullshape.py::sync_state explains; same bound as the single-GPU fused-vs-dense test); the
+            # entity-sharded pass sums an entity's pairs in the order its atomic cursor hands out
+            mtol = 1e-4 if model in ("RotatE", "ComplEx", "DistMult") else 2e-3
             for key, okey in (("exp_avg", "m"), ("exp_avg_sq", "v")):
                 g, w = mom[key].cpu().numpy(), ref.adam[name][okey]
-                assert relinf(g, w) <= 1e-4, (model, path, name, key, relinf(g, w))
+                assert relinf(g, w) <= mtol, (model, path, name, key, relinf(g, w))
                 identical_on_all_ranks(mom[key], f"{model}/{path}/{name}/{key}")
         results[path] = {n: getattr(m, n).detach().clone() for n in names}
     os.environ.pop("KGE_PEER_DENSE", None)

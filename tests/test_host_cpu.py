@@ -303,15 +303,15 @@ def test_shard_abi_argument_errors_without_a_gpu():
     assert lib.kge_train_shard_workspace_bytes(ctypes.byref(m), 2, 8, 16) >= 2 * 8 * 19 * 8
     sh = _lib.KgeShard(world=1, rank=0)
     rc = lib.kge_train_rows_sharded(ctypes.byref(m), _lib.TAIL_BATCH, 0, 1.0, None, None, None, None, 8, 4, 16, None, None,
-                                    None, None, ctypes.byref(sh), None, None)
+                                    None, None, ctypes.byref(sh), None, None, None)
     assert rc == _lib.ERR_INVALID and b"bad shard description" in lib.kge_last_error()
     sh = _lib.KgeShard(world=2, rank=0, block_bytes=1 << 20, gather_offset=256, rows_max=4)
     sh.block[0], sh.block[1] = 1 << 30, 1 << 31
     rc = lib.kge_train_rows_sharded(ctypes.byref(m), _lib.TAIL_BATCH, 0, 1.0, None, None, None, None, 8, 4, 16, None, None,
-                                    None, None, ctypes.byref(sh), None, None)
+                                    None, None, ctypes.byref(sh), None, None, None)
     assert rc == _lib.ERR_INVALID and b"entity table must live inside the local peer block" in lib.kge_last_error()
     grp = _lib.KgePeerGroup(world=2, rank=0)
-    rc = lib.kge_peer_barrier(ctypes.byref(grp), 0, 1, 0, None, None)
+    rc = lib.kge_peer_barrier(ctypes.byref(grp), 0, 1, 0, 0, None, None)
     assert rc == _lib.ERR_INVALID and b"channels 2 and 3" in lib.kge_last_error()
 
 
