@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(1024) scan_tiles_gathered_kernel(const int *hi
   const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
   int v = 0;
   if (i >= eb && i < ee) {
-    for (int r = 0; r < mir.world; ++r) {
-      int x;
-      asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(x) : "l"(at_rank(mir, hist + i, r)) : "memory");
-      v += x;
-    }
+    int x[KGE_PEER_MAX_RANKS];                             // all peers' loads in flight together (one NVLink round trip)
+#pragma unroll
+    for (int r = 0; r < KGE_PEER_MAX_RANKS; ++r)
+      if (r < mir.world) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(x[r]) : "l"(at_rank(mir, hist + i, r)));
+#pragma unroll
+    for (int r = 0; r < KGE_PEER_MAX_RANKS; ++r)
+      if (r < mir.world) v += x[r];
   }
   int total;
   const int excl = block_exclusive_scan_1024(v, warp_tot, total);
@@ -259,7 +261,7 @@ static int launch_rows(const kge_model_t *m, bool head, RowArgs &a, cudaStream_t
   a.gamma = m->gamma;
   a.scale = phase_scale(m);
   if (a.row_count <= 0 || a.N <= 0) return KGE_OK;
-  const bool aligned = (((uintptr_t)m->entity | (uintptr_t)a.gE) & 15) == 0;
+  const bool aligned = (((uintptr_t)m->entity | (uintptr_t)a.gE | (uintptr_t)m->relation) & 15) == 0 && m->relation_dim % 4 == 0;
   const bool vec4 = aligned && (a.d % 4 == 0) && (m->entity_dim % 4 == 0);
   const int Dq = (int)m->entity_dim;
   size_t smem = sizeof(float) * (2 * (size_t)((Dq + 3) & ~3) + (a.do_loss ? 2 * (size_t)a.N : 0) + 32);
@@ -391,7 +393,7 @@ extern "C" int kge_train_rows(const kge_model_t *m, int mode, int loss_kind, flo
 static bool plan_split(const kge_model_t *m, int64_t rows, int64_t N, bool fused_adam) {
   const bool cplx = m->model == KGE_COMPLEX || m->model == KGE_ROTATE;
   const int64_t d = cplx ? m->entity_dim / 2 : m->entity_dim;
-  return ((uintptr_t)m->entity & 15) == 0 && N <= 8192 &&
+  return (((uintptr_t)m->entity | (uintptr_t)m->relation) & 15) == 0 && m->relation_dim % 4 == 0 && N <= 8192 &&
          split_path_shape_ok(rows, N, m->entity_dim, d, cplx, m->nentity, fused_adam);
 }
 

@@ -100,8 +100,9 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
       const int nch = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16);
       const int var = split_variant();
       const size_t hs = (size_t)Hs * 128 * nch;              // padded slot (floats)
+      // q, dq, rot, the score arrays, scratch, and the double-buffered stage of the positive triple's rows (+ its 2 mbarriers)
       const size_t fixed_s = sizeof(float) * (hs + (size_t)((a.De + 3) & ~3) + 2 * (size_t)((a.d + 3) & ~3) +
-                                              2 * (size_t)a.N + 32) + 16;
+                                              2 * (size_t)a.N + 32 + 2 * (2 * (size_t)a.De + (size_t)a.Dr)) + 16 + 16;
       // Ws = row groups per CTA (one warp each, or a pair of warps: variants 3 / 4); a group owns two slots, two
       // mbarriers and the pair's exchange words
       const int wpr = split_warps_per_row(var);

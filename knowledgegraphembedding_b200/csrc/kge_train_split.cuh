@@ -101,18 +101,26 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   // Every row group owns a ring of D = a.ring slots (2..4).  The gather is bound by the bytes in flight per SM against
   // the L2 / DRAM latency (B200, cfg 3: 16 slots of 8 KB per SM gave the same 0.33 ms with 8 warps at 255 registers and
   // with 16 warps at 128; 12 slots were slower), so the ring is as deep as the shared memory allows.
-  // layout: [slots: nwarps x D x HS | q: HS | dq: De | rot: 2 d | sc[N] | gg[N] | scratch(32) | mbarriers: nwarps x D |
-  //          pair exchange: nwarps x 4 | parking slot of each group: nwarps], all derived from `smem`
+  // layout: [slots: nwarps x D x HS | stage: 2 x (2 De + Dr) | q: HS | dq: De | rot: 2 d | sc[N] | gg[N] | scratch(32) |
+  //          stage mbarriers: 2 | ring mbarriers: nwarps x D | pair exchange: nwarps x 4 | parking slot of each group:
+  //          nwarps], all derived from `smem`.
+  // stage: the head, tail and relation rows of the row's positive triple (the fixed side is one of them), copied by the
+  // bulk engine one row AHEAD (double buffer), so that the block-wide phases -- query vector, chain rule, positive
+  // triple -- read shared memory instead of waiting on four dependent global-load round trips per row (phase counters
+  // r2k: 17 % of the kernel's cycles sat in those two phases).
   const int D = a.ring;
   float *slots = smem + (size_t)(D * warp) * HS;
-  float *q = smem + (size_t)(D * nwarps) * HS;
+  const int STG = 2 * a.De + a.Dr;                         // floats per stage buffer (multiple of 4: 16-byte copies)
+  float *stage = smem + (size_t)(D * nwarps) * HS;
+  float *q = stage + 2 * STG;
   float *dq = q + HS;                           // compact [d | d]
   float *rot = dq + Dq4;                        // [2][d4] cos / sin of the row's relation phases (RotatE)
   const int d4 = (a.d + 3) & ~3;
   float *sc = rot + 2 * d4;                     // [N]
   float *gg = sc + a.N;                         // [N]
   float *scratch = gg + a.N;                    // [32]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(scratch + 32);
+  uint64_t *sbars = reinterpret_cast<uint64_t *>(scratch + 32);    // [2] one per stage buffer
+  uint64_t *bars = sbars + 2;
   const uint32_t halfbytes = (uint32_t)a.d * 4u;
   uint64_t *gbars = bars + D * warp;                       // this group's mbarriers
   uint32_t par = 0;                                         // phase parity of every slot's mbarrier (bit s)
@@ -127,11 +135,13 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     const int padn = DP - a.d, nslots = D * nwarps + 1;
     for (int i = tid; i < nslots * H * padn; i += blockDim.x) {
       const int sl = i / (H * padn), r = i % (H * padn);
-      smem[(size_t)sl * HS + (r / padn) * DP + a.d + (r % padn)] = 0.f;
+      float *base = sl < D * nwarps ? smem + (size_t)sl * HS : q;          // (q does not follow the slots directly)
+      base[(r / padn) * DP + a.d + (r % padn)] = 0.f;
     }
   }
   if (lane == 0 && hw == 0)
     for (int k = 0; k < D; ++k) mbar_init(gbars + k, 1);
+  if (tid == 0) { mbar_init(sbars, 1); mbar_init(sbars + 1, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -148,18 +158,43 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   int64_t ids = 0, ids_nxt = 0, ids_next_row = 0;
   bool next_row_ready = false;
   int ids_base = -32;
-  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x) {
-    const int64_t b = a.row_begin + rl;
-    int64_t hid = a.positive[b * 3 + 0], rid = a.positive[b * 3 + 1], tidx = a.positive[b * 3 + 2];
-    int64_t fid = HEAD ? tidx : hid;
-    if ((uint64_t)fid >= (uint64_t)a.nentity || (uint64_t)rid >= (uint64_t)a.nrelation) {
+  // (head, relation, tail) of a row, clamped like every gather (the error flag cancels the update)
+  auto load_triple = [&](int64_t bb, int64_t &h, int64_t &r, int64_t &t) {
+    h = a.positive[bb * 3 + 0]; r = a.positive[bb * 3 + 1]; t = a.positive[bb * 3 + 2];
+    if ((uint64_t)h >= (uint64_t)a.nentity || (uint64_t)t >= (uint64_t)a.nentity || (uint64_t)r >= (uint64_t)a.nrelation) {
       if (tid == 0 && a.err) *a.err = 1;
-      fid = 0; rid = 0;
+      if ((uint64_t)h >= (uint64_t)a.nentity) h = 0;
+      if ((uint64_t)t >= (uint64_t)a.nentity) t = 0;
+      if ((uint64_t)r >= (uint64_t)a.nrelation) r = 0;
     }
-    const float *F = a.E + fid * a.De;
-    const float *Rr = a.R + rid * a.Dr;
-    const int64_t *cand = a.cand + b * a.cand_stride;
+  };
+  auto stage_issue = [&](int buf, int64_t h, int64_t r, int64_t t) {     // thread 0: rows of a triple -> stage[buf]
+    float *dst = stage + (size_t)buf * STG;
+    const uint32_t eb = (uint32_t)a.De * 4u, rb = (uint32_t)a.Dr * 4u;
+    mbar_expect_tx(sbars + buf, 2 * eb + rb);
+    bulk_g2s(dst, a.E + h * a.De, eb, sbars + buf);
+    bulk_g2s(dst + a.De, a.E + t * a.De, eb, sbars + buf);
+    bulk_g2s(dst + 2 * a.De, a.R + r * a.Dr, rb, sbars + buf);
+  };
+  int64_t hid = 0, rid = 0, tidx = 0, nhid = 0, nrid = 0, ntid = 0;
+  if ((int)blockIdx.x < a.row_count) {
+    load_triple(a.row_begin + blockIdx.x, hid, rid, tidx);
+    if (tid == 0) stage_issue(0, hid, rid, tidx);
+  }
+  int rowi = 0;                                            // rows done by this CTA: stage buffer = rowi & 1
+  for (int rl = blockIdx.x; rl < a.row_count; rl += gridDim.x, ++rowi) {
+    const int64_t b = a.row_begin + rl;
     const bool has_next = rl + (int)gridDim.x < a.row_count;
+    if (rowi) { hid = nhid; rid = nrid; tidx = ntid; }
+    const int64_t fid = HEAD ? tidx : hid;
+    const int cb = rowi & 1;
+    if (has_next) {                                        // next row's triple: its rows travel under this row's loop
+      load_triple(b + gridDim.x, nhid, nrid, ntid);        // (buffer 1 - cb was last read before the previous row's final
+      if (tid == 0) stage_issue(cb ^ 1, nhid, nrid, ntid); //  barrier)
+    }
+    const float *Hs = stage + (size_t)cb * STG, *Ts = Hs + a.De, *Rr = Hs + 2 * a.De;
+    const float *F = HEAD ? Ts : Hs;
+    const int64_t *cand = a.cand + b * a.cand_stride;
     long long tph = a.phase_cycles ? clock64() : 0;    // debug: cycles per phase of this row (thread 0)
 
     // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
@@ -201,6 +236,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     }
 
     // ---- phase 0: query vector (kept in shared memory and published for the entity-major pass) ----------
+    mbar_wait(sbars + cb, (uint32_t)(rowi >> 1) & 1u);    // this row's head / tail / relation rows are in shared memory
     float *qout = ws.Qtab + (size_t)rl * a.De;
     for (int k = tid; k < a.d; k += blockDim.x) {
       if constexpr (MODEL == KGE_ROTATE) {                 // model.py:209-212, once per row
@@ -534,17 +570,15 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     if (a.pos_row_loss) {
       constexpr int OPS = op_of(MODEL, false);
       __syncthreads();                                      // dq / q of the negatives are no longer needed
-      int64_t ph = hid, pt = tidx;
-      if ((uint64_t)ph >= (uint64_t)a.nentity) ph = 0;
-      if ((uint64_t)pt >= (uint64_t)a.nentity) pt = 0;
+      const int64_t ph = hid, pt = tidx;
       if (ws.Dvec && tid < 3) {                             // direct entries of this row: (fixed, head, tail)
         const int64_t target = tid == 0 ? fid : (tid == 1 ? ph : pt);
         store_all(a.mir, ws.dids + 3 * rl + tid, (int)target);
         atomicAdd(ws.cnt + target, 1);
       }
-      const float *Hrow = a.E + ph * a.De, *Trow = a.E + pt * a.De;
-      // (tail-batch: q = fold(h, r) is the q of the negatives, still in shared memory, unless an id was out of range)
-      if (HEAD || ph != fid) {
+      const float *Hrow = Hs, *Trow = Ts;
+      // (tail-batch: q = fold(h, r) is the q of the negatives, still in shared memory)
+      if (HEAD) {
         for (int k = tid; k < a.d; k += blockDim.x) {
           if constexpr (MODEL == KGE_ROTATE) build_q_rot<false>(Hrow, rot[k], rot[d4 + k], k, a.d, q, DP);
           else build_q<MODEL, false>(Hrow, Rr, k, a.d, a.scale, q, DP);
