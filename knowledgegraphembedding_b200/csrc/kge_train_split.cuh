@@ -62,11 +62,12 @@ __device__ __forceinline__ void unit_group(const float (&q0)[4], const float (&q
     for (int j = 0; j < 4; j += 2) {
       const f2 av = sub2(pack2(q0[j], q0[j + 1]), pack2(x0[j], x0[j + 1]));
       const f2 bv = sub2(pack2(q1[j], q1[j + 1]), pack2(x1[j], x1[j + 1]));
-      const f2 m2 = fma2(bv, bv, mul2(av, av));
+      // |q - x|^2 + FLT_MIN: the guard of the reciprocal square root rides in the FMA chain (it is absorbed by rounding
+      // for every |q - x| > 1e-15); at q == x the differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
+      const f2 m2 = fma2(bv, bv, fma2(av, av, pack2(kFltMin, kFltMin)));
       float m2a, m2b;
       unpack2(m2, m2a, m2b);
-      // 1/|q - x|; at q == x the differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
-      const f2 inv = pack2(rsqrt_fast(fmaxf(m2a, kFltMin)), rsqrt_fast(fmaxf(m2b, kFltMin)));
+      const f2 inv = pack2(rsqrt_fast(m2a), rsqrt_fast(m2b));
       u0[j >> 1] = mul2(av, inv);
       u1[j >> 1] = mul2(bv, inv);
       part2 = fma2(m2, inv, part2);                        // += |q - x|
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
           // with no pipe above 40 %), (C) u = (a, b) / |.| and the distance |.| = a u_a + b u_b.
           constexpr int SG = NCL >= 4 ? 4 : NCL;            // chunks per stage group (16 complex dimensions per lane)
           f2 pacc[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};   // 4 short FFMA2 chains
+          const f2 tiny2 = pack2(kFltMin, kFltMin);        // guard of the reciprocal square root, folded into the FMA chain
 #pragma unroll
           for (int g0 = 0; g0 < NCL; g0 += SG) {
             f2 m2[SG][2];
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
                 const f2 bv = sub2(pack2(qr[g0 + i][1][2 * jj], qr[g0 + i][1][2 * jj + 1]), pack2(x1[2 * jj], x1[2 * jj + 1]));
                 u[g0 + i][0][jj] = av;
                 u[g0 + i][1][jj] = bv;
-                m2[i][jj] = fma2(bv, bv, mul2(av, av));
+                m2[i][jj] = fma2(bv, bv, fma2(av, av, tiny2));
               }
             }
 #pragma unroll
@@ -319,8 +321,9 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
               for (int jj = 0; jj < 2; ++jj) {
                 float ma, mb;
                 unpack2(m2[i][jj], ma, mb);
-                // 1/|q - x|; at q == x the differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
-                m2[i][jj] = pack2(rsqrt_fast(fmaxf(ma, kFltMin)), rsqrt_fast(fmaxf(mb, kFltMin)));
+                // 1/|q - x| (of |q - x|^2 + FLT_MIN, absorbed by rounding for every |q - x| > 1e-15); at q == x the
+                // differences are exactly 0, so u = 0 * finite = 0 (torch's norm subgradient)
+                m2[i][jj] = pack2(rsqrt_fast(ma), rsqrt_fast(mb));
               }
 #pragma unroll
             for (int i = 0; i < SG; ++i)
@@ -823,15 +826,15 @@ __global__ void __launch_bounds__(entity_warps(S, FUSED) * 32, 1) entity_kernel(
             if constexpr (OP == OP_CDIST) {
               // RotatE: d|q - x| / dx on packed pairs (FADD2 / FMUL2 / FFMA2): acc -= (q - x) * go / |q - x|,
               // zero at q == x like the scalar form
-              const f2 ngo = pack2(-go, -go);
+              const f2 ngo = pack2(-go, -go), tiny2 = pack2(kFltMin, kFltMin);
 #pragma unroll
               for (int j = 0; j < V; j += 2) {
                 const f2 av = sub2(pack2(q0[j], q0[j + 1]), pack2(x0[c][j], x0[c][j + 1]));
                 const f2 bv = sub2(pack2(q1[j], q1[j + 1]), pack2(x1[c][j], x1[c][j + 1]));
-                const f2 m2 = fma2(bv, bv, mul2(av, av));
+                const f2 m2 = fma2(bv, bv, fma2(av, av, tiny2));       // (+ FLT_MIN: the rsqrt guard, see unit_group)
                 float m2a, m2b;
                 unpack2(m2, m2a, m2b);
-                const f2 inv = mul2(pack2(rsqrt_fast(fmaxf(m2a, kFltMin)), rsqrt_fast(fmaxf(m2b, kFltMin))), ngo);
+                const f2 inv = mul2(pack2(rsqrt_fast(m2a), rsqrt_fast(m2b)), ngo);
                 acc[c][0][j >> 1] = fma2(av, inv, acc[c][0][j >> 1]);
                 acc[c][1][j >> 1] = fma2(bv, inv, acc[c][1][j >> 1]);
               }
