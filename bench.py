@@ -153,14 +153,18 @@ def ncu_traffic(wl):
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "prof_train_r*.raw.csv")), reverse=True):
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
-        total = 0.0
+        per_kernel = {}                                 # the capture may hold several launches (steps) of each kernel
         for r in rows[2:]:
-            if "row_kernel_split" not in r[0] and "entity_kernel" not in r[0]:
+            kind = "row" if "row_kernel_split" in r[0] else ("entity" if "entity_kernel" in r[0] else None)
+            if kind is None:
                 continue
+            t = 0.0
             for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 i = hdr.index(name)
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-                total += float(r[i]) * scale
+                t += float(r[i]) * scale
+            per_kernel.setdefault(kind, []).append(t)
+        total = sum(sum(v) / len(v) for v in per_kernel.values())
         if total:
             return total, "not measured in this run: " + os.path.relpath(path, ROOT) + " (ncu --set full of this command)"
     return None, None

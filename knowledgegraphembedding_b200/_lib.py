@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libkge_b200.so")
+LIB_PATH = os.environ.get("KGE_LIB") or os.path.join(HERE, "csrc", "libkge_b200.so")   # KGE_LIB: an A/B build (build.py)
 
 TRANSE, DISTMULT, COMPLEX, ROTATE, PROTATE = range(5)
 MODEL_IDS = {"TransE": TRANSE, "DistMult": DISTMULT, "ComplEx": COMPLEX, "RotatE": ROTATE, "pRotatE": PROTATE}

@@ -40,9 +40,16 @@ def _object_stale(src, obj):
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in [src] + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra_flags=()):
     """Compile every CUDA source (one nvcc process per file, in parallel) and link csrc/libkge_b200.so; returns the
-    path.  Objects are kept under csrc/build/ so that an edit recompiles only the files it touches."""
+    path.  Objects are kept under csrc/build/ so that an edit recompiles only the files it touches.
+    variant / extra_flags (A/B experiments): build csrc/libkge_b200_<variant>.so with extra nvcc flags from its own object
+    directory; KGE_LIB=<path> makes _lib.py load it."""
+    global LIB, OBJ_DIR
+    if variant:
+        LIB = os.path.join(CSRC, "libkge_b200_%s.so" % variant)
+        OBJ_DIR = os.path.join(CSRC, "build", variant)
+        force = True
     if not force and not is_stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
@@ -53,7 +60,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", suffix + ".o"))
         objs.append(obj)
         if force or _object_stale(src, obj):
-            jobs.append((src + suffix, [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) +
+            jobs.append((src + suffix, [nvcc] + NVCC_FLAGS + list(extra_flags) + extra + (["-Xptxas", "-v"] if verbose else []) +
                          ["-c", src, "-o", obj]))
 
     def run(job):
