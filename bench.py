@@ -505,7 +505,7 @@ class Bench:
                 "what": "KGEModel.filtered_ranks end to end, warm: host triples -> H2D -> filter lookup + count kernels -> "
                         "host ranks; the filter index of all_true_triples is cached from the cold call",
                 "cold": {"value": 2 * nq / cold_s, "seconds": cold_s,
-                         "what": "first call: builds the filter index from the python list of all true triples, uploads it"},
+                         "what": "first call: python list of all true triples -> int64 array on the host, H2D, filter index built on the device (counting sort)"},
                 "count_kernel_ms": kernel_ms, "count_kernel_queries_per_sec": 2 * nq / (kernel_ms * 1e-3) if kernel_ms else None,
                 "sharding": f"entities/{self.world}", "filter_triples": len(all_true)}, all_true, test
 

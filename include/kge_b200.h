@@ -253,6 +253,21 @@ int kge_eval_filter_bits_lookup(const int64_t *index_keys, const int64_t *index_
                                 int64_t nkeys, const int64_t *queries, int64_t Q, int mode, int64_t nentity,
                                 int64_t nrelation, uint32_t *filter_bits, void *stream);
 
+/* The index itself built on the device (dataloader.py:122-162 builds the python set of all true triples; the host-side
+ * FilterIndex sorts them with numpy): a direct-address CSR over the key space nentity*nrelation (< 2^31) by counting
+ * sort -- histogram of the keys, tiled scan, scatter.  triples [ntriples,3] int64 on the device; offsets
+ * [nentity*nrelation + 1] int32 and entities [ntriples] int32 are the result (run of key k = entities[offsets[k] ..
+ * offsets[k+1]), order inside a run unspecified); scratch: kge_eval_filter_index_scratch_bytes().  A triple with an id
+ * outside the tables sets *err_flag and is skipped.  kge_eval_filter_bits_lookup_dense is the lookup for this layout
+ * (one load pair per query instead of a binary search).                                                        */
+int64_t kge_eval_filter_index_scratch_bytes(int64_t nentity, int64_t nrelation);
+int kge_eval_filter_index_build(const int64_t *triples, int64_t ntriples, int mode, int64_t nentity, int64_t nrelation,
+                                int32_t *offsets, int32_t *entities, void *scratch, int64_t scratch_bytes,
+                                int32_t *err_flag, void *stream);
+int kge_eval_filter_bits_lookup_dense(const int32_t *index_offsets, const int32_t *index_entities,
+                                      const int64_t *queries, int64_t Q, int mode, int64_t nentity, int64_t nrelation,
+                                      uint32_t *filter_bits, void *stream);
+
 /* ---- negative sampling: TrainDataset.__getitem__ (dataloader.py:28-67) on the device ----
  * For row b (train triple triple_index[b]) draw N entity ids uniformly from the entities that are NOT in the
  * row's sorted true list true_entities[key_start[t] .. +key_len[t])  (the true heads of (r,t) for head-batch, the

@@ -95,6 +95,11 @@ PROTOTYPES = {
     "kge_sample_negatives": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, ctypes.c_uint64,
                                      ctypes.c_uint64, c_void_p, c_void_p]),
     "kge_eval_filter_bits": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "kge_eval_filter_index_scratch_bytes": (c_int64, [c_int64, c_int64]),
+    "kge_eval_filter_index_build": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                            c_int64, c_void_p, c_void_p]),
+    "kge_eval_filter_bits_lookup_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64,
+                                                  c_void_p, c_void_p]),
     "kge_peer_alloc": (c_int, [c_int, c_int64, POINTER(c_void_p)]),
     "kge_peer_free": (c_int, [c_void_p]),
     "kge_peer_export": (c_int, [c_void_p, c_void_p]),

@@ -407,6 +407,47 @@ __global__ void filter_lookup_kernel(const int64_t *__restrict__ keys, const int
   }
 }
 
+// ---- device-side build of the filter index (dataloader.py:122-162 keeps all true triples in a python set and probes it
+// once per entity per query): a direct-address CSR over the key space nentity x nrelation, by counting sort --
+// histogram of the keys, tiled exclusive scan (the train path's scan kernels), scatter.  offsets[key] .. offsets[key + 1]
+// then delimit the true heads of (r, t) / true tails of (h, r); no sorted key table, no binary search per query.
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int *__restrict__ cnt, int *__restrict__ cursor,
+                                                          int *__restrict__ tile_tot, int64_t n);      // kge_train.cu
+__global__ void __launch_bounds__(1024) scan_apply_kernel(int *__restrict__ cnt, int *__restrict__ cursor,
+                                                          const int *__restrict__ tile_tot, int64_t n);
+
+template <bool PLACE>
+__global__ void filter_index_kernel(const int64_t *__restrict__ tri, int64_t n, int head_batch, int64_t nentity,
+                                    int64_t nrelation, int *__restrict__ cnt_or_cursor, int32_t *__restrict__ entities,
+                                    int32_t *err) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t h = tri[3 * i], r = tri[3 * i + 1], t = tri[3 * i + 2];
+    if ((uint64_t)h >= (uint64_t)nentity || (uint64_t)t >= (uint64_t)nentity || (uint64_t)r >= (uint64_t)nrelation) {
+      if (err) *err = 1;                                   // (a triple outside the tables can never be a query's answer)
+      continue;
+    }
+    const int64_t key = head_batch ? r * nentity + t : h * nrelation + r;
+    const int pos = atomicAdd(cnt_or_cursor + key, 1);
+    if (PLACE) entities[pos] = (int32_t)(head_batch ? h : t);
+  }
+}
+
+__global__ void filter_lookup_dense_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ values,
+                                           const int64_t *__restrict__ queries, int64_t Q, int head_batch,
+                                           int64_t nentity, int64_t nrelation, int words, uint32_t *__restrict__ bits) {
+  for (int64_t qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    const int64_t h = queries[qi * 3], r = queries[qi * 3 + 1], t = queries[qi * 3 + 2];
+    const int64_t fixed = head_batch ? t : h;
+    if ((uint64_t)fixed >= (uint64_t)nentity || (uint64_t)r >= (uint64_t)nrelation) continue;   // flagged by the query kernels
+    const int64_t key = head_batch ? r * nentity + t : h * nrelation + r;
+    const int b = offsets[key], e = offsets[key + 1];
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int32_t j = values[i];
+      atomicOr(&bits[qi * words + (j >> 5)], 1u << (j & 31));
+    }
+  }
+}
+
 template <int OP>
 static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
   constexpr int H = op_is_complex(OP) ? 2 : 1;
@@ -633,6 +674,62 @@ extern "C" int kge_eval_filter_bits_lookup(const int64_t *index_keys, const int6
   const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
   filter_lookup_kernel<<<grid, 128, 0, st>>>(index_keys, index_offsets, index_entities, nkeys, queries, Q,
                                              mode == KGE_HEAD_BATCH, nentity, nrelation, words, filter_bits);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+static size_t align256e(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int64_t kge_eval_filter_index_scratch_bytes(int64_t nentity, int64_t nrelation) {
+  if (nentity <= 0 || nrelation <= 0) return 0;
+  const int64_t nkeys = nentity * nrelation;
+  return (int64_t)(align256e((size_t)nkeys * 4) + align256e((size_t)((nkeys + 1023) / 1024) * 4));
+}
+
+extern "C" int kge_eval_filter_index_build(const int64_t *triples, int64_t ntriples, int mode, int64_t nentity,
+                                           int64_t nrelation, int32_t *offsets, int32_t *entities, void *scratch,
+                                           int64_t scratch_bytes, int32_t *err_flag, void *stream) {
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "negative batch mode %d not supported", mode);
+  KGE_REQUIRE(nentity > 0 && nrelation > 0 && ntriples >= 0 && ntriples < (1ll << 31), "bad sizes");
+  const int64_t nkeys = nentity * nrelation;
+  KGE_REQUIRE(nkeys < (1ll << 31) - 1024, "key space of %lld entries is too large for the direct-address index",
+              (long long)nkeys);
+  KGE_REQUIRE(offsets && scratch && (entities || ntriples == 0) && (triples || ntriples == 0), "null pointer");
+  KGE_REQUIRE(scratch_bytes >= kge_eval_filter_index_scratch_bytes(nentity, nrelation), "scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int *cnt = offsets;
+  int *cursor = (int *)scratch;
+  int *tile_tot = (int *)((char *)scratch + align256e((size_t)nkeys * 4));
+  KGE_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(nkeys + 1) * 4, st));
+  int grid = (int)((ntriples + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  const int head = mode == KGE_HEAD_BATCH;
+  filter_index_kernel<false><<<grid, 256, 0, st>>>(triples, ntriples, head, nentity, nrelation, cnt, nullptr, err_flag);
+  KGE_CUDA_OK(cudaGetLastError());
+  const int tiles = (int)((nkeys + 1023) / 1024);
+  scan_tiles_kernel<<<tiles, 1024, 0, st>>>(cnt, cursor, tile_tot, nkeys);
+  KGE_CUDA_OK(cudaGetLastError());
+  scan_apply_kernel<<<tiles, 1024, 0, st>>>(cnt, cursor, tile_tot, nkeys);
+  KGE_CUDA_OK(cudaGetLastError());
+  filter_index_kernel<true><<<grid, 256, 0, st>>>(triples, ntriples, head, nentity, nrelation, cursor, entities, nullptr);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+extern "C" int kge_eval_filter_bits_lookup_dense(const int32_t *index_offsets, const int32_t *index_entities,
+                                                 const int64_t *queries, int64_t Q, int mode, int64_t nentity,
+                                                 int64_t nrelation, uint32_t *filter_bits, void *stream) {
+  KGE_REQUIRE(mode == KGE_HEAD_BATCH || mode == KGE_TAIL_BATCH, "negative batch mode %d not supported", mode);
+  KGE_REQUIRE(index_offsets && index_entities && filter_bits && Q >= 0 && nentity > 0 && nrelation > 0, "bad arguments");
+  KGE_REQUIRE(queries || Q == 0, "null pointer");
+  if (Q == 0) return KGE_OK;
+  const int words = (int)((nentity + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(filter_bits, 0, sizeof(uint32_t) * (size_t)Q * words, st));
+  const int grid = (int)(Q < 148 * 16 ? Q : 148 * 16);
+  filter_lookup_dense_kernel<<<grid, 128, 0, st>>>(index_offsets, index_entities, queries, Q, mode == KGE_HEAD_BATCH,
+                                                   nentity, nrelation, words, filter_bits);
   KGE_CUDA_OK(cudaGetLastError());
   return KGE_OK;
 }

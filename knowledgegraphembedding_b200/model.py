@@ -8,6 +8,7 @@ calling the scoring paths with parameters that are not on a B200 raises.
 """
 import collections
 import ctypes
+import itertools
 import logging
 import os
 
@@ -846,25 +847,58 @@ class KGEModel(nn.Module):
         return ws['out']
 
     # ------------------------------------------------------------------------------------------ evaluation
+    # largest key space (nentity * nrelation) for the device-built direct-address filter index: 2^27 keys = 0.5 GB of
+    # int32 offsets per mode; beyond it (or with KGE_FILTER_HOST_INDEX=1) the host-built sorted-key index is used
+    _DENSE_FILTER_KEYS = 1 << 27
+
     def _filter_index(self, all_true_triples, nentity, nrelation):
-        # the cache holds the list itself (an id() alone can be reused by a later temporary such as train+valid+test)
-        # and is keyed on identity + length; a list mutated in place to the same length must be passed as a new object
+        """Cache entry for one `all_true_triples` list.  It holds the list itself (an id() alone can be reused by a later
+        temporary such as train+valid+test) and is keyed on identity + length; a list mutated in place to the same length
+        must be passed as a new object."""
         key = (len(all_true_triples), nentity, nrelation)
         held = self._filter_cache
-        if held is None or held[0] is not all_true_triples or held[1] != key:
-            self._filter_cache = held = (all_true_triples, key, FilterIndex(all_true_triples, nentity, nrelation), {})
-        return held[2]
+        if held is None or held['list'] is not all_true_triples or held['key'] != key:
+            self._filter_cache = held = {'list': all_true_triples, 'key': key, 'host': None, 'triples': {}, 'tables': {}}
+        return held
 
-    def _filter_tables(self, index, mode, dev):
-        """The index of all true triples, resident on the device (uploaded once per list, mode and device)."""
-        held = self._filter_cache[3]
-        if (mode, dev) not in held:
-            keys, offsets, values = index.table(mode)
-            held[(mode, dev)] = (torch.from_numpy(np.ascontiguousarray(keys)).to(dev),
-                                 torch.from_numpy(np.ascontiguousarray(offsets)).to(dev),
-                                 torch.from_numpy(np.ascontiguousarray(values)).to(dev) if values.size else
-                                 torch.zeros(1, dtype=torch.int32, device=dev), int(keys.size))
-        return held[(mode, dev)]
+    def _filter_tables(self, held, mode, dev, st):
+        """The index of all true triples, resident on the device (once per list, mode and device):
+        ('dense', offsets int32 [nentity*nrelation+1], entities int32) built ON the device by counting sort
+        (kge_eval_filter_index_build), or ('sorted', keys, offsets, entities, nkeys) from the host-side FilterIndex."""
+        tab = held['tables'].get((mode, dev))
+        if tab is not None:
+            return tab
+        n, nentity, nrelation = held['key']
+        if nentity * nrelation <= self._DENSE_FILTER_KEYS and not os.environ.get('KGE_FILTER_HOST_INDEX'):
+            tri = held['triples'].get(dev)
+            if tri is None:
+                lst = held['list']
+                try:          # python list of 3-tuples -> int64 [n,3]: the one host pass over the list (0.09 s per 483 k)
+                    arr = np.fromiter(itertools.chain.from_iterable(lst), dtype=np.int64, count=3 * n)
+                except (TypeError, ValueError):
+                    arr = np.asarray(lst, dtype=np.int64).reshape(-1)
+                if arr.size != 3 * n or (n and (len(lst[0]) != 3 or len(lst[-1]) != 3)):
+                    raise ValueError('all_true_triples must be a list of (head, relation, tail)')
+                tri = held['triples'][dev] = torch.from_numpy(arr).to(dev)
+            lib = _lib.load()
+            nkeys = nentity * nrelation
+            offsets = torch.empty(nkeys + 1, dtype=torch.int32, device=dev)
+            entities = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            sbytes = int(lib.kge_eval_filter_index_scratch_bytes(nentity, nrelation))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            _lib.call("kge_eval_filter_index_build", _ptr(tri), n, _lib.MODE_IDS[mode], nentity, nrelation, _ptr(offsets),
+                      _ptr(entities), _ptr(scratch), sbytes, None, st)      # (scratch: stream-ordered reuse by the allocator)
+            tab = ('dense', offsets, entities)
+        else:
+            if held['host'] is None:
+                held['host'] = FilterIndex(held['list'], nentity, nrelation)
+            keys, offsets, values = held['host'].table(mode)
+            tab = ('sorted', torch.from_numpy(np.ascontiguousarray(keys)).to(dev),
+                   torch.from_numpy(np.ascontiguousarray(offsets)).to(dev),
+                   torch.from_numpy(np.ascontiguousarray(values)).to(dev) if values.size else
+                   torch.zeros(1, dtype=torch.int32, device=dev), int(keys.size))
+        held['tables'][(mode, dev)] = tab
+        return tab
 
     def filtered_ranks(self, test_triples, all_true_triples, mode, query_chunk=4096, return_scores=False, exact=False,
                        return_approx=False):
@@ -882,7 +916,9 @@ class KGEModel(nn.Module):
             queries_all = np.asarray(test_triples, dtype=np.int64).reshape(-1, 3)
             queries_dev = torch.from_numpy(queries_all).to(dev, non_blocking=True)      # one H2D for the whole list
             self._ws['queries_np'] = (test_triples, len(test_triples), queries_all, queries_dev)
-        f_keys, f_offsets, f_values, f_nkeys = self._filter_tables(index, mode, dev)
+        if mode not in ('head-batch', 'tail-batch'):
+            raise ValueError('negative batch mode %s not supported' % mode)       # dataloader.py:147
+        ftab = self._filter_tables(index, mode, dev, st)
         rank, world = _dist()
         ent_begin, ent_end = shard_bounds(nentity, rank, world, align=128)
         desc = self._descriptor()
@@ -923,8 +959,12 @@ class KGEModel(nn.Module):
             pos = self._buffer('pos_score', Q, torch.float32, dev)
             counts = counts_all[lo:lo + Q]
             # filter bitmap of the chunk, looked up on the device in the resident index (dataloader.py:134-154)
-            _lib.call("kge_eval_filter_bits_lookup", _ptr(f_keys), _ptr(f_offsets), _ptr(f_values), f_nkeys,
-                      _ptr(queries), Q, m, nentity, nrelation, _ptr(bits), st)
+            if ftab[0] == 'dense':
+                _lib.call("kge_eval_filter_bits_lookup_dense", _ptr(ftab[1]), _ptr(ftab[2]), _ptr(queries), Q, m, nentity,
+                          nrelation, _ptr(bits), st)
+            else:
+                _lib.call("kge_eval_filter_bits_lookup", _ptr(ftab[1]), _ptr(ftab[2]), _ptr(ftab[3]), ftab[4],
+                          _ptr(queries), Q, m, nentity, nrelation, _ptr(bits), st)
             _lib.call("kge_eval_query_vectors", ctypes.byref(desc), m, _ptr(queries), Q, _ptr(qvec), _ptr(err), st)
             _lib.call("kge_eval_positive_scores", ctypes.byref(desc), m, _ptr(qvec), _ptr(queries), Q, _ptr(phase),
                       _ptr(pos), st)

@@ -431,6 +431,28 @@ def test_device_filter_lookup_equals_host_csr_bitmap():
             assert torch.equal(got, want), (nentity, mode)
             if ntrue:
                 assert int((want != 0).sum()) > 0
+            # the index built ON the device (counting sort into a direct-address CSR) holds the same runs as the host's
+            # sorted-key index, and its lookup sets the same bits
+            lib = _lib.load()
+            tri = torch.tensor(all_true, dtype=torch.int64, device=dev).reshape(-1, 3)
+            d_off32 = torch.full((nentity * nrel + 1,), -7, dtype=torch.int32, device=dev)
+            d_ent32 = torch.zeros(max(len(all_true), 1), dtype=torch.int32, device=dev)
+            sbytes = int(lib.kge_eval_filter_index_scratch_bytes(nentity, nrel))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.call("kge_eval_filter_index_build", _ptr(tri) if len(all_true) else None, len(all_true),
+                      _lib.MODE_IDS[mode], nentity, nrel, _ptr(d_off32), _ptr(d_ent32), _ptr(scratch), sbytes, _ptr(flag),
+                      _stream(dev))
+            dense = torch.full((len(test) * words,), -1, dtype=torch.int32, device=dev)
+            _lib.call("kge_eval_filter_bits_lookup_dense", _ptr(d_off32), _ptr(d_ent32), _ptr(q), len(test),
+                      _lib.MODE_IDS[mode], nentity, nrel, _ptr(dense), _stream(dev))
+            assert torch.equal(dense, want), (nentity, mode, "device-built index")
+            assert int(flag.item()) == 0
+            off32, ent32 = d_off32.cpu().numpy(), d_ent32.cpu().numpy()
+            assert off32[0] == 0 and off32[-1] == len(all_true) and np.all(np.diff(off32) >= 0)
+            for k, lo, hi in zip(keys.tolist(), offsets[:-1].tolist(), offsets[1:].tolist()):
+                assert sorted(ent32[off32[k]:off32[k + 1]].tolist()) == sorted(values[lo:hi].tolist())
+            assert int(np.count_nonzero(np.diff(off32))) == keys.size       # no run outside the host index's keys
 
 
 # ------------------------------------------------------------------------------------------------ API behaviour

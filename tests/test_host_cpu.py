@@ -315,6 +315,18 @@ def test_shard_abi_argument_errors_without_a_gpu():
     assert rc == _lib.ERR_INVALID and b"channels 2 and 3" in lib.kge_last_error()
 
 
+def test_filter_index_build_argument_errors_without_a_gpu():
+    from knowledgegraphembedding_b200 import _lib
+    lib = _lib.load()
+    assert lib.kge_eval_filter_index_scratch_bytes(100, 7) >= 700 * 4 + 4
+    rc = lib.kge_eval_filter_index_build(None, 0, _lib.SINGLE, 100, 7, 16, 16, 16, 1 << 20, None, None)
+    assert rc == _lib.ERR_INVALID and b"negative batch mode 0 not supported" in lib.kge_last_error()
+    rc = lib.kge_eval_filter_index_build(None, 0, _lib.HEAD_BATCH, 1 << 20, 1 << 12, 16, 16, 16, 1 << 20, None, None)
+    assert rc == _lib.ERR_INVALID and b"too large for the direct-address index" in lib.kge_last_error()
+    rc = lib.kge_eval_filter_index_build(None, 0, _lib.HEAD_BATCH, 100, 7, 16, 16, 16, 8, None, None)
+    assert rc == _lib.ERR_INVALID and b"scratch too small" in lib.kge_last_error()
+
+
 def test_peer_abi_argument_errors_without_a_gpu():
     import ctypes
     from knowledgegraphembedding_b200 import _lib
