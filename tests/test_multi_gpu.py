@@ -33,6 +33,18 @@ def test_peer_exchange_and_sharded_eval_against_oracle(backend):
     run_worker(min(torch.cuda.device_count(), 8), backend, KGE_PEER_BACKEND=backend)
 
 
+def _gpu0_shareable():
+    """Two processes can hold contexts on GPU 0 only in the default compute mode."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        mode = pynvml.nvmlDeviceGetComputeMode(pynvml.nvmlDeviceGetHandleByIndex(0))
+        return mode == pynvml.NVML_COMPUTEMODE_DEFAULT
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and not _gpu0_shareable(), reason="GPU 0 is in an exclusive compute mode")
 def test_two_ranks_sharing_one_gpu_against_oracle():
     """The multi-GPU train paths (entity-sharded optimizer, dense peer exchange, all-reduce) and entity-sharded evaluation
     with TWO RANKS ON ONE GPU: runs on the 1-GPU test box too.  Peer memory is cudaIpc between two processes on the same
