@@ -78,14 +78,15 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(int *__restrict__ cnt,
 }
 
 __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
-                                     int N, int64_t nentity, const float *__restrict__ G, const int *__restrict__ dids,
-                                     int *__restrict__ cursor, int *__restrict__ perm, float *__restrict__ gsorted) {
+                                     int N, int64_t nentity, const int *__restrict__ ids32, const float *__restrict__ G,
+                                     const int *__restrict__ dids, int *__restrict__ cursor, int *__restrict__ perm,
+                                     float *__restrict__ gsorted) {
   const int64_t pairs = (int64_t)rows * N;
   const int64_t total = pairs + (dids ? 3 * (int64_t)rows : 0);
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     if (p < pairs) {
       const int rl = (int)(p / N), n = (int)(p % N);
-      int64_t id = cand[(row_begin + rl) * cand_stride + n];
+      int64_t id = ids32 ? ids32[p] : cand[(row_begin + rl) * cand_stride + n];     // (ids32: clamped by the row kernel)
       if ((uint64_t)id >= (uint64_t)nentity) id = 0;
       const int pos = atomicAdd(cursor + id, 1);
       perm[pos] = rl;                                      // the entity pass only needs the q row and dL/ds
@@ -218,7 +219,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity) {
   return align256(rows * N * 4) + align256(rows * De * 4) + align256((nentity + 1) * 4 + nentity * 4 + 64) +
          align256(((nentity + 1023) / 1024) * 4) + 2 * align256(rows * (N + 3) * 4) + align256(rows * 3 * De * 4) +
-         align256(rows * 3 * 4);
+         align256(rows * 3 * 4) + align256(rows * N * 4);
 }
 
 SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int64_t nentity) {
@@ -234,7 +235,8 @@ SplitWs carve_split_ws(void *workspace, int64_t rows, int64_t N, int64_t De, int
   ws.perm = (int *)wp;     wp += align256((size_t)rows * (N + 3) * 4);
   ws.gsorted = (float *)wp; wp += align256((size_t)rows * (N + 3) * 4);
   ws.Dvec = (float *)wp;   wp += align256((size_t)rows * 3 * De * 4);
-  ws.dids = (int *)wp;
+  ws.dids = (int *)wp;     wp += align256((size_t)rows * 3 * 4);
+  ws.ids32 = (int *)wp;
   return ws;
 }
 

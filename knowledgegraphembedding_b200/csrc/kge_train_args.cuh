@@ -102,6 +102,8 @@ struct SplitWs {             // carved from the caller's workspace
   float *Dvec;               // [rows * 3, De] direct gradient rows (fixed entity, positive head, positive tail), or NULL:
                              //             those rows are added to gE with atomics instead
   int *dids;                 // [rows * 3]  target entity of every direct row
+  int *ids32;                // [rows, N]   the row kernel's clamped int32 copy of the candidate ids (what the counting sort
+                             //             reads: the caller's int64 ids may sit in pinned host memory), or NULL
 };
 
 size_t split_workspace_bytes(int64_t rows, int64_t N, int64_t De, int64_t nentity);

@@ -188,7 +188,8 @@ static int launch_rows_v(const RowArgs &a, bool vec4, int threads, size_t smem, 
           int g2 = (int)((pairs + 255) / 256);
           if (g2 > 148 * 16) g2 = 148 * 16;
           scatter_pairs_kernel<<<g2, 256, 0, st>>>(a.cand, a.cand_stride, a.row_begin, a.row_count, a.N, a.nentity,
-                                                   ws.G, ws.Dvec ? ws.dids : nullptr, ws.cursor, ws.perm, ws.gsorted);
+                                                   ws.ids32, ws.G, ws.Dvec ? ws.dids : nullptr, ws.cursor, ws.perm,
+                                                   ws.gsorted);
           KGE_CUDA_OK(cudaGetLastError());
         }
         if (a.defer_entity) {

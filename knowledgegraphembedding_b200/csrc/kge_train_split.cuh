@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
   int64_t ids = 0, ids_nxt = 0, ids_next_row = 0;
   bool next_row_ready = false;
   int ids_base = -32;
+  int cand_rl = 0;
   // (head, relation, tail) of a row, clamped like every gather (the error flag cancels the update)
   auto load_triple = [&](int64_t bb, int64_t &h, int64_t &r, int64_t &t) {
     h = a.positive[bb * 3 + 0]; r = a.positive[bb * 3 + 1]; t = a.positive[bb * 3 + 2];
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     const float *Hs = stage + (size_t)cb * STG, *Ts = Hs + a.De, *Rr = Hs + 2 * a.De;
     const float *F = HEAD ? Ts : Hs;
     const int64_t *cand = a.cand + b * a.cand_stride;
+    cand_rl = rl;                                          // row whose candidate list issue() walks
     long long tph = a.phase_cycles ? clock64() : 0;    // debug: cycles per phase of this row (thread 0)
 
     // candidate ids of this warp (n = warp + j * nwarps), fetched 32 at a time with one load per lane and handed out
@@ -213,13 +215,20 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
           ids = ids_nxt;
         }
         ids_base = j;
+        // the window becomes current: clamp its ids once (like every gather) and keep an int32 copy on the device --
+        // the counting sort reads that instead of the caller's int64 array, which may live in pinned HOST memory
+        // (zero-copy batches: this kernel's prefetched window loads are then the only PCIe reads of the ids)
+        const int nw = warp + (j + lane) * nwarps;
+        if (nw < a.N) {
+          if ((uint64_t)ids >= (uint64_t)a.nentity) { if (a.err) *a.err = 1; ids = 0; }
+          if (ws.ids32 && hw == 0) ws.ids32[(size_t)cand_rl * a.N + nw] = (int)ids;
+        }
       }
       if (j == ids_base + 8) {                             // next window of this row, 24 candidates ahead of its use
         const int n = warp + (ids_base + 32 + lane) * nwarps;
         ids_nxt = n < a.N ? cand[n] : 0;
       }
-      int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
-      if ((uint64_t)id >= (uint64_t)a.nentity) { if (lane == 0 && a.err) *a.err = 1; id = 0; }
+      const int64_t id = __shfl_sync(0xffffffffu, ids, j - ids_base);
       if (lane == 0 && hw == 0) {
         atomicAdd(ws.cnt + id, 1);                        // histogram for the entity-major pass
         uint64_t *bar = gbars + s;
@@ -463,6 +472,7 @@ __global__ void __launch_bounds__(split_warps(op_is_complex(op_of(MODEL, HEAD)),
     const int ps = (cons + D - 1) % D;
     if (has_next) {
       cand = a.cand + (b + gridDim.x) * a.cand_stride;
+      cand_rl = rl + gridDim.x;
       ids_base = -32;
       next_row_ready = true;
       for (int k = 0; k + 1 < D; ++k)
@@ -645,8 +655,9 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const int *__restrict_
 __global__ void __launch_bounds__(1024) scan_apply_kernel(int *__restrict__ cnt, int *__restrict__ cursor,
                                                           const int *__restrict__ tile_tot, int64_t n);
 __global__ void scatter_pairs_kernel(const int64_t *__restrict__ cand, int64_t cand_stride, int64_t row_begin, int rows,
-                                     int N, int64_t nentity, const float *__restrict__ G, const int *__restrict__ dids,
-                                     int *__restrict__ cursor, int *__restrict__ perm, float *__restrict__ gsorted);
+                                     int N, int64_t nentity, const int *__restrict__ ids32, const float *__restrict__ G,
+                                     const int *__restrict__ dids, int *__restrict__ cursor, int *__restrict__ perm,
+                                     float *__restrict__ gsorted);
 
 struct EntArgs {
   float *E;                  // read; written in place by the fused optimizer

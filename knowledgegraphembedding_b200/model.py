@@ -629,6 +629,17 @@ class KGEModel(nn.Module):
             return 1
         return min(n, 8)
 
+    def _train_plan(self, rows, N):
+        """(workspace bytes, kge_train_plan bits) for `rows` local positive rows x N candidates, cached per shape."""
+        desc = self._own_descriptor()
+        wkey = (rows, N, desc.entity_dim, desc.nentity, desc.entity, desc.relation)
+        held = self._ws.get('train_ws_bytes')
+        if held is None or held[0] != wkey:
+            lib = _lib.load()
+            held = self._ws['train_ws_bytes'] = (wkey, lib.kge_train_workspace_bytes(ctypes.byref(desc), rows, N),
+                                                 lib.kge_train_plan(ctypes.byref(desc), rows, N))
+        return held[1], held[2]
+
     def train_step_async(self, optimizer, batch, args):
         """Everything train_step does on the device, without the final read-back: returns the device buffer
         [positive_sample_loss, negative_sample_loss, loss, regularization, err_flag(int32 bits), ...]."""
@@ -645,8 +656,23 @@ class KGEModel(nn.Module):
         model._ws['staged_host_batch'] = (positive_sample, negative_sample, subsampling_weight)
         positive = _on_device(positive_sample, dev, torch.int64,
                               lambda n: model._buffer('stage_pos', n, torch.int64, dev)[:n], st)
-        negative = _on_device(negative_sample, dev, torch.int64,
-                              lambda n: model._buffer('stage_neg', n, torch.int64, dev)[:n], st)
+        fused_adam = KGEModel._fusable_adam(model, optimizer)
+        # Zero-copy negatives (KGE_ZERO_COPY=1, off by default): a pinned host batch is not copied when the single-read row
+        # kernel will run -- it reads each candidate id exactly once, through windows prefetched 24 candidates (and a whole
+        # row) ahead, and leaves the int32 copy that the counting sort needs on the device.  Measured on B200 (cfg 3):
+        # 0.745 vs 0.728 ms per end-to-end step with the staging copy -- the strided 8-byte window loads become 262 k
+        # separate PCIe reads, slower than one 2 MB DMA -- so the staging copy stays the default.
+        negative = None
+        if (os.environ.get('KGE_ZERO_COPY') == '1' and negative_sample.device.type == 'cpu'
+                and negative_sample.dtype == torch.int64 and negative_sample.dim() == 2
+                and negative_sample.numel() and negative_sample.is_contiguous() and negative_sample.is_pinned()):
+            plan0 = model._train_plan(negative_sample.shape[0], negative_sample.shape[1])[1]
+            if (plan0 & _lib.PLAN_SINGLE_READ) or ((plan0 & _lib.PLAN_ENTITY_ADAM) and fused_adam
+                                                   and not os.environ.get('KGE_KEEP_GRADS')):
+                negative = negative_sample           # host pointer == device pointer (unified addressing)
+        if negative is None:
+            negative = _on_device(negative_sample, dev, torch.int64,
+                                  lambda n: model._buffer('stage_neg', n, torch.int64, dev)[:n], st)
         rows, N = negative.shape
         uni = bool(getattr(args, 'uni_weight', False))
         weight = None if uni else _on_device(subsampling_weight, dev, torch.float32,
@@ -659,7 +685,6 @@ class KGEModel(nn.Module):
 
         err = model._err_flag()
         rank, world = _dist()
-        fused_adam = KGEModel._fusable_adam(model, optimizer)
         if world > 1 and fused_adam:
             # multi-GPU default: entity-sharded optimizer (owner computes; no dense gradient, no exchange kernel)
             held = model._shard_state(B, N, rank, world, dev)
@@ -669,13 +694,7 @@ class KGEModel(nn.Module):
         desc = model._own_descriptor()
         # which kernels run for this shape (cached per shape): the single-read path can also apply the entity table's
         # Adam update inside the backward -- on one device, with a stock Adam, unless the caller wants p.grad
-        wkey = (rows, N, desc.entity_dim, desc.nentity)
-        held = model._ws.get('train_ws_bytes')
-        if held is None or held[0] != wkey:
-            lib = _lib.load()
-            held = model._ws['train_ws_bytes'] = (wkey, lib.kge_train_workspace_bytes(ctypes.byref(desc), rows, N),
-                                                  lib.kge_train_plan(ctypes.byref(desc), rows, N))
-        wbytes, plan = held[1], held[2]
+        wbytes, plan = model._train_plan(rows, N)
         fuse_entity = bool(fused_adam and world == 1 and rows == B and (plan & _lib.PLAN_ENTITY_ADAM)
                            and not os.environ.get('KGE_KEEP_GRADS'))
         ws = model._grad_workspace(B, entity_grad=not fuse_entity)

@@ -638,6 +638,46 @@ def test_two_stage_rotate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d,
         assert m._ws['two_stage_last_ambiguous'] < 0.02 * nq * nentity + 64
 
 
+def test_pinned_negatives_are_read_in_place(monkeypatch):
+    """KGE_ZERO_COPY=1 with a pinned host batch: the candidate ids are not staged on the device, the single-read row
+    kernel reads them from host memory through its prefetched windows and leaves the int32 copy for the counting sort.
+    Same losses and tables as the (default) staged copy and as a pageable batch; includes an id window that ends in the
+    middle (N = 40)."""
+    torch.manual_seed(1)
+    nentity, nrel, d, gamma, B, N = 700, 5, 32, 9.0, 200, 40
+    st = O.init_tables("RotatE", nentity, nrel, d, gamma, True, False, seed=5)
+    args = ns(negative_adversarial_sampling=True)
+    batches = []
+    for i in range(3):
+        pos = torch.stack([torch.randint(nentity, (B,)), torch.randint(nrel, (B,)), torch.randint(nentity, (B,))], 1)
+        batches.append((pos, torch.randint(nentity, (B, N)), torch.rand(B) + 0.1, "tail-batch" if i % 2 == 0 else "head-batch"))
+    out = {}
+    for tag in ("pinned", "staged", "pageable"):
+        if tag == "pinned":
+            monkeypatch.setenv("KGE_ZERO_COPY", "1")
+        else:
+            monkeypatch.delenv("KGE_ZERO_COPY", raising=False)
+        m = make_model("RotatE", nentity, nrel, d, gamma, st)
+        opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+        feed = [(p.pin_memory(), n.pin_memory(), w.pin_memory(), md) if tag != "pageable" else (p, n, w, md)
+                for p, n, w, md in batches]
+        logs = [KGE().train_step(m, opt, iter([b]), args) for b in feed]
+        assert ('stage_neg' in m._ws) == (tag != "pinned"), tag          # zero-copy: no device staging buffer for the ids
+        out[tag] = (logs, m.entity_embedding.detach().cpu().numpy().copy())
+    for tag in ("staged", "pageable"):
+        for a, b in zip(out["pinned"][0], out[tag][0]):
+            assert all(abs(a[k] - b[k]) <= 1e-6 * abs(b[k]) for k in b), (tag, a, b)
+        assert outlier_fraction(out["pinned"][1], out[tag][1]) < 1e-4, tag
+    # an out-of-range id in a pinned batch is flagged like in a staged one
+    m = make_model("RotatE", nentity, nrel, d, gamma, st)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+    bad = batches[0][1].clone()
+    bad[7, 33] = nentity + 5
+    monkeypatch.setenv("KGE_ZERO_COPY", "1")
+    with pytest.raises(IndexError):
+        KGE().train_step(m, opt, iter([(batches[0][0].pin_memory(), bad.pin_memory(), batches[0][2].pin_memory(), "tail-batch")]), args)
+
+
 def test_train_step_pulls_exactly_one_batch_per_call():
     """The reference's iterator contract (model.py:261): one next(train_iterator) per train_step, at the call; a finite
     iterator of K batches yields exactly K steps and raises StopIteration at call K+1; two iterators used alternately
