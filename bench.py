@@ -458,6 +458,7 @@ class Bench:
         ts = None
         if self.rank == 0:
             from oracle import c_oracle as C
+            C.set_num_threads(host_cores())              # (torchrun exports OMP_NUM_THREADS=1)
             ts = C.TrainState(model, st, gamma, d)
         worst = 0.0
         for b in make_batches(nentity, nrel, B * self.world, N, steps, seed=11):
@@ -466,6 +467,7 @@ class Bench:
             if ts is not None:
                 ref = C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0, regularization=reg)
                 worst = max(worst, max(abs(log[k] - ref[k]) / abs(ref[k]) for k in ref))
+            self.barrier()       # the other ranks wait here on the host, not inside the next step's bounded GPU barrier
         self.barrier()
         if ts is None:
             return None

@@ -148,6 +148,7 @@ def check_full_size(dev):
     oracle = None
     if rank == 0:                                # one rank runs the CPU oracle (all host cores), the others wait
         from oracle import c_oracle as C
+        C.set_num_threads(len(os.sched_getaffinity(0)))       # (torchrun exports OMP_NUM_THREADS=1)
         ts = C.TrainState(model, st, gamma, d)
         oracle = ([C.train_step(ts, b, lr=lr, adversarial=True, alpha=1.0) for b in pool], ts)
     dist.barrier()
