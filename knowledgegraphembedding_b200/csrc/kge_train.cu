@@ -569,12 +569,15 @@ extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_k
   KGE_REQUIRE(row_count == sh.rows_of[sh.rank] && row_count <= B_total, "row_count does not match the shard description");
   KGE_REQUIRE(kge_train_plan(m, sh.rows_max, N) & KGE_PLAN_ENTITY_ADAM,
               "kge_train_plan does not offer the fused entity optimizer for this shape");
-  if (row_count == 0) return KGE_OK;
-  KGE_REQUIRE(positive && negative && row_loss && pos_row_loss && grad_relation, "null pointer");
   DeviceGuard device_guard;
   if ((rc = device_guard.enter(m->device))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   char *g = (char *)sh.block[sh.rank] + sh.gather_offset;
+  // this rank's histogram: the owners sum it whether or not the rank holds rows in this step (a short last batch can
+  // leave a rank empty after steps in which it counted pairs); every peer's scan of the last step is done
+  KGE_CUDA_OK(cudaMemsetAsync(g + L.hist, 0, (size_t)m->nentity * 4, st));
+  if (row_count == 0) return KGE_OK;
+  KGE_REQUIRE(positive && negative && row_loss && pos_row_loss && grad_relation, "null pointer");
   const int64_t R = sh.rows_max, De = m->entity_dim;
   // the id mirror is independent of the row kernel: with an auxiliary stream it runs next to it (joined at the end)
   cudaStream_t aux = aux_stream ? (cudaStream_t)aux_stream : st;
@@ -603,7 +606,6 @@ extern "C" int kge_train_rows_sharded(const kge_model_t *m, int mode, int loss_k
   ws.Dvec = (float *)(g + L.Dvec) + (size_t)sh.rank * 3 * R * De;
   ws.dids = (int *)(g + L.dids) + (size_t)sh.rank * 3 * R;
   ws.cnt = (int *)(g + L.hist);                            // this rank's histogram; the owners read their ranges of it
-  KGE_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, (size_t)m->nentity * 4, st));   // (every peer's scan of the last step is done)
   RowArgs a{};
   bool head;
   if ((rc = resolve_mode(mode, positive, negative, N, a, head))) return rc;

@@ -43,9 +43,12 @@ def build(model, nentity, nrel, d, gamma, st, dev):
 
 
 def batches(nentity, nrel, B, N, count, seed):
+    """B: rows per batch, or a list of per-step sizes (a short last batch can leave some ranks without rows)."""
     rng = np.random.RandomState(seed)
     out = []
+    sizes = list(B) if isinstance(B, (list, tuple)) else [B] * count
     for i in range(count):
+        B = sizes[i]
         pos = np.stack([rng.randint(nentity, size=B), rng.randint(nrel, size=B), rng.randint(nentity, size=B)], 1)
         neg = rng.randint(nentity, size=(B, N))
         w = np.sqrt(1.0 / rng.randint(8, 200, size=B)).astype(np.float32)
@@ -225,6 +228,7 @@ def main():
         check_case("pRotatE", 517, 3, 12, 6.0, 33, 8, 3, dev)
         check_case("ComplEx", 1001, 7, 32, 20.0, 64, 32, 3, dev, reg=1e-3)
         check_case("TransE", 200, 3, 8, 6.0, 1, 8, 2, dev)
+        check_case("RotatE", 301, 5, 16, 6.0, [48, 1, 33], 16, 3, dev)   # batch sizes change: a rank goes empty and back
         check_eval(dev)
         check_full_size(dev)                    # BASELINE configs[2] shape, 1024 rows per rank, against the C oracle
         dist.barrier()
@@ -246,6 +250,7 @@ def main():
     check_case("TransE", 1000, 11, 48, 9.0, 16, 16, 3, dev, adversarial=False, uni_weight=True)
     check_case("TransE", 200, 3, 8, 6.0, 1, 8, 2, dev)
     check_case("DistMult", 777, 5, 20, 10.0, 40, 24, 3, dev, reg=1e-3)
+    check_case("RotatE", 301, 5, 16, 6.0, [48, 1, 33], 16, 3, dev)     # batch sizes change: ranks go empty and back
     check_eval(dev)
     check_full_size(dev)
     dist.barrier()
