@@ -210,7 +210,8 @@ int kge_eval_count_ranks(const kge_model_t *m, int mode, const float *qvec, cons
                          const uint32_t *filter_bits, int64_t ent_begin, int64_t ent_end,
                          int32_t *counts, float *scores_out, void *stream);
 
-/* Two-stage variant of step 3 (RotatE): a fast tile pass (approximate sqrt, free association) counts every candidate
+/* Two-stage variant of step 3 (RotatE, pRotatE): a fast tile pass (RotatE: approximate sqrt, free association, packed
+ * FP32; pRotatE: reduction by pi + one sin.approx instead of the reproducible polynomial sine) counts every candidate
  * whose order against the positive is certain under a proven error band; the few undecidable (q, j) pairs are
  * re-scored with the exact op sequence.  Counts are identical to kge_eval_count_ranks.  Models without a fast
  * variant run the exact kernel.  amb_count[1] = 1 reports an overflow of amb_pairs (caller re-runs exact).       */

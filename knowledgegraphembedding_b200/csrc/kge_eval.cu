@@ -31,15 +31,34 @@ __device__ __forceinline__ float op_exact(float q0, float q1, float x0, float x1
 // Fast (non-canonical) element op of the two-stage RotatE evaluation: contraction allowed, one-instruction
 // approximate sqrt.  Per-term relative deviation from op_exact is below 2^-20 (sqrt.approx <= 2^-21, the a^2+b^2
 // association <= 2^-22, exact rounding <= 2^-24); see kFastBand.
+// pRotatE: |sin(t)| has period pi, so t is reduced by the nearest multiple of pi (two-constant Cody-Waite: the product
+// k * 3.140625 is exact for |k| < 2^15; each of the two FMAs rounds once, <= 1.2e-7 for |r| <= 2; the residual constant
+// is good to 2^-24 relative, i.e. <= |k| * 6e-11) to r in [-pi/2, pi/2], where sin.approx (one MUFU instruction) is
+// within 2^-20.9 = 5.1e-7 of sin (PTX ISA, quadrant 00): 8 instructions instead of the ~35 of sin_rep.  For |t| < 4e4
+// (|k| < 1.3e4) the reduction error is <= 2.4e-7 + 8e-7; beyond that the result is NaN, which the epilogue turns into
+// "undecidable" (exact re-score), never into a wrong count.
+__device__ __forceinline__ float abs_sin_fast(float t) {
+  const float k = rintf(t * 0.318309886183790672f);
+  float r = fmaf(-k, 3.140625f, t);
+  r = fmaf(-k, 9.67653589793e-4f, r);
+  float s;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(r));
+  return fabsf(t) < 4.0e4f ? fabsf(s) : __int_as_float(0x7fc00000);
+}
 template <int OP>
 __device__ __forceinline__ float op_fast(float q0, float q1, float x0, float x1) {
-  static_assert(OP == OP_CDIST, "only the complex-modulus op has a fast variant");
-  const float a = q0 - x0, b = q1 - x1;
-  return sqrt_approx(fmaf(a, a, b * b));
+  static_assert(OP == OP_CDIST || OP == OP_SUBSIN || OP == OP_ADDSIN, "ops with a fast variant");
+  if constexpr (OP == OP_CDIST) {
+    const float a = q0 - x0, b = q1 - x1;
+    return sqrt_approx(fmaf(a, a, b * b));
+  } else if constexpr (OP == OP_SUBSIN) return abs_sin_fast(q0 - x0);
+  else return abs_sin_fast(x0 + q0);
 }
 // |s_fast - s_canonical| <= kFastBand * (gamma - s_fast): 2^-20 per term + two blocked fp32 sums of the same
 // blocks (each within (32 + d/32) * 2^-24 <= 6e-6 of the exact sum for d <= 2048), rounded up.
 constexpr float kFastBand = 1.6e-5f;
+// pRotatE: per term |fast - canonical| <= 5.1e-7 + 1.04e-6 (above) + 1.8e-7 (sin_rep's own 1.5 ulp) < kFastSinTerm; sums as above
+constexpr float kFastSinTerm = 2.0e-6f, kFastSinSum = 1.2e-5f;
 
 template <int OP>
 __device__ __forceinline__ float finish_exact(float acc, float gamma, float modulus) {
@@ -312,9 +331,11 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) count_ranks_kernel(const Eval
       if (filtered) s = fadd(sp, -1.0f);                   // candidate replaced by the positive, bias -1
       else if (ej != pid) {
         if constexpr (FAST) {                              // s is only within eps of the canonical score
-          const float eps = kFastBand * (a.gamma - s) + 1e-12f;
+          float eps;
+          if constexpr (OP == OP_CDIST) eps = kFastBand * (a.gamma - s) + 1e-12f;
+          else eps = fabsf(modulus) * (float)a.d * kFastSinTerm + kFastSinSum * fabsf(a.gamma - s) + 1e-12f;
           if (s - eps > sp) ++c;
-          else if (s + eps >= sp) {                        // undecidable here: exact re-score later
+          else if (!(s + eps < sp)) {                      // undecidable here (or NaN): exact re-score later
             const int slot = atomicAdd(a.amb_count, 1);
             if (slot < a.amb_capacity) a.amb[slot] = make_int2((int)qi, (int)ej);
             else a.amb_count[1] = 1;
@@ -336,7 +357,8 @@ template <int OP>
 __global__ void rescore_pairs_kernel(const int2 *__restrict__ amb, const int *__restrict__ amb_count, int capacity,
                                      const float *__restrict__ qvec, const float *__restrict__ E, int d, int De,
                                      const float *__restrict__ pos_score, const int64_t *__restrict__ queries,
-                                     int pos_col, float gamma, int32_t *__restrict__ counts) {
+                                     int pos_col, float gamma, int32_t *__restrict__ counts,
+                                     const float *__restrict__ modulus = nullptr) {
   int n = amb_count[0];
   if (n > capacity) n = capacity;
   const int lane = threadIdx.x & 31;
@@ -344,7 +366,7 @@ __global__ void rescore_pairs_kernel(const int2 *__restrict__ amb, const int *__
   for (int i = wid; i < n; i += nw) {
     const int2 p = amb[i];
     const float s = finish_exact<OP>(canonical_pair_score<OP>(qvec + (int64_t)p.x * De, E + (int64_t)p.y * De, d),
-                                     gamma, 1.f);
+                                     gamma, modulus ? modulus[0] : 1.f);
     if (lane == 0) {
       const float sp = pos_score[p.x];
       const int64_t pid = queries[(int64_t)p.x * 3 + pos_col];
@@ -453,7 +475,7 @@ static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
   constexpr int H = op_is_complex(OP) ? 2 : 1;
   const size_t smem = sizeof(float) * 2 * (TQ + TJ) * H * ST;
   dim3 grid((unsigned)((a.ent_end - a.ent_begin + TJ - 1) / TJ), (unsigned)((a.Q + TQ - 1) / TQ));
-  if constexpr (OP == OP_CDIST) {
+  if constexpr (OP == OP_CDIST || OP == OP_SUBSIN || OP == OP_ADDSIN) {
     if (a.amb && aligned && !a.scores_out && a.d <= 2048) {          // two-stage: fast tile pass + exact re-score
       KGE_CUDA_OK(cudaMemsetAsync(a.amb_count, 0, 2 * sizeof(int), st));
       auto k = count_ranks_kernel<OP, true, true>;
@@ -461,7 +483,7 @@ static int launch_count(const EvalArgs &a, bool aligned, cudaStream_t st) {
       k<<<grid, EVAL_THREADS, smem, st>>>(a);
       KGE_CUDA_OK(cudaGetLastError());
       rescore_pairs_kernel<OP><<<148 * 4, 256, 0, st>>>(a.amb, a.amb_count, a.amb_capacity, a.qvec, a.X, a.d, a.De,
-                                                        a.pos_score, a.queries, a.pos_col, a.gamma, a.counts);
+                                                        a.pos_score, a.queries, a.pos_col, a.gamma, a.counts, a.modulus);
       KGE_CUDA_OK(cudaGetLastError());
       return KGE_OK;
     }

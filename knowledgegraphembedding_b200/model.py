@@ -951,7 +951,8 @@ class KGEModel(nn.Module):
         # the ambiguous band keeps the counts identical); KGE_EVAL_SIMT=1 forces the exact tile kernel
         exact = exact or return_scores or bool(os.environ.get("KGE_EVAL_SIMT"))
         gemm = bool(_lib.load().kge_eval_gemm_supported(ctypes.byref(desc))) and not exact
-        two_stage = self.model_name == 'RotatE' and not exact and self.entity_dim % 8 == 0
+        two_stage = not exact and ((self.model_name == 'RotatE' and self.entity_dim % 8 == 0) or
+                                   (self.model_name == 'pRotatE' and self.entity_dim % 4 == 0))
         nchunks = (queries_all.shape[0] + query_chunk - 1) // query_chunk
         # one int32 buffer [rank counts | per-chunk (ambiguous pairs, overflow flag)]: a single all-reduce and a single
         # read-back per call

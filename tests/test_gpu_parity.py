@@ -638,6 +638,36 @@ def test_two_stage_rotate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d,
         assert m._ws['two_stage_last_ambiguous'] < 0.02 * nq * nentity + 64
 
 
+@pytest.mark.parametrize("nentity,nrel,d,gamma,nq,scale", [
+    (14951, 1345, 1000, 24.0, 160, 1.0),      # FB15k shape at random init
+    (14951, 1345, 1000, 24.0, 96, 5.0),       # phases up to +-5 pi: the reduction by pi runs over several periods
+    (1031, 5, 36, 6.0, 200, 3.0),
+    (1031, 5, 36, 6.0, 64, 3.0e4),            # absurd phases (|t| up to 1e5): the fast pass answers NaN -> exact re-score
+])
+def test_two_stage_protate_eval_ranks_identical_to_exact_kernel(nentity, nrel, d, gamma, nq, scale, monkeypatch):
+    """pRotatE filtered ranking through the fast tile pass (reduction by pi + sin.approx) + exact re-score of the
+    undecidable band gives the same integer ranks as the exact kernel (bit-exact against the C oracle)."""
+    st = O.init_tables("pRotatE", nentity, nrel, d, gamma, False, False, seed=12)
+    st["entity_embedding"] = (st["entity_embedding"] * scale).astype(np.float32)
+    rng = np.random.RandomState(13)
+    all_true = sorted({(int(rng.randint(nentity)), int(rng.randint(nrel)), int(rng.randint(min(nentity, 400))))
+                       for _ in range(20000)})
+    test = [all_true[i] for i in rng.choice(len(all_true), nq, replace=False)]
+    m = make_model("pRotatE", nentity, nrel, d, gamma, st)
+    if scale > 1e3:
+        monkeypatch.setenv("KGE_EVAL_AMB_CAP", str(nq * nentity + 64))     # every pair may be undecidable here
+    for mode in ("head-batch", "tail-batch"):
+        monkeypatch.setenv("KGE_EVAL_SIMT", "1")
+        exact = m.filtered_ranks(test, all_true, mode)
+        monkeypatch.delenv("KGE_EVAL_SIMT")
+        m._ws.pop('two_stage_last_ambiguous', None)
+        fast = m.filtered_ranks(test, all_true, mode)
+        assert 'two_stage_last_ambiguous' in m._ws, "two-stage path was not taken"
+        np.testing.assert_array_equal(fast, exact)
+        if scale <= 1e3:
+            assert m._ws['two_stage_last_ambiguous'] < 0.02 * nq * nentity + 64
+
+
 def test_pinned_negatives_are_read_in_place(monkeypatch):
     """KGE_ZERO_COPY=1 with a pinned host batch: the candidate ids are not staged on the device, the single-read row
     kernel reads them from host memory through its prefetched windows and leaves the int32 copy for the counting sort.
