@@ -19,7 +19,7 @@ ap.add_argument("--workload", default="rotate_fb15k")
 ap.add_argument("--queries", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
-model, nentity, nrel, d, gamma, B, N, lr, de, dr = WORKLOADS[a.workload]
+model, nentity, nrel, d, gamma, B, N, lr, de, dr = WORKLOADS[a.workload][:10]
 m = KGEModel(model, nentity, nrel, d, gamma, double_entity_embedding=de, double_relation_embedding=dr).cuda()
 dev = m.entity_embedding.device
 rng = np.random.RandomState(0)
