@@ -45,19 +45,19 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
     path.  Objects are kept under csrc/build/ so that an edit recompiles only the files it touches.
     variant / extra_flags (A/B experiments): build csrc/libkge_b200_<variant>.so with extra nvcc flags from its own object
     directory; KGE_LIB=<path> makes _lib.py load it."""
-    global LIB, OBJ_DIR
+    lib_path, obj_dir = LIB, OBJ_DIR
     if variant:
-        LIB = os.path.join(CSRC, "libkge_b200_%s.so" % variant)
-        OBJ_DIR = os.path.join(CSRC, "build", variant)
+        lib_path = os.path.join(CSRC, "libkge_b200_%s.so" % variant)
+        obj_dir = os.path.join(CSRC, "build", variant)
         force = True
     if not force and not is_stale():
-        return LIB
+        return lib_path
     from concurrent.futures import ThreadPoolExecutor
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     jobs, objs = [], []
     for src, suffix, extra in UNITS:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", suffix + ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", suffix + ".o"))
         objs.append(obj)
         if force or _object_stale(src, obj):
             jobs.append((src + suffix, [nvcc] + NVCC_FLAGS + list(extra_flags) + extra + (["-Xptxas", "-v"] if verbose else []) +
@@ -72,11 +72,11 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
                 raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
             if verbose:
                 print(res.stderr)
-    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs,
                          cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
